@@ -1,0 +1,685 @@
+"""
+Host-side mirror of the reference's Python-level wrappers (fastremap/fastremap.pyx, "L2").
+
+Same names, argument names, defaults, return types and exceptions as the reference's public
+surface (fastremap/__init__.py:1-24, fastremap/fastremap.pyi), so the reference's own tests read
+unchanged against this module.  Every array loop is a CUDA kernel behind the C ABI of
+include/fastremap_b200.h; nothing here falls back to the CPU.
+
+Inputs may be numpy arrays (uploaded, results downloaded) or CUDA torch tensors (device-resident:
+results are CUDA tensors; with in_place=True a contiguous tensor is rewritten where it lies).
+
+Keyword-only extras that do not change any default: `max_labels` (table sizing hint).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as D
+from ._lib import FastremapB200Error
+from .dtypes import fit_dtype
+
+_u64 = np.uint64
+
+
+def _L():
+  return _lib.load()
+
+
+def _pow2_at_least(v: int) -> int:
+  v = max(int(v), 1)
+  return 1 << (v - 1).bit_length()
+
+
+def _to_py(bits: int, dtype) -> int:
+  """Raw 64-bit pattern at dtype width -> Python int in that dtype."""
+  dtype = np.dtype(dtype)
+  bits &= (1 << (8 * dtype.itemsize)) - 1
+  if np.issubdtype(dtype, np.signedinteger) and bits >> (8 * dtype.itemsize - 1):
+    bits -= 1 << (8 * dtype.itemsize)
+  return bits
+
+
+def _to_bits(value, dtype) -> int:
+  """Python int -> raw pattern at dtype width; OverflowError when not representable (the
+  reference gets that from Cython's integer conversion)."""
+  dtype = np.dtype(dtype)
+  info = np.iinfo(dtype)
+  value = int(value)
+  if value < info.min or value > info.max:
+    raise OverflowError("value too large to convert to %s" % dtype.name)
+  return value & ((1 << (8 * dtype.itemsize)) - 1)
+
+
+def _require_int(dtype, what):
+  if not D.is_int_dtype(dtype):
+    raise TypeError("fastremap_b200.%s supports integer dtypes (uint8-uint64, int8-int64); got %s. "
+                    "There is no CPU fallback for other dtypes." % (what, np.dtype(dtype)))
+
+
+# ------------------------------------------------------------------------------------- label table
+
+
+class LabelTable:
+  """Device label table: `cap` 16-byte slots + meta block (see include/fastremap_b200.h)."""
+
+  def __init__(self, dtype, min_entries: int, init_val: int):
+    dtype = np.dtype(dtype)
+    self.dtype = dtype
+    direct_cap = int(_L().frb_table_direct_cap(D.code(dtype)))
+    self.direct = 1 if direct_cap else 0
+    self.cap = direct_cap if direct_cap else max(_pow2_at_least(2 * max(min_entries, 1)), 4096)
+    self.init_val = init_val & _lib.EMPTY
+    self.slots = D.alloc(self.cap * 16)
+    self.meta = D.alloc_meta()
+    self.clear()
+
+  def clear(self):
+    _lib.check(_L().frb_table_init(D.ptr(self.slots), self.cap, D.ptr(self.meta), self.init_val, D.stream()),
+               "frb_table_init")
+
+  def grow(self, at_least_entries: int = 0):
+    if self.direct:
+      raise FastremapB200Error("direct label table cannot overflow")
+    self.cap = max(self.cap * 4, _pow2_at_least(4 * max(at_least_entries, 1)))
+    self.slots = D.alloc(self.cap * 16)
+    self.clear()
+
+  def read_meta(self) -> np.ndarray:
+    return D.read_u64(self.meta)
+
+  def overfull(self, meta) -> bool:
+    if self.direct:
+      return False
+    return bool(meta[_lib.META_OVERFLOW]) or int(meta[_lib.META_COUNT]) * 2 > self.cap
+
+
+def _default_entries(n: int, max_labels) -> int:
+  """Initial sizing of a hash table for an n-voxel volume when the label count is unknown:
+  n/128 labels (8.4 M at 1024^3; a 256 MiB table), at least 32 Ki; grown x4 on overflow."""
+  if max_labels is not None:
+    return int(max_labels) + 1
+  return int(min(max(n // 128, 1 << 15), 1 << 27))
+
+
+def _run_build(fn, table: LabelTable):
+  """Run a table-building launch; on overflow grow the table and repeat.  Returns meta."""
+  while True:
+    fn(table)
+    meta = table.read_meta()
+    if not table.overfull(meta):
+      return meta
+    table.grow(int(meta[_lib.META_COUNT]))
+
+
+def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positions=False) -> LabelTable:
+  """Build a label table from device arrays of L keys / values of `dtype` (K: frb_table_insert)."""
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  init = 0
+  table = LabelTable(dtype, L, init)
+
+  def build(t):
+    _lib.check(_L().frb_table_insert(D.ptr(keys_dev), w, None if positions else D.ptr(vals_dev), w, 0, L, op,
+                                     t.direct, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()), "frb_table_insert")
+
+  _run_build(build, table)
+  if positions:
+    _lib.check(_L().frb_table_resolve(D.ptr(vals_dev), w, D.ptr(table.slots), table.cap, D.ptr(table.meta), D.stream()),
+               "frb_table_resolve")
+  return table
+
+
+def _relabel(src_buf, n, dtype, table: LabelTable, policy, fill_bits=0, zero_fixed=False, dst_wide=None, dst_narrow=None,
+             narrow_width=0):
+  _lib.check(_L().frb_relabel(D.ptr(src_buf), D.ptr(dst_wide), D.ptr(dst_narrow), narrow_width, n, D.code(dtype),
+                              D.ptr(table.slots), table.cap, table.direct, D.ptr(table.meta), policy, fill_bits,
+                              1 if zero_fixed else 0, D.stream()), "frb_relabel")
+
+
+def _cast(src_buf, src_dtype, dst_dtype, n):
+  dst = D.alloc(n * np.dtype(dst_dtype).itemsize)
+  _lib.check(_L().frb_cast(D.ptr(src_buf), D.code(src_dtype), D.ptr(dst), D.code(dst_dtype), n, D.stream()), "frb_cast")
+  return dst
+
+
+# ------------------------------------------------------------------------------------- scans
+
+
+def _scan(vol_buf, n, dtype):
+  """(min, max, pixel_pairs, nonzero) of a flat device buffer in one fused pass."""
+  out = torch.zeros(4, dtype=torch.int64, device=D.dev())
+  _lib.check(_L().frb_minmax_pairs(D.ptr(vol_buf), n, D.code(dtype), D.ptr(out), D.stream()), "frb_minmax_pairs")
+  r = D.read_u64(out)
+  return _to_py(int(r[0]), dtype), _to_py(int(r[1]), dtype), int(r[2]), int(r[3])
+
+
+def minmax(arr):
+  """(min(arr), max(arr)) in a single pass; (None, None) if empty (reference: fastremap.pyx:70-93)."""
+  if not isinstance(arr, torch.Tensor):
+    arr = np.asarray(arr)
+    if arr.size == 0:
+      return None, None
+  elif arr.numel() == 0:
+    return None, None
+  v = D.ingest(arr, alias_ok=True)
+  if v.dtype == np.dtype("bool"):
+    v.dtype = np.dtype("u1")
+  _require_int(v.dtype, "minmax")
+  mn, mx, _, _ = _scan(v.buf, v.n, v.dtype)
+  return mn, mx
+
+
+def pixel_pairs(labels):
+  """Number of equal adjacent memory locations (reference: fastremap.pyx:829-853)."""
+  size = labels.numel() if isinstance(labels, torch.Tensor) else np.asarray(labels).size
+  if size == 0:
+    return 0
+  v = D.ingest(labels, alias_ok=True)
+  _require_int(v.dtype, "pixel_pairs")
+  return _scan(v.buf, v.n, v.dtype)[2]
+
+
+def refit(arr, value=None, increase_only=False, exotics=False):
+  """Resize to the smallest dtype of the same kind that fits `value` (reference: fastremap.pyx:259-301)."""
+  is_t = isinstance(arr, torch.Tensor)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else np.asarray(arr).dtype
+  if value is None:
+    min_value, max_value = minmax(arr)
+    if min_value is None or max_value is None:
+      min_value = 0
+      max_value = 0
+    value = max_value if abs(max_value) > abs(min_value) else min_value
+  dtype = np.dtype(fit_dtype(adtype, value, exotics=exotics))
+  if increase_only and dtype.itemsize <= adtype.itemsize:
+    return arr
+  elif dtype == adtype:
+    return arr
+  _require_int(adtype, "refit")
+  v = D.ingest(arr, alias_ok=True)
+  out = _cast(v.buf, v.dtype, dtype, v.n) if v.n else D.alloc(0)
+  return D.emit(out, dtype, v.shape, v.order, v.is_torch)
+
+
+# ------------------------------------------------------------------------------------- renumber
+
+
+class RenumberResult:
+  """Device-side result of the renumber kernels (all buffers are flat uint8 CUDA tensors)."""
+  __slots__ = ("out", "out_dtype", "keys", "ids", "n_labels", "table", "wide")
+
+
+def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
+                    flat_offset=0, total_n=None, merge=None) -> RenumberResult:
+  """
+  K1 -> K2 -> K3 on a flat device buffer.
+    write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
+    merge: optional callable(table) -> table run between K1 and K2 (multi-GPU key-table merge).
+  """
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  c = D.code(dtype)
+  L = _L()
+  table = LabelTable(dtype, _default_entries(n, max_labels), _lib.EMPTY)
+
+  def build(t):
+    _lib.check(L.frb_renumber_build(D.ptr(src_buf), n, c, flat_offset, 1 if preserve_zero else 0, D.ptr(t.slots), t.cap,
+                                    D.ptr(t.meta), D.stream()), "frb_renumber_build")
+
+  meta = _run_build(build, table)
+  if merge is not None:
+    table = merge(table)
+    meta = table.read_meta()
+  nl = int(meta[_lib.META_COUNT])
+
+  keys = D.alloc(nl * w)
+  ids = D.alloc(nl * w)
+  ws_bytes = int(L.frb_renumber_rank_ws_bytes(nl))
+  ws = D.alloc(ws_bytes)
+  index_bits = max(int((total_n if total_n is not None else n + flat_offset)).bit_length(), 1)
+  _lib.check(L.frb_renumber_rank(D.ptr(table.slots), table.cap, D.ptr(table.meta), c, int(np.int64(start)), index_bits,
+                                 D.ptr(keys), D.ptr(ids), nl, D.ptr(ws), ws_bytes, D.stream()), "frb_renumber_rank")
+
+  # fastremap.pyx:253-255: fit to the NEXT id (typed, so it wraps in the array dtype) unless |start| is larger
+  factor = _to_py(int(np.int64(start)) + nl, dtype)
+  if abs(start) > abs(factor):
+    factor = start
+  out_dtype = np.dtype(fit_dtype(dtype, factor))
+  wo = out_dtype.itemsize
+
+  res = RenumberResult()
+  res.keys, res.ids, res.n_labels, res.table, res.out_dtype = keys, ids, nl, table, out_dtype
+  narrow = D.alloc(n * wo) if wo < w else None
+  need_wide = write_wide or wo >= w
+  wide_dst = src_buf if need_wide else None
+  _relabel(src_buf, n, dtype, table, _lib.MISS_ERROR, 0, preserve_zero, wide_dst, narrow, wo if narrow is not None else 0)
+  res.wide = src_buf if need_wide else None
+  if wo < w:
+    res.out = narrow
+  elif wo == w:
+    res.out = src_buf
+  else:
+    res.out = _cast(src_buf, dtype, out_dtype, n)
+  return res
+
+
+def _mapping_to_dict(res: RenumberResult, dtype, preserve_zero) -> dict:
+  keys = D.download(res.keys, res.n_labels, dtype).tolist()
+  ids = D.download(res.ids, res.n_labels, dtype).tolist()
+  mapping = {0: 0} if preserve_zero else {}
+  mapping.update(zip(keys, ids))
+  return mapping
+
+
+def renumber(arr, start=1, preserve_zero=True, in_place=False, *, max_labels=None):
+  """
+  Renumber the labels of `arr` in order of first appearance in memory, starting from `start`
+  (0 stays 0 when preserve_zero), and refit to the narrowest dtype that holds the next id.
+  Returns (renumbered array, {old: new}).  Reference: fastremap.pyx:121-161 and :196-257.
+  """
+  is_t = isinstance(arr, torch.Tensor)
+  if not is_t:
+    arr = np.asarray(arr)
+  size = arr.numel() if is_t else arr.size
+  if size == 0:
+    return arr, {}
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  if adtype == np.dtype("bool") and preserve_zero:
+    return arr, {0: 0, 1: start}
+  elif adtype == np.dtype("bool"):
+    arr = arr.view(torch.uint8) if is_t else arr.view(np.uint8)
+    adtype = np.dtype("u1")
+  _require_int(adtype, "renumber")
+
+  if is_t:
+    v = D.ingest(arr, alias_ok=bool(in_place))
+    in_place_eff = v.aliases_input
+  else:
+    in_place_eff = bool(in_place) and (arr.flags["F_CONTIGUOUS"] or arr.flags["C_CONTIGUOUS"]) and arr.flags.writeable
+    v = D.ingest(arr)
+  res = renumber_device(v.buf, v.n, v.dtype, start=start, preserve_zero=preserve_zero, write_wide=in_place_eff,
+                        max_labels=max_labels)
+  mapping = _mapping_to_dict(res, v.dtype, preserve_zero)
+
+  if is_t:
+    if res.out_dtype == v.dtype:
+      out = arr if in_place_eff else D.emit(res.out, v.dtype, v.shape, v.order, True)
+    else:
+      out = D.emit(res.out, res.out_dtype, v.shape, v.order, True)
+    return out, mapping
+
+  if in_place_eff:
+    # the caller's buffer receives the ids at the old width (what the reference leaves behind)
+    D.download_into(res.wide, v.nbytes, D.flat_view(v.host))
+    if res.out_dtype == v.dtype:
+      return v.host, mapping
+  return D.emit(res.out, res.out_dtype, v.shape, v.order, False), mapping
+
+
+# ------------------------------------------------------------------------------------- remap family
+
+
+def _check_missing(table: LabelTable, out_buf, dtype, message: str):
+  meta = table.read_meta()
+  idx = int(meta[_lib.META_MISSING_INDEX])
+  if idx != _lib.EMPTY:
+    w = np.dtype(dtype).itemsize
+    label = D.download(out_buf[idx * w:(idx + 1) * w], 1, dtype).tolist()[0]  # a missing label is left as it was
+    raise KeyError(message.format(label))
+
+
+def _dict_to_arrays(table: dict, dtype):
+  """dict -> typed key / value arrays; OverflowError if a key or value does not fit the dtype."""
+  dtype = np.dtype(dtype)
+  n = len(table)
+  try:
+    keys = np.fromiter(table.keys(), dtype=dtype, count=n)
+    vals = np.fromiter(table.values(), dtype=dtype, count=n)
+  except (OverflowError, ValueError, TypeError):
+    keys = np.array([_to_bits(k, dtype) for k in table.keys()], dtype=np.uint64).astype("u%d" % dtype.itemsize).view(dtype)
+    vals = np.array([_to_bits(x, dtype) for x in table.values()], dtype=np.uint64).astype("u%d" % dtype.itemsize).view(dtype)
+  return keys, vals
+
+
+def remap(arr, table, preserve_missing_labels=False, in_place=False):
+  """
+  Remap the values of `arr` through the dict `table`.  A value missing from `table` is left alone
+  (preserve_missing_labels=True) or raises KeyError.  Reference: fastremap.pyx:654-703 and :705-769.
+  After a KeyError the contents of an in-place CUDA tensor are unspecified (the reference leaves a
+  partially rewritten prefix); a numpy input is left untouched.
+  """
+  if type(arr) == list:
+    arr = np.array(arr)
+  is_t = isinstance(arr, torch.Tensor)
+  if not is_t:
+    arr = np.asarray(arr)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  size = arr.numel() if is_t else arr.size
+
+  original_dtype = adtype
+  if len(table):
+    min_label, max_label = min(table.values()), max(table.values())
+    fit_value = min_label if abs(min_label) > abs(max_label) else max_label
+    arr = refit(arr, fit_value, increase_only=True)
+    adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  widened = adtype != original_dtype
+
+  if is_t:
+    writeable, contiguous = True, None  # decided by ingest
+  else:
+    writeable = arr.flags.writeable
+    contiguous = arr.flags.f_contiguous or arr.flags.c_contiguous
+
+  identity = all([k == v for k, v in table.items()]) and preserve_missing_labels
+  if identity or size == 0:
+    if is_t:
+      return arr if (in_place or widened) else arr.clone()
+    make_copy = ((not in_place) or (not writeable) or (not contiguous)) and not widened
+    return np.copy(arr, order="F" if arr.flags["F_CONTIGUOUS"] else "C") if make_copy else arr
+
+  _require_int(adtype, "remap")
+  keys, vals = _dict_to_arrays(table, adtype)  # OverflowError before any device work
+
+  if is_t:
+    v = D.ingest(arr, alias_ok=bool(in_place) or widened)
+    in_place_eff = v.aliases_input
+  else:
+    in_place_eff = (bool(in_place) and writeable and contiguous) or widened
+    v = D.ingest(arr)
+
+  if preserve_missing_labels and len(table) == 1:
+    before, after = int(keys.view("u%d" % adtype.itemsize)[0]), int(vals.view("u%d" % adtype.itemsize)[0])
+    _lib.check(_L().frb_replace_one(D.ptr(v.buf), D.ptr(v.buf), v.n, D.code(adtype), before, after, D.stream()),
+               "frb_replace_one")
+  else:
+    kd, vd = D.upload_array(keys), D.upload_array(vals)
+    t = table_from_arrays(kd, vd, len(keys), adtype, op=_lib.OP_SET)
+    policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
+    _relabel(v.buf, v.n, adtype, t, policy, dst_wide=v.buf)
+    if not preserve_missing_labels:
+      _check_missing(t, v.buf, adtype, "{} was not in the remap table.")
+
+  if is_t:
+    return arr if v.aliases_input else D.emit(v.buf, adtype, v.shape, v.order, True)
+  if in_place_eff:
+    D.download_into(v.buf, v.nbytes, D.flat_view(v.host))
+    return v.host
+  return D.emit(v.buf, adtype, v.shape, v.order, False)
+
+
+def mask(arr, labels, in_place=False, value=0):
+  """Set every voxel whose label is in `labels` to `value` (reference: fastremap.pyx:438-458)."""
+  labels = {lbl: value for lbl in labels}
+  return remap(arr, labels, preserve_missing_labels=True, in_place=in_place)
+
+
+def mask_except(arr, labels, in_place=False, value=0):
+  """Set every voxel whose label is NOT in `labels` to `value` (reference: fastremap.pyx:460-490, :492-527)."""
+  if not isinstance(labels, list):
+    raise TypeError("Argument 'labels' has incorrect type (expected list, got %s)" % type(labels).__name__)
+  is_t = isinstance(arr, torch.Tensor)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  if not D.is_int_dtype(adtype):
+    raise TypeError("No matching signature found")
+  lab = np.array([_to_bits(x, adtype) for x in labels], dtype=np.uint64).astype("u%d" % adtype.itemsize).view(adtype)
+  fill = _to_bits(value, adtype)
+
+  if is_t:
+    v = D.ingest(arr, alias_ok=bool(in_place))
+    in_place_eff = v.aliases_input
+  else:
+    contiguous = arr.flags.f_contiguous or arr.flags.c_contiguous
+    in_place_eff = bool(in_place) and arr.flags.writeable and contiguous
+    v = D.ingest(arr)
+  if v.n:
+    kd = D.upload_array(lab)
+    t = table_from_arrays(kd, kd, len(lab), adtype, op=_lib.OP_SET)
+    _relabel(v.buf, v.n, adtype, t, _lib.MISS_FILL, fill_bits=fill, dst_wide=v.buf)
+  if is_t:
+    return arr if v.aliases_input else D.emit(v.buf, adtype, v.shape, v.order, True)
+  if in_place_eff:
+    D.download_into(v.buf, v.nbytes, D.flat_view(v.host))
+    return v.host
+  return D.emit(v.buf, adtype, v.shape, v.order, False)
+
+
+def _check_1d_same_dtype(arrs, names):
+  dts = []
+  for a, nm in zip(arrs, names):
+    nd = a.dim() if isinstance(a, torch.Tensor) else np.asarray(a).ndim
+    if nd != 1:
+      raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d)" % nd)
+    dts.append(D.numpy_dtype(a.dtype) if isinstance(a, torch.Tensor) else np.asarray(a).dtype)
+  if any(d != dts[0] for d in dts):
+    raise ValueError("Buffer dtype mismatch, expected '%s' but got '%s'" % (dts[0], [d for d in dts if d != dts[0]][0]))
+  return dts[0]
+
+
+def _finish_1d(arr, v, in_place_eff):
+  if v.is_torch:
+    return arr if v.aliases_input else D.emit(v.buf, v.dtype, v.shape, v.order, True)
+  if in_place_eff:
+    D.download_into(v.buf, v.nbytes, D.flat_view(v.host))
+    return v.host
+  return D.emit(v.buf, v.dtype, v.shape, v.order, False)
+
+
+def remap_from_array(arr, vals, in_place=True):
+  """arr[i] = vals[arr[i]] where arr[i] < len(vals), else unchanged.  1-D, unsigned, same dtype
+  (reference: fastremap.pyx:771-791; an empty `vals` is a no-op here, it is an out-of-bounds read there)."""
+  dt = _check_1d_same_dtype([arr, vals], ["arr", "vals"])
+  if not np.issubdtype(dt, np.unsignedinteger):
+    raise TypeError("No matching signature found")
+  is_t = isinstance(arr, torch.Tensor)
+  if is_t:
+    v = D.ingest(arr, alias_ok=bool(in_place))
+    in_place_eff = v.aliases_input
+  else:
+    in_place_eff = bool(in_place) and arr.flags.writeable and arr.flags.c_contiguous
+    v = D.ingest(arr)
+  vv = D.ingest(vals, alias_ok=True)
+  if v.n and vv.n:
+    _lib.check(_L().frb_remap_from_array(D.ptr(v.buf), D.ptr(v.buf), v.n, D.ptr(vv.buf), vv.n, D.code(dt), D.stream()),
+               "frb_remap_from_array")
+  return _finish_1d(arr, v, in_place_eff)
+
+
+def remap_from_array_kv(arr, keys, vals, preserve_missing_labels=True, in_place=True):
+  """Remap through parallel key / value arrays (later duplicate keys win).  1-D, one integer dtype
+  (reference: fastremap.pyx:793-827)."""
+  dt = _check_1d_same_dtype([arr, keys, vals], ["arr", "keys", "vals"])
+  if not D.is_int_dtype(dt):
+    raise TypeError("No matching signature found")
+  nk = keys.numel() if isinstance(keys, torch.Tensor) else keys.size
+  nv = vals.numel() if isinstance(vals, torch.Tensor) else vals.size
+  assert nk == nv
+  is_t = isinstance(arr, torch.Tensor)
+  if is_t:
+    v = D.ingest(arr, alias_ok=bool(in_place))
+    in_place_eff = v.aliases_input
+  else:
+    in_place_eff = bool(in_place) and arr.flags.writeable and arr.flags.c_contiguous
+    v = D.ingest(arr)
+  if v.n:
+    kv, vv = D.ingest(keys, alias_ok=True), D.ingest(vals, alias_ok=True)
+    # positions + max => the last duplicate of a key supplies its value (fastremap.pyx:810-811)
+    t = table_from_arrays(kv.buf, vv.buf, nk, dt, op=_lib.OP_MAX, positions=True) if nk else LabelTable(dt, 1, 0)
+    policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
+    _relabel(v.buf, v.n, dt, t, policy, dst_wide=v.buf)
+    if not preserve_missing_labels:
+      _check_missing(t, v.buf, dt, "{} was not in the remap keys.")
+  return _finish_1d(arr, v, in_place_eff)
+
+
+# ------------------------------------------------------------------------------------- component_map
+
+
+def component_map_arrays(component_labels, parent_labels, max_labels=None):
+  """Device part of component_map: returns (keys, parents) as numpy arrays (unordered)."""
+  is_t = isinstance(component_labels, torch.Tensor)
+  if is_t:
+    vc = D.ingest(component_labels, alias_ok=True)
+    vp = D.ingest(parent_labels, alias_ok=True)
+    if vc.order != vp.order:
+      vp = D.ingest(parent_labels.contiguous() if vc.order == "C" else parent_labels, alias_ok=True)
+      if vc.order != vp.order:
+        raise FastremapB200Error("component_map: tensors must share one memory order")
+  else:
+    # both arrays take the memory order of the first (fastremap.pyx:95-102)
+    if component_labels.flags.c_contiguous:
+      component_labels, parent_labels = np.ascontiguousarray(component_labels), np.ascontiguousarray(parent_labels)
+    else:
+      component_labels, parent_labels = np.asfortranarray(component_labels), np.asfortranarray(parent_labels)
+    vc, vp = D.ingest(component_labels), D.ingest(parent_labels)
+  _require_int(vc.dtype, "component_map")
+  _require_int(vp.dtype, "component_map")
+  L = _L()
+  table = LabelTable(vc.dtype, _default_entries(vc.n, max_labels), 0)
+
+  def build(t):
+    _lib.check(L.frb_component_build(D.ptr(vc.buf), vc.n, D.code(vc.dtype), 0, D.ptr(t.slots), t.cap, D.ptr(t.meta),
+                                     D.stream()), "frb_component_build")
+
+  meta = _run_build(build, table)
+  nl = int(meta[_lib.META_COUNT])
+  keys = D.alloc(nl * vc.dtype.itemsize)
+  pars = D.alloc(nl * vp.dtype.itemsize)
+  _lib.check(L.frb_component_gather(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.code(vc.dtype), D.ptr(vp.buf),
+                                    D.code(vp.dtype), 0, D.ptr(keys), D.ptr(pars), nl, D.stream()), "frb_component_gather")
+  return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
+
+
+def component_map(component_labels, parent_labels):
+  """{component label: parent label}; on conflicts the last run start in memory order wins
+  (reference: fastremap.pyx:529-563 and :565-587)."""
+  if not isinstance(component_labels, torch.Tensor):
+    if not isinstance(component_labels, np.ndarray):
+      component_labels = np.array(component_labels)
+    if not isinstance(parent_labels, np.ndarray):
+      parent_labels = np.array(parent_labels)
+    size = component_labels.size
+  else:
+    size = component_labels.numel()
+  if size == 0:
+    return {}
+  if tuple(component_labels.shape) != tuple(parent_labels.shape):
+    raise ValueError("The size of the inputs must match: {} vs {}".format(
+      tuple(component_labels.shape), tuple(parent_labels.shape)))
+  keys, pars = component_map_arrays(component_labels, parent_labels)
+  return dict(zip(keys.tolist(), pars.tolist()))
+
+
+# ------------------------------------------------------------------------------------- unique
+
+# strategy thresholds (they change speed only, never results -- SURVEY App. A-11)
+DENSE_MAX_BINS = 1 << 27        # 1 GiB of uint64 bins
+HASH_MAX_FRACTION = 8           # hash strategy while distinct labels <= n / 8, else sort + RLE
+
+
+def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
+  """
+  Sorted distinct labels and their counts of a flat device buffer.
+  Returns (uniq_buf, counts_buf, n_unique); buffers are flat uint8 CUDA tensors (labels in `dtype`,
+  counts uint64).  strategy in {None, "dense", "hash", "sort"}.
+  """
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  c = D.code(dtype)
+  L = _L()
+  mn = mx = None
+  if strategy is None or strategy == "dense":
+    mn, mx, _, _ = _scan(buf, n, dtype)
+  if strategy is None:
+    strategy = "dense" if (mx - mn + 1) <= min(DENSE_MAX_BINS, max(4 * n, 1 << 16)) else "hash"
+  if strategy == "dense":
+    bins = mx - mn + 1
+    min_bits = _to_bits(mn, dtype)
+    counts = torch.zeros(bins, dtype=torch.int64, device=D.dev())
+    _lib.check(L.frb_hist_dense(D.ptr(buf), n, c, min_bits, D.ptr(counts), bins, D.stream()), "frb_hist_dense")
+    meta = D.alloc_meta()
+    ws_bytes = int(L.frb_compact_bins_ws_bytes(bins))
+    ws = D.alloc(ws_bytes)
+    _lib.check(L.frb_compact_bins_count(D.ptr(counts), bins, D.ptr(meta), D.ptr(ws), ws_bytes, D.stream()),
+               "frb_compact_bins_count")
+    nu = int(D.read_u64(meta)[_lib.META_LIST_COUNT])
+    uniq, cts = D.alloc(nu * w), D.alloc(nu * 8)
+    _lib.check(L.frb_compact_bins_emit(D.ptr(counts), bins, c, min_bits, D.ptr(uniq), D.ptr(cts), nu, D.ptr(ws), D.stream()),
+               "frb_compact_bins_emit")
+    return uniq, cts, nu
+  if strategy == "hash":
+    table = LabelTable(dtype, _default_entries(n, max_labels), 0)
+    limit = max(n // HASH_MAX_FRACTION, 1 << 16)
+
+    def build(t):
+      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()), "frb_hist_hash")
+
+    while True:
+      build(table)
+      meta = table.read_meta()
+      if not table.overfull(meta):
+        break
+      if table.cap // 2 > limit:  # label set too large to hash profitably
+        return unique_counts_device(buf, n, dtype, strategy="sort")
+      table.grow(int(meta[_lib.META_COUNT]))
+    nu = int(meta[_lib.META_COUNT])
+    k64, v64 = D.alloc(nu * 8), D.alloc(nu * 8)
+    _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), nu, D.stream()),
+               "frb_table_export")
+    ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
+    ws = D.alloc(ws_bytes)
+    uniq, cts = D.alloc(nu * w), D.alloc(nu * 8)
+    _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, c, D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes, D.stream()),
+               "frb_sort_table_pairs")
+    return uniq, cts, nu
+  if strategy == "sort":
+    meta = D.alloc_meta()
+    ws_bytes = int(L.frb_unique_sort_ws_bytes(n, c))
+    ws = D.alloc(ws_bytes)
+    _lib.check(L.frb_unique_sort_count(D.ptr(buf), n, c, D.ptr(meta), D.ptr(ws), ws_bytes, D.stream()), "frb_unique_sort_count")
+    nu = int(D.read_u64(meta)[_lib.META_LIST_COUNT])
+    uniq, cts = D.alloc(nu * w), D.alloc(nu * 8)
+    _lib.check(L.frb_unique_sort_emit(n, c, D.ptr(uniq), D.ptr(cts), nu, D.ptr(ws), D.stream()), "frb_unique_sort_emit")
+    return uniq, cts, nu
+  raise ValueError("unknown unique strategy %r" % (strategy,))
+
+
+def unique(labels, return_index=False, return_inverse=False, return_counts=False, axis=None, *, strategy=None):
+  """
+  Sorted unique labels, optionally with counts (reference: fastremap.pyx:855-965).
+  return_index / return_inverse / axis are on the "next" list of this build and raise
+  NotImplementedError rather than fall back to a CPU implementation.
+  """
+  is_t = isinstance(labels, torch.Tensor)
+  if not is_t and not isinstance(labels, np.ndarray):
+    labels = np.array(labels)
+  if return_index or return_inverse or axis is not None:
+    raise NotImplementedError("fastremap_b200.unique: return_index / return_inverse / axis are not built yet "
+                              "(no CPU fallback by design)")
+  adtype = D.numpy_dtype(labels.dtype) if is_t else labels.dtype
+  _require_int(adtype, "unique")
+  voxels = labels.numel() if is_t else labels.size
+
+  def wrap(u_np, c_np):
+    if is_t:
+      u = torch.from_numpy(u_np).to(labels.device) if u_np.size else torch.empty(0, dtype=labels.dtype, device=labels.device)
+      cc = torch.from_numpy(c_np).to(labels.device)
+      return (u, cc) if return_counts else u
+    return (u_np, c_np) if return_counts else u_np
+
+  if voxels == 0:
+    return wrap(np.array([], dtype=adtype), np.array([], dtype=np.uint32))
+  v = D.ingest(labels, alias_ok=True)
+  if voxels == 1:
+    return wrap(D.download(v.buf, 1, adtype), np.array([1], dtype=np.uint32))
+  uniq, cts, nu = unique_counts_device(v.buf, v.n, v.dtype, strategy=strategy)
+  if is_t:
+    u = uniq[: nu * adtype.itemsize].view(D.torch_dtype(adtype))
+    return (u, cts[: nu * 8].view(torch.uint64)) if return_counts else u
+  u_np = D.download(uniq, nu, adtype)
+  if return_counts:
+    return u_np, D.download(cts, nu, np.uint64)
+  return u_np

@@ -1,0 +1,236 @@
+// frb_component.cu -- K7 (component_map) and the synthetic-volume generator.
+//
+// K7 replaces _component_map (fastremap.pyx:565-587).  The reference stores
+// remap[cc[i]] = parent[i] at every run start of cc in memory order, so for each label the LAST
+// run start wins.  Here every run start offers (i + 1) to the label's slot with atomicMax; the
+// gather pass then reads parent[] at the winning index.  CTAs walk the volume from the back so
+// that after the first few tiles almost every offer is already dominated and ends at the
+// 16-byte slot read without an atomic.
+#include "frb_internal.cuh"
+
+namespace frb {
+
+static constexpr int ROWS = 4;
+static constexpr int TILE_VECS = 8 * ROWS * 32;
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
+                  u64* __restrict__ meta) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
+  unsigned int inserted = 0;
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail first (it holds the largest indices)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 key = ld_elem<W>(cc, i);
+      if (i == 0 || key != ld_elem<W>(cc, i - 1))
+        table_update<FRB_OP_MAX>(slots, mask, direct, meta, key, (u64)i + 1 + flat_offset, &inserted);
+    }
+  }
+  for (size_t tt = blockIdx.x; tt < tiles; tt += gridDim.x) {
+    u64 ovf = 0;
+    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
+    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) break;
+    const size_t t = tiles - 1 - tt;
+    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
+    uint4 v[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      const size_t vi = vbase + u * 32 + lane;
+      valid[u] = vi < nvec;
+      v[u] = valid[u] ? ld_stream16(cc + vi) : make_uint4(0, 0, 0, 0);
+    }
+    u64 carry = 0;
+    bool carry_ok = false;
+    if (vbase > 0 && vbase < nvec) {
+      carry = ld_elem<W>(cc, vbase * V - 1);
+      carry_ok = true;
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      const u64 last = vec_get<W>(v[u], V - 1);
+      u64 prev = __shfl_up_sync(FRB_FULL_MASK, last, 1);
+      const u64 row_last = __shfl_sync(FRB_FULL_MASK, last, 31);
+      bool has_prev = true;
+      if (lane == 0) { prev = carry; has_prev = carry_ok; }
+      carry = row_last;
+      carry_ok = true;
+      if (valid[u]) {
+        const size_t i0 = (vbase + u * 32 + lane) * V;
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          const u64 key = vec_get<W>(v[u], j);
+          const bool head = !has_prev || key != prev;
+          prev = key;
+          has_prev = true;
+          if (head) table_update<FRB_OP_MAX>(slots, mask, direct, meta, key, (u64)(i0 + j) + 1 + flat_offset, &inserted);
+        }
+      }
+    }
+  }
+  block_add_to(&meta[FRB_META_COUNT], inserted);
+}
+
+template <int WC>
+__global__ void __launch_bounds__(256)
+k_component_gather(const Slot* __restrict__ slots, u64 cap, u64* __restrict__ meta, const void* __restrict__ parent, int wp,
+                   u64 flat_offset, void* __restrict__ keys_out, void* __restrict__ parents_out, size_t capacity) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const size_t cap_r = (cap + 31) & ~(size_t)31;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap_r; s += stride) {
+    Slot cur;
+    cur.key = FRB_EMPTY;
+    cur.val = 0;
+    if (s < cap) cur = slots[s];
+    const bool occ = cur.key != FRB_EMPTY;
+    const unsigned int b = __ballot_sync(FRB_FULL_MASK, occ);
+    if (b == 0) continue;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(&meta[FRB_META_LIST_COUNT], (u64)__popc(b));
+    base = __shfl_sync(FRB_FULL_MASK, base, 0);
+    if (occ) {
+      const u64 pos = base + __popc(b & ((1u << lane) - 1u));
+      if (pos < capacity) {
+        st_elem<WC>(keys_out, pos, cur.key);
+        st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(cur.val - 1 - flat_offset)));
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {
+    const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
+    if (pos < capacity) {
+      st_elem<WC>(keys_out, pos, FRB_EMPTY);
+      st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(meta[FRB_META_SIDE_VAL] - 1 - flat_offset)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ synthetic volume
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
+  u64 z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ u64 mix(u64 seed, u64 idx) { return splitmix64(seed * 0xD1342543DE82EF95ull + idx); }
+
+struct SynthArgs {
+  u64 nz, ny, nx, z0, nz_total, gz, gy, gx, seed, zero_thresh, noise_thresh, idmask, cell_div;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256) k_synth(void* __restrict__ out, SynthArgs S) {
+  constexpr int V = 16 / W;
+  const u64 n = S.nz * S.ny * S.nx;
+  const u64 ncells = S.gz * S.gy * S.gx;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nvec = (n + V - 1) / V;
+  for (size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+    u64 r[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const u64 i = (u64)vi * V + j;
+      u64 label = 0;
+      if (i < n) {
+        const u64 x = i % S.nx;
+        const u64 yz = i / S.nx;
+        const u64 y = yz % S.ny;
+        const u64 zg = yz / S.ny + S.z0;
+        u64 c = (((zg * S.gz) / S.nz_total) * S.gy + (y * S.gy) / S.ny) * S.gx + (x * S.gx) / S.nx;
+        if (S.noise_thresh) {
+          const u64 hn = mix(S.seed + 2, (zg * S.ny + y) * S.nx + x);
+          if ((hn >> 40) < S.noise_thresh) c = (c + 1 + (hn & 7)) % ncells;
+        }
+        c /= S.cell_div;
+        label = mix(S.seed, c) & S.idmask;
+        if (label == 0) label = 1;
+        if ((mix(S.seed + 1, c) >> 40) < S.zero_thresh) label = 0;
+      }
+      r[j] = label;
+    }
+    const size_t i0 = vi * V;
+    if (i0 + V <= n) {
+      store_results<V, W>(out, i0, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; j++)
+        if (i0 + j < n) st_elem<W>(out, i0 + j, r[j]);
+    }
+  }
+}
+
+}  // namespace frb
+
+using namespace frb;
+
+extern "C" {
+
+int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
+                        uint64_t* meta, void* stream) {
+  if (!dtype_ok(cc_dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!cc || !aligned16(cc)))) { set_error("frb_component_build: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(cc_dtype);
+  const int direct = w <= 2 ? 1 : 0;
+  if (direct && cap != frb_table_direct_cap(cc_dtype)) { set_error("frb_component_build: direct table needs cap == 2^bits"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const uint4* p = (const uint4*)cc;
+  Slot* s = (Slot*)slots;
+  u64* m = (u64*)meta;
+  switch (w) {
+    case 1: k_component_build<1><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
+    case 2: k_component_build<2><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
+    case 4: k_component_build<4><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
+    default: k_component_build<8><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
+  }
+  return check_launch("k_component_build");
+}
+
+int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
+                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream) {
+  if (!dtype_ok(cc_dtype) || !dtype_ok(p_dtype) || !slots || !meta || !parent || (capacity && (!keys_out || !parents_out))) { set_error("frb_component_gather: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(&((u64*)meta)[FRB_META_LIST_COUNT], 0, sizeof(u64), st);
+  Grid g = grid_for((size_t)cap, 256 * 8, 8);
+  const int wc = dtype_width(cc_dtype), wp = dtype_width(p_dtype);
+  const Slot* s = (const Slot*)slots;
+  u64* m = (u64*)meta;
+  switch (wc) {
+    case 1: k_component_gather<1><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
+    case 2: k_component_gather<2><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
+    case 4: k_component_gather<4><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
+    default: k_component_gather<8><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
+  }
+  return check_launch("k_component_gather");
+}
+
+int frb_synth_volume(void* out, int dtype, uint64_t nz, uint64_t ny, uint64_t nx, uint64_t z0, uint64_t nz_total,
+                     uint64_t gz, uint64_t gy, uint64_t gx, uint64_t seed, double zero_frac, double noise,
+                     uint64_t cell_div, void* stream) {
+  if (!dtype_ok(dtype) || !out || !aligned16(out) || !nz || !ny || !nx || !nz_total || !gz || !gy || !gx || !cell_div) { set_error("frb_synth_volume: bad arguments"); return FRB_ERR_BAD_ARG; }
+  const int w = dtype_width(dtype);
+  SynthArgs S;
+  S.nz = nz; S.ny = ny; S.nx = nx; S.z0 = z0; S.nz_total = nz_total; S.gz = gz; S.gy = gy; S.gx = gx; S.seed = seed;
+  S.zero_thresh = (u64)(zero_frac * 16777216.0);
+  S.noise_thresh = (u64)(noise * 16777216.0);
+  const int idbits = dtype_signed(dtype) ? 8 * w - 1 : (8 * w > 63 ? 63 : 8 * w);
+  S.idmask = (1ull << idbits) - 1ull;
+  S.cell_div = cell_div;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)(nz * ny * nx);
+  Grid g = grid_for(n / (16 / w) + 1, 256 * 2, 16);
+  switch (w) {
+    case 1: k_synth<1><<<g.blocks, g.threads, 0, st>>>(out, S); break;
+    case 2: k_synth<2><<<g.blocks, g.threads, 0, st>>>(out, S); break;
+    case 4: k_synth<4><<<g.blocks, g.threads, 0, st>>>(out, S); break;
+    default: k_synth<8><<<g.blocks, g.threads, 0, st>>>(out, S); break;
+  }
+  return check_launch("k_synth");
+}
+
+}  // extern "C"

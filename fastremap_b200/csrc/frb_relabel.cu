@@ -1,0 +1,287 @@
+// frb_relabel.cu -- K3: the per-voxel table lookup + store, with the refit narrowing fused in.
+//
+// Replaces the write half of _renumber (fastremap.pyx:240/:244/:248), _remap (:749-767),
+// _mask_except (:516-525), remap_from_array_kv (:817-825), remap_from_array (:785-789) and the
+// astype of refit (:301).
+//
+// Every lane looks up all V = 16/W elements of its 16-byte vector.  Equal neighbours inside a
+// warp hit the same 16-byte slot, so the hardware coalesces them into one L1 request and the
+// reference's serial "same as previous voxel" shortcut is not needed; the first probe of each
+// element is issued unconditionally so all V loads are in flight before the first compare.
+// The table is read-only here (ld.global.nc, L1-allocating); the volume streams past L1.
+#include "frb_internal.cuh"
+
+namespace frb {
+
+static constexpr int ROWS = 4;
+static constexpr int TILE_VECS = 8 * ROWS * 32;
+
+struct RelabelArgs {
+  const Slot* slots;
+  u64 mask;
+  const u64* meta_ro;
+  u64* meta;
+  u64 fill;
+  int direct;
+  int policy;
+  int zero_fixed;
+};
+
+// result for one element whose home slot `first` has already been loaded
+__device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h, const Slot& first, size_t idx) {
+  if (A.zero_fixed && key == 0) return 0;
+  bool found;
+  u64 val = 0;
+  if (first.key == key && key != FRB_EMPTY) {
+    found = true;
+    val = first.val;
+  } else if (A.direct) {
+    found = false;
+  } else if (first.key == FRB_EMPTY && key != FRB_EMPTY) {
+    found = false;
+  } else {
+    found = table_find_from(A.slots, A.mask, A.meta_ro, key, (h + (key == FRB_EMPTY ? 0 : 1)) & A.mask, &val);
+  }
+  if (found) return A.policy == FRB_MISS_FILL ? key : val;
+  if (A.policy == FRB_MISS_KEEP) return key;
+  if (A.policy == FRB_MISS_FILL) return A.fill;
+  atomicMin(&A.meta[FRB_META_MISSING_INDEX], (u64)idx);
+  return key;
+}
+
+template <int W, int WO, bool WIDE>
+__global__ void __launch_bounds__(256)
+k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
+  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
+    uint4 v[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      const size_t vi = vbase + u * 32 + lane;
+      valid[u] = vi < nvec;
+      v[u] = valid[u] ? ld_stream16(src + vi) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      if (!valid[u]) continue;
+      const size_t i0 = (vbase + u * 32 + lane) * V;
+      u64 key[V], h[V], r[V];
+      Slot first[V];
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        key[j] = vec_get<W>(v[u], j);
+        h[j] = A.direct ? key[j] : (hash_key(key[j]) & A.mask);
+        first[j] = ld_slot_ro(A.slots + h[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < V; j++) r[j] = relabel_one(A, key[j], h[j], first[j], i0 + j);
+      if (WIDE) store_results<V, W>(dst_wide, i0, r);
+      if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 key = ld_elem<W>(src, i);
+      const u64 h = A.direct ? key : (hash_key(key) & A.mask);
+      const Slot first = ld_slot_ro(A.slots + h);
+      const u64 r = relabel_one(A, key, h, first, i);
+      if (WIDE) st_elem<W>(dst_wide, i, r);
+      if (WO > 0) st_elem<(WO > 0 ? WO : 1)>(dst_narrow, i, r);
+    }
+  }
+}
+
+template <int W, int WO, bool WIDE>
+static int launch_relabel(const void* src, void* dst_wide, void* dst_narrow, size_t n, const RelabelArgs& A, cudaStream_t st) {
+  Grid g = grid_for(n / (16 / W) + 1, TILE_VECS, 8);
+  k_relabel<W, WO, WIDE><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst_wide, dst_narrow, n, A);
+  return check_launch("k_relabel");
+}
+
+template <int W>
+static int dispatch_relabel(const void* src, void* dst_wide, void* dst_narrow, int wo, size_t n, const RelabelArgs& A, cudaStream_t st) {
+  const bool wide = dst_wide != nullptr;
+  if (!dst_narrow) wo = 0;
+#define FRB_CASE(WO_)                                                                                 \
+  if (wo == WO_) {                                                                                    \
+    if (wide) return launch_relabel<W, WO_, true>(src, dst_wide, dst_narrow, n, A, st);               \
+    if (WO_ > 0) return launch_relabel<W, WO_, false>(src, dst_wide, dst_narrow, n, A, st);           \
+  }
+  FRB_CASE(0)
+  FRB_CASE(1)
+  if constexpr (W >= 2) { FRB_CASE(2) }
+  if constexpr (W >= 4) { FRB_CASE(4) }
+  if constexpr (W >= 8) { FRB_CASE(8) }
+#undef FRB_CASE
+  set_error("frb_relabel: unsupported width combination (narrow_width must be <= input width; one destination needed)");
+  return FRB_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------- single pair replace
+template <int W>
+__global__ void __launch_bounds__(256)
+k_replace_one(const uint4* src, void* dst, size_t n, u64 before, u64 after) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+    const uint4 v = ld_stream16(src + vi);
+    u64 r[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const u64 k = vec_get<W>(v, j);
+      r[j] = k == before ? after : k;
+    }
+    store_results<V, W>(dst, vi * V, r);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 k = ld_elem<W>(src, i);
+      st_elem<W>(dst, i, k == before ? after : k);
+    }
+}
+
+// ---------------------------------------------------------------------- remap_from_array
+template <int W>
+__global__ void __launch_bounds__(256)
+k_remap_from_array(const uint4* src, void* dst, size_t n, const void* __restrict__ vals, u64 nvals) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+    const uint4 v = ld_stream16(src + vi);
+    u64 r[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const u64 k = vec_get<W>(v, j);
+      r[j] = k < nvals ? (u64)__ldg(((const typename UIntOf<W>::type*)vals) + k) : k;
+    }
+    store_results<V, W>(dst, vi * V, r);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 k = ld_elem<W>(src, i);
+      st_elem<W>(dst, i, k < nvals ? ld_elem<W>(vals, (size_t)k) : k);
+    }
+}
+
+// ---------------------------------------------------------------------- cast (refit astype)
+template <int WI, int WO, bool SIGNED_IN>
+__global__ void __launch_bounds__(256) k_cast(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
+  // element-strided, ELEMS per thread unrolled: each warp instruction touches 32 consecutive elements
+  constexpr int ELEMS = 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = ((size_t)blockIdx.x * blockDim.x) * ELEMS; base < n; base += stride * ELEMS) {
+    u64 v[ELEMS];
+#pragma unroll
+    for (int e = 0; e < ELEMS; e++) {
+      const size_t i = base + (size_t)e * blockDim.x + threadIdx.x;
+      v[e] = i < n ? ld_elem<WI>(src, i) : 0;
+    }
+#pragma unroll
+    for (int e = 0; e < ELEMS; e++) {
+      const size_t i = base + (size_t)e * blockDim.x + threadIdx.x;
+      if (i < n) st_elem<WO>(dst, i, SIGNED_IN ? sign_extend(v[e], WI) : v[e]);
+    }
+  }
+}
+
+template <int WI, int WO>
+static int launch_cast(const void* src, void* dst, size_t n, bool signed_in, cudaStream_t st) {
+  Grid g = grid_for(n, 256 * 8, 16);
+  if (signed_in) k_cast<WI, WO, true><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
+  else k_cast<WI, WO, false><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
+  return check_launch("k_cast");
+}
+
+}  // namespace frb
+
+using namespace frb;
+
+extern "C" {
+
+int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
+                const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill, int zero_fixed,
+                void* stream) {
+  if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (!dst_wide && !dst_narrow) ||
+      (n && (!src || !aligned16(src) || (dst_wide && !aligned16(dst_wide)) || (dst_narrow && !aligned16(dst_narrow)))) ||
+      policy < 0 || policy > 2) {
+    set_error("frb_relabel: bad arguments (pointers must be 16-byte aligned)");
+    return FRB_ERR_BAD_ARG;
+  }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  RelabelArgs A;
+  A.slots = (const Slot*)slots;
+  A.mask = cap - 1;
+  A.meta_ro = (const u64*)meta;
+  A.meta = (u64*)meta;
+  A.fill = trunc_width(fill, w);
+  A.direct = direct ? 1 : 0;
+  A.policy = policy;
+  A.zero_fixed = zero_fixed ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (w) {
+    case 1: return dispatch_relabel<1>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
+    case 2: return dispatch_relabel<2>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
+    case 4: return dispatch_relabel<4>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
+    default: return dispatch_relabel<8>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
+  }
+}
+
+int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream) {
+  if (!dtype_ok(dtype) || (n && (!src || !dst || !aligned16(src) || !aligned16(dst)))) { set_error("frb_replace_one: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n / (16 / w) + 1, 256 * 4, 16);
+  const u64 b = trunc_width(before, w), af = trunc_width(after, w);
+  switch (w) {
+    case 1: k_replace_one<1><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
+    case 2: k_replace_one<2><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
+    case 4: k_replace_one<4><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
+    default: k_replace_one<8><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
+  }
+  return check_launch("k_replace_one");
+}
+
+int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals, size_t nvals, int dtype, void* stream) {
+  if (!dtype_ok(dtype) || dtype_signed(dtype) || (n && (!src || !dst || !aligned16(src) || !aligned16(dst))) || (nvals && !vals)) {
+    set_error("frb_remap_from_array: bad arguments (unsigned dtypes only)");
+    return FRB_ERR_BAD_ARG;
+  }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n / (16 / w) + 1, 256 * 4, 16);
+  switch (w) {
+    case 1: k_remap_from_array<1><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
+    case 2: k_remap_from_array<2><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
+    case 4: k_remap_from_array<4><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
+    default: k_remap_from_array<8><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
+  }
+  return check_launch("k_remap_from_array");
+}
+
+int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {
+  if (!dtype_ok(src_dtype) || !dtype_ok(dst_dtype) || (n && (!src || !dst))) { set_error("frb_cast: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  const int wi = dtype_width(src_dtype), wo = dtype_width(dst_dtype);
+  const bool sg = dtype_signed(src_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FRB_CAST(WI_, WO_) if (wi == WI_ && wo == WO_) return launch_cast<WI_, WO_>(src, dst, n, sg, st);
+  FRB_CAST(1, 1) FRB_CAST(1, 2) FRB_CAST(1, 4) FRB_CAST(1, 8)
+  FRB_CAST(2, 1) FRB_CAST(2, 2) FRB_CAST(2, 4) FRB_CAST(2, 8)
+  FRB_CAST(4, 1) FRB_CAST(4, 2) FRB_CAST(4, 4) FRB_CAST(4, 8)
+  FRB_CAST(8, 1) FRB_CAST(8, 2) FRB_CAST(8, 4) FRB_CAST(8, 8)
+#undef FRB_CAST
+  set_error("frb_cast: unsupported widths");
+  return FRB_ERR_BAD_ARG;
+}
+
+}  // extern "C"

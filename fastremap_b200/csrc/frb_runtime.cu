@@ -1,0 +1,195 @@
+// frb_runtime.cu -- launch bookkeeping, error reporting, table init/insert/export entry points.
+#include <stdio.h>
+#include <string.h>
+
+#include "frb_common.cuh"
+
+namespace frb {
+
+unsigned long long g_launches = 0;
+static char g_error[512] = "";
+int g_sm_count = 0;
+
+void set_error(const char* msg) {
+  strncpy(g_error, msg, sizeof(g_error) - 1);
+  g_error[sizeof(g_error) - 1] = 0;
+}
+
+int check_launch(const char* what) {
+  g_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    set_error(buf);
+    return FRB_ERR_CUDA;
+  }
+  return FRB_OK;
+}
+
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+// ---------------------------------------------------------------------------------- table init
+__global__ void __launch_bounds__(256) k_table_init(Slot* slots, u64 cap, u64* meta, u64 init_val) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  ulonglong2 e = make_ulonglong2(FRB_EMPTY, init_val);
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride)
+    *reinterpret_cast<ulonglong2*>(slots + s) = e;
+  if (blockIdx.x == 0 && threadIdx.x < FRB_META_WORDS) {
+    u64 v = 0;
+    if (threadIdx.x == FRB_META_MISSING_INDEX) v = FRB_EMPTY;
+    if (threadIdx.x == FRB_META_SIDE_VAL) v = init_val;
+    meta[threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------- insert
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_table_insert(const void* __restrict__ keys, int kw, const void* __restrict__ vals, int vw, u64 val_offset, size_t L,
+               int direct, Slot* slots, u64 mask, u64* meta) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned int inserted = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += stride) {
+    u64 k = ld_elem_rt(keys, kw, i);
+    u64 v = vals ? ld_elem_rt(vals, vw, i) : (u64)i + val_offset;
+    table_update<OP>(slots, mask, direct, meta, k, v, &inserted);
+  }
+  block_add_to(&meta[FRB_META_COUNT], inserted);
+}
+
+__global__ void __launch_bounds__(256)
+k_table_resolve(const void* __restrict__ vals, int vw, Slot* slots, u64 cap, u64* meta) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
+    if (slots[s].key != FRB_EMPTY) slots[s].val = ld_elem_rt(vals, vw, (size_t)slots[s].val);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT])
+    meta[FRB_META_SIDE_VAL] = ld_elem_rt(vals, vw, (size_t)meta[FRB_META_SIDE_VAL]);
+}
+
+// ---------------------------------------------------------------------------------- export
+// mode 0: (key bits, value); mode 1: (value, slot index) -- the (sort key, payload) list of K2
+__global__ void __launch_bounds__(256)
+k_table_export(const Slot* __restrict__ slots, u64 cap, u64* meta, u64* __restrict__ a_out, u64* __restrict__ b_out,
+               size_t capacity, int mode) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  // cap is a power of two >= 256 or the loop bound is rounded up so whole warps stay converged
+  const size_t cap_r = (cap + 31) & ~(size_t)31;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap_r; s += stride) {
+    Slot cur;
+    cur.key = FRB_EMPTY;
+    cur.val = 0;
+    if (s < cap) cur = slots[s];
+    const bool occ = cur.key != FRB_EMPTY;
+    const unsigned int b = __ballot_sync(FRB_FULL_MASK, occ);
+    if (b == 0) continue;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(&meta[FRB_META_LIST_COUNT], (u64)__popc(b));
+    base = __shfl_sync(FRB_FULL_MASK, base, 0);
+    if (occ) {
+      const u64 pos = base + __popc(b & ((1u << lane) - 1u));
+      if (pos < capacity) {
+        if (mode == 0) { a_out[pos] = cur.key; b_out[pos] = cur.val; }
+        else { a_out[pos] = cur.val; b_out[pos] = (u64)s; }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {
+    const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
+    if (pos < capacity) {
+      if (mode == 0) { a_out[pos] = FRB_EMPTY; b_out[pos] = meta[FRB_META_SIDE_VAL]; }
+      else { a_out[pos] = meta[FRB_META_SIDE_VAL]; b_out[pos] = cap; }
+    }
+  }
+}
+
+int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* b_out, size_t capacity, int mode,
+                        cudaStream_t st) {
+  cudaMemsetAsync(&meta[FRB_META_LIST_COUNT], 0, sizeof(u64), st);
+  Grid g = grid_for((size_t)cap, 256 * 8, 8);
+  k_table_export<<<g.blocks, g.threads, 0, st>>>(slots, cap, meta, a_out, b_out, capacity, mode);
+  return check_launch("k_table_export");
+}
+
+}  // namespace frb
+
+using namespace frb;
+
+namespace frb { extern int g_sm_count; }
+
+extern "C" {
+
+size_t frb_table_bytes(uint64_t cap) { return (size_t)cap * sizeof(Slot); }
+
+uint64_t frb_table_direct_cap(int dtype) {
+  if (!dtype_ok(dtype)) return 0;
+  const int w = dtype_width(dtype);
+  return w == 1 ? 256ull : (w == 2 ? 65536ull : 0ull);
+}
+
+int frb_table_init(void* slots, uint64_t cap, uint64_t* meta, uint64_t init_val, void* stream) {
+  if (!slots || !meta || cap == 0 || (cap & (cap - 1)) != 0 || !aligned16(slots)) {
+    set_error("frb_table_init: bad arguments (cap must be a power of two, slots 16-byte aligned)");
+    return FRB_ERR_BAD_ARG;
+  }
+  Grid g = grid_for((size_t)cap, 256 * 8, 8);
+  k_table_init<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((Slot*)slots, cap, (u64*)meta, init_val);
+  return check_launch("k_table_init");
+}
+
+int frb_table_insert(const void* keys, int key_width, const void* vals, int val_width, uint64_t val_offset, size_t L,
+                     int op, int direct, void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+  if (!slots || !meta || (L && !keys) || (cap & (cap - 1)) != 0) {
+    set_error("frb_table_insert: bad arguments");
+    return FRB_ERR_BAD_ARG;
+  }
+  if (L == 0) return FRB_OK;
+  Grid g = grid_for(L, 256 * 4, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  Slot* s = (Slot*)slots;
+  u64* m = (u64*)meta;
+  switch (op) {
+    case FRB_OP_MIN: k_table_insert<FRB_OP_MIN><<<g.blocks, g.threads, 0, st>>>(keys, key_width, vals, val_width, val_offset, L, direct, s, cap - 1, m); break;
+    case FRB_OP_MAX: k_table_insert<FRB_OP_MAX><<<g.blocks, g.threads, 0, st>>>(keys, key_width, vals, val_width, val_offset, L, direct, s, cap - 1, m); break;
+    case FRB_OP_ADD: k_table_insert<FRB_OP_ADD><<<g.blocks, g.threads, 0, st>>>(keys, key_width, vals, val_width, val_offset, L, direct, s, cap - 1, m); break;
+    case FRB_OP_SET: k_table_insert<FRB_OP_SET><<<g.blocks, g.threads, 0, st>>>(keys, key_width, vals, val_width, val_offset, L, direct, s, cap - 1, m); break;
+    default: set_error("frb_table_insert: bad op"); return FRB_ERR_BAD_ARG;
+  }
+  return check_launch("k_table_insert");
+}
+
+int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+  if (!vals || !slots || !meta) { set_error("frb_table_resolve: bad arguments"); return FRB_ERR_BAD_ARG; }
+  Grid g = grid_for((size_t)cap, 256 * 8, 8);
+  k_table_resolve<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>(vals, val_width, (Slot*)slots, cap, (u64*)meta);
+  return check_launch("k_table_resolve");
+}
+
+int frb_table_export(const void* slots, uint64_t cap, uint64_t* meta, uint64_t* keys_out, uint64_t* vals_out,
+                     size_t capacity, void* stream) {
+  if (!slots || !meta || (capacity && (!keys_out || !vals_out))) { set_error("frb_table_export: bad arguments"); return FRB_ERR_BAD_ARG; }
+  return launch_table_export((const Slot*)slots, cap, (u64*)meta, (u64*)keys_out, (u64*)vals_out, capacity, 0, (cudaStream_t)stream);
+}
+
+int frb_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return FRB_ERR_CUDA; }
+  g_sm_count = 0;
+  return FRB_OK;
+}
+
+uint64_t frb_launch_count(void) { return g_launches; }
+const char* frb_last_error(void) { return g_error; }
+
+}  // extern "C"

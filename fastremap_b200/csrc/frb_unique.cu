@@ -1,0 +1,418 @@
+// frb_unique.cu -- K4/K5: unique(return_counts) strategies.
+//
+// Replaces _unique_via_array (fastremap.pyx:1061-1138), _unique_via_shifted_array (:984-1001),
+// _unique_via_renumber (:1003-1022) and _unique_via_sort (:1024-1059).  All strategies produce
+// the same (sorted labels, counts); the host picks by label range / cardinality:
+//   dense  counts[label - min] += 1, then an ordered compaction of the non-empty bins
+//   hash   (label -> count) table, then a sort of the L distinct labels
+//   sort   radix sort of all N voxels, then run-length encode
+// The counting kernels aggregate before they touch memory: each lane first run-length encodes
+// its own 16-byte vector, then the warp merges equal labels with match.any + redux so that a
+// 512-byte row costs one atomic per distinct label instead of one per voxel.
+#include "frb_internal.cuh"
+
+namespace frb {
+
+static constexpr int ROWS = 4;
+static constexpr int TILE_VECS = 8 * ROWS * 32;
+
+struct DenseSink {
+  u64* counts;
+  u64 min_bits;
+  int w;
+  __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int*) const {
+    atomicAdd(&counts[trunc_width(key - min_bits, w)], (u64)c);
+  }
+};
+struct HashSink {
+  Slot* slots;
+  u64 mask;
+  int direct;
+  u64* meta;
+  __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int* inserted) const {
+    table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
+  }
+};
+
+template <int W, typename Sink>
+__global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
+  unsigned int inserted = 0;
+  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
+    uint4 v[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      const size_t vi = vbase + u * 32 + lane;
+      valid[u] = vi < nvec;
+      v[u] = valid[u] ? ld_stream16(a + vi) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+      const unsigned int m = __ballot_sync(FRB_FULL_MASK, valid[u]);
+      if (!valid[u]) continue;
+      // run-length encode the lane's V elements: the leading run is merged across the warp,
+      // later runs (label boundaries inside the vector, rare) go to the sink directly
+      const u64 k0 = vec_get<W>(v[u], 0);
+      u64 cur = k0;
+      unsigned int c = 1, lead = 0;
+      bool leading = true;
+#pragma unroll
+      for (int j = 1; j < V; j++) {
+        const u64 kj = vec_get<W>(v[u], j);
+        if (kj == cur) {
+          c++;
+        } else {
+          if (leading) { lead = c; leading = false; }
+          else sink(cur, c, &inserted);
+          cur = kj;
+          c = 1;
+        }
+      }
+      if (leading) lead = c;
+      const unsigned int peers = __match_any_sync(m, k0);
+      const unsigned int total = __reduce_add_sync(peers, lead);
+      if (lane == __ffs(peers) - 1) sink(k0, total, &inserted);
+      if (!leading) sink(cur, c, &inserted);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
+  if (count_target) block_add_to(count_target, inserted);
+}
+
+// ------------------------------------------------------------------ ordered compaction of bins
+static inline int compact_blocks(size_t n) {
+  size_t need = (n + 2047) / 2048;
+  size_t cap = (size_t)sm_count() * 8;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+static inline size_t compact_chunk(size_t n, int blocks) {
+  size_t c = (n + blocks - 1) / blocks;
+  return align_up(c < 1 ? 1 : c, 256);
+}
+
+// block-wide exclusive prefix of a 0/1 flag (256 threads); returns the prefix, *total = block sum
+__device__ __forceinline__ unsigned int block_flag_scan(bool flag, unsigned int* total) {
+  __shared__ unsigned int wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int b = __ballot_sync(FRB_FULL_MASK, flag);
+  if (lane == 0) wsum[warp] = __popc(b);
+  __syncthreads();
+  unsigned int pre = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const unsigned int s = wsum[w];
+    if (w < warp) pre += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return pre + __popc(b & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256)
+k_bins_count(const u64* __restrict__ counts, u64 bins, size_t chunk, u64* __restrict__ block_counts) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > bins) end = bins;
+  unsigned int c = 0;
+  for (size_t i = beg + threadIdx.x; i < end; i += 256) c += counts[i] != 0 ? 1 : 0;
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  c = __reduce_add_sync(FRB_FULL_MASK, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_bins_emit(const u64* __restrict__ counts, u64 bins, size_t chunk, const u64* __restrict__ block_offs, u64 min_bits,
+            void* __restrict__ uniq_out, u64* __restrict__ counts_out, size_t capacity) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > bins) end = bins;
+  u64 run = block_offs[blockIdx.x];
+  for (size_t base = beg; base < end; base += 256) {
+    const size_t i = base + threadIdx.x;
+    const u64 c = i < end ? counts[i] : 0;
+    unsigned int tot;
+    const unsigned int pre = block_flag_scan(c != 0, &tot);
+    if (c != 0) {
+      const u64 pos = run + pre;
+      if (pos < capacity) {
+        st_elem<W>(uniq_out, pos, min_bits + (u64)i);
+        counts_out[pos] = c;
+      }
+    }
+    run += tot;
+  }
+}
+
+// ------------------------------------------------------------------ sorted (label, count) pairs
+__global__ void __launch_bounds__(256) k_flip_sign(u64* keys, size_t L, u64 flip) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += stride) keys[i] ^= flip;
+}
+template <int W>
+__global__ void __launch_bounds__(256)
+k_emit_pairs(const u64* __restrict__ keys, const u64* __restrict__ vals, size_t L, u64 flip, void* __restrict__ uniq_out,
+             u64* __restrict__ vals_out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += stride) {
+    st_elem<W>(uniq_out, i, keys[i] ^ flip);
+    vals_out[i] = vals[i];
+  }
+}
+
+// ------------------------------------------------------------------ sort + run-length encode
+template <int W, typename K>
+__global__ void __launch_bounds__(256) k_widen_flip(const void* __restrict__ a, size_t n, K* __restrict__ out, K flip) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (K)ld_elem<W>(a, i) ^ flip;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256)
+k_heads_count(const K* __restrict__ sorted, size_t n, size_t chunk, u64* __restrict__ block_counts) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  unsigned int c = 0;
+  for (size_t i = beg + threadIdx.x; i < end; i += 256) c += (i == 0 || sorted[i] != sorted[i - 1]) ? 1 : 0;
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  c = __reduce_add_sync(FRB_FULL_MASK, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+
+// A run [start, end) of label k with output position p: the head writes uniq[p] and adds -start
+// to counts[p]; the tail adds end.  counts_out is zeroed by the caller, so counts[p] = end - start.
+template <int W, typename K>
+__global__ void __launch_bounds__(256)
+k_heads_emit(const K* __restrict__ sorted, size_t n, size_t chunk, const u64* __restrict__ block_offs, K flip,
+             void* __restrict__ uniq_out, u64* __restrict__ counts_out, size_t capacity) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  u64 run = block_offs[blockIdx.x];
+  for (size_t base = beg; base < end; base += 256) {
+    const size_t i = base + threadIdx.x;
+    const bool in = i < end;
+    const K k = in ? sorted[i] : (K)0;
+    const bool head = in && (i == 0 || k != sorted[i - 1]);
+    const bool tail = in && (i + 1 == n || k != sorted[i + 1]);
+    unsigned int tot;
+    const unsigned int pre = block_flag_scan(head, &tot);
+    // output position of the run this element belongs to = (#heads at or before i) - 1
+    const u64 p = run + pre + (head ? 1 : 0) - 1;
+    if (head && p < capacity) {
+      st_elem<W>(uniq_out, p, (u64)(k ^ flip));
+      atomicAdd(&counts_out[p], (u64)0 - (u64)i);
+    }
+    if (tail && p < capacity) atomicAdd(&counts_out[p], (u64)i + 1);
+    run += tot;
+  }
+}
+
+}  // namespace frb
+
+using namespace frb;
+
+extern "C" {
+
+int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, void* stream) {
+  if (!dtype_ok(dtype) || !counts || bins == 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_dense: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  DenseSink sink;
+  sink.counts = (u64*)counts;
+  sink.min_bits = trunc_width(min_bits, w);
+  sink.w = w;
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const uint4* p = (const uint4*)a;
+  switch (w) {
+    case 1: k_hist<1, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
+    case 2: k_hist<2, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
+    case 4: k_hist<4, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
+    default: k_hist<8, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
+  }
+  return check_launch("k_hist<dense>");
+}
+
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+  if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_hash: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  HashSink sink;
+  sink.slots = (Slot*)slots;
+  sink.mask = cap - 1;
+  sink.direct = w <= 2 ? 1 : 0;
+  sink.meta = (u64*)meta;
+  if (sink.direct && cap != frb_table_direct_cap(dtype)) { set_error("frb_hist_hash: direct table needs cap == 2^bits"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const uint4* p = (const uint4*)a;
+  u64* ct = &((u64*)meta)[FRB_META_COUNT];
+  switch (w) {
+    case 1: k_hist<1, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
+    case 2: k_hist<2, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
+    case 4: k_hist<4, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
+    default: k_hist<8, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
+  }
+  return check_launch("k_hist<hash>");
+}
+
+size_t frb_compact_bins_ws_bytes(uint64_t bins) { return (size_t)compact_blocks((size_t)bins) * sizeof(u64) + 256; }
+
+int frb_compact_bins_count(const uint64_t* counts, uint64_t bins, uint64_t* meta, void* ws, size_t ws_bytes, void* stream) {
+  if (!counts || !meta || !ws || bins == 0 || ws_bytes < frb_compact_bins_ws_bytes(bins)) { set_error("frb_compact_bins_count: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks((size_t)bins);
+  const size_t chunk = compact_chunk((size_t)bins, blocks);
+  k_bins_count<<<blocks, 256, 0, st>>>((const u64*)counts, bins, chunk, (u64*)ws);
+  int rc = check_launch("k_bins_count");
+  if (rc) return rc;
+  return scan_exclusive_u64((u64*)ws, (size_t)blocks, &((u64*)meta)[FRB_META_LIST_COUNT], st);
+}
+
+int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint64_t min_bits, void* uniq_out,
+                          uint64_t* counts_out, size_t capacity, const void* ws, void* stream) {
+  if (!dtype_ok(dtype) || !counts || !ws || bins == 0 || (capacity && (!uniq_out || !counts_out))) { set_error("frb_compact_bins_emit: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks((size_t)bins);
+  const size_t chunk = compact_chunk((size_t)bins, blocks);
+  const int w = dtype_width(dtype);
+  const u64 mb = trunc_width(min_bits, w);
+  const u64* c = (const u64*)counts;
+  const u64* offs = (const u64*)ws;
+  u64* co = (u64*)counts_out;
+  switch (w) {
+    case 1: k_bins_emit<1><<<blocks, 256, 0, st>>>(c, bins, chunk, offs, mb, uniq_out, co, capacity); break;
+    case 2: k_bins_emit<2><<<blocks, 256, 0, st>>>(c, bins, chunk, offs, mb, uniq_out, co, capacity); break;
+    case 4: k_bins_emit<4><<<blocks, 256, 0, st>>>(c, bins, chunk, offs, mb, uniq_out, co, capacity); break;
+    default: k_bins_emit<8><<<blocks, 256, 0, st>>>(c, bins, chunk, offs, mb, uniq_out, co, capacity); break;
+  }
+  return check_launch("k_bins_emit");
+}
+
+// workspace: 2 ping-pong lists of L uint64 + radix histograms
+size_t frb_sort_pairs_ws_bytes(size_t L) {
+  const size_t c = L < 1 ? 1 : L;
+  return 2 * align_up(c * sizeof(u64), 256) + radix_hist_bytes(c);
+}
+
+int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, void* uniq_out, uint64_t* vals_out, void* ws,
+                         size_t ws_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !ws || ws_bytes < frb_sort_pairs_ws_bytes(L) || (L && (!keys || !vals || !uniq_out || !vals_out))) {
+    set_error("frb_sort_table_pairs: bad arguments");
+    return FRB_ERR_BAD_ARG;
+  }
+  if (L == 0) return FRB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w = dtype_width(dtype);
+  const u64 flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
+  const size_t lb = align_up(L * sizeof(u64), 256);
+  u64* k_alt = (u64*)ws;
+  u64* v_alt = (u64*)((char*)ws + lb);
+  void* hist = (char*)ws + 2 * lb;
+  int rc;
+  Grid g = grid_for(L, 256 * 4, 8);
+  if (flip) {
+    k_flip_sign<<<g.blocks, g.threads, 0, st>>>((u64*)keys, L, flip);
+    if ((rc = check_launch("k_flip_sign"))) return rc;
+  }
+  if ((rc = radix_sort_u64((u64*)keys, (u64*)vals, k_alt, v_alt, L, 0, 8 * w, hist, st))) return rc;
+  switch (w) {
+    case 1: k_emit_pairs<1><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
+    case 2: k_emit_pairs<2><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
+    case 4: k_emit_pairs<4><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
+    default: k_emit_pairs<8><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
+  }
+  return check_launch("k_emit_pairs");
+}
+
+// workspace: sorted keys (n * kw) | ping-pong (n * kw) | block counts | radix histograms;  kw = 4 (W<=4) or 8
+static inline size_t usort_key_bytes(int dtype) { return dtype_width(dtype) == 8 ? 8 : 4; }
+size_t frb_unique_sort_ws_bytes(size_t n, int dtype) {
+  if (!dtype_ok(dtype)) return 0;
+  const size_t c = n < 1 ? 1 : n;
+  return 2 * align_up(c * usort_key_bytes(dtype), 256) + align_up((size_t)compact_blocks(c) * sizeof(u64), 256) + radix_hist_bytes(c);
+}
+
+int frb_unique_sort_count(const void* a, size_t n, int dtype, uint64_t* meta, void* ws, size_t ws_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !a || n == 0 || !meta || !ws || ws_bytes < frb_unique_sort_ws_bytes(n, dtype)) { set_error("frb_unique_sort_count: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w = dtype_width(dtype);
+  const size_t kb = usort_key_bytes(dtype);
+  const size_t lb = align_up(n * kb, 256);
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  char* base = (char*)ws;
+  u64* block_counts = (u64*)(base + 2 * lb);
+  void* hist = base + 2 * lb + align_up((size_t)blocks * sizeof(u64), 256);
+  const u64 flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
+  Grid g = grid_for(n, 256 * 8, 16);
+  int rc;
+  if (kb == 8) {
+    u64* keys = (u64*)base;
+    u64* alt = (u64*)(base + lb);
+    k_widen_flip<8, u64><<<g.blocks, g.threads, 0, st>>>(a, n, keys, flip);
+    if ((rc = check_launch("k_widen_flip"))) return rc;
+    if ((rc = radix_sort_u64(keys, nullptr, alt, nullptr, n, 0, 64, hist, st))) return rc;
+    k_heads_count<u64><<<blocks, 256, 0, st>>>(keys, n, chunk, block_counts);
+  } else {
+    uint32_t* keys = (uint32_t*)base;
+    uint32_t* alt = (uint32_t*)(base + lb);
+    switch (w) {
+      case 1: k_widen_flip<1, uint32_t><<<g.blocks, g.threads, 0, st>>>(a, n, keys, (uint32_t)flip); break;
+      case 2: k_widen_flip<2, uint32_t><<<g.blocks, g.threads, 0, st>>>(a, n, keys, (uint32_t)flip); break;
+      default: k_widen_flip<4, uint32_t><<<g.blocks, g.threads, 0, st>>>(a, n, keys, (uint32_t)flip); break;
+    }
+    if ((rc = check_launch("k_widen_flip"))) return rc;
+    if ((rc = radix_sort_u32(keys, alt, n, 0, 8 * w, hist, st))) return rc;
+    k_heads_count<uint32_t><<<blocks, 256, 0, st>>>(keys, n, chunk, block_counts);
+  }
+  if ((rc = check_launch("k_heads_count"))) return rc;
+  return scan_exclusive_u64(block_counts, (size_t)blocks, &((u64*)meta)[FRB_META_LIST_COUNT], st);
+}
+
+int frb_unique_sort_emit(size_t n, int dtype, void* uniq_out, uint64_t* counts_out, size_t capacity, const void* ws, void* stream) {
+  if (!dtype_ok(dtype) || n == 0 || !ws || (capacity && (!uniq_out || !counts_out))) { set_error("frb_unique_sort_emit: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (capacity == 0) return FRB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int w = dtype_width(dtype);
+  const size_t kb = usort_key_bytes(dtype);
+  const size_t lb = align_up(n * kb, 256);
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  const char* base = (const char*)ws;
+  const u64* block_offs = (const u64*)(base + 2 * lb);
+  const u64 flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
+  cudaMemsetAsync(counts_out, 0, capacity * sizeof(u64), st);
+  u64* co = (u64*)counts_out;
+  if (kb == 8) {
+    k_heads_emit<8, u64><<<blocks, 256, 0, st>>>((const u64*)base, n, chunk, block_offs, flip, uniq_out, co, capacity);
+  } else {
+    const uint32_t* keys = (const uint32_t*)base;
+    switch (w) {
+      case 1: k_heads_emit<1, uint32_t><<<blocks, 256, 0, st>>>(keys, n, chunk, block_offs, (uint32_t)flip, uniq_out, co, capacity); break;
+      case 2: k_heads_emit<2, uint32_t><<<blocks, 256, 0, st>>>(keys, n, chunk, block_offs, (uint32_t)flip, uniq_out, co, capacity); break;
+      default: k_heads_emit<4, uint32_t><<<blocks, 256, 0, st>>>(keys, n, chunk, block_offs, (uint32_t)flip, uniq_out, co, capacity); break;
+    }
+  }
+  return check_launch("k_heads_emit");
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+/*
+ * fastremap_b200.h -- C ABI of the B200-native relabel hot path.
+ *
+ * The reference (seung-lab/fastremap) has no FFI: its boundary is the Python module
+ * surface (fastremap/__init__.py:1-24, signatures in fastremap/fastremap.pyi).  The host
+ * side of this library (fastremap_b200/api.py) keeps that surface verbatim; the entry
+ * points below are what it binds with ctypes, and each one names the typed inner loop of
+ * fastremap/fastremap.pyx that it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; the library never allocates
+ *    device memory (workspace sizes come from the *_bytes() queries);
+ *  - volume pointers (a, src, dst*) must be 16-byte aligned; n is in elements (voxels);
+ *  - arrays are walked in MEMORY order (the caller flattens C or F arrays by stride);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - return value: FRB_OK or an FRB_ERR_* code for argument / launch errors.  Data
+ *    dependent outcomes (table overflow, missing label) are reported through the table's
+ *    `meta` block, which the caller reads back after synchronising;
+ *  - dtype codes are frb_dtype; "raw bits" means the element zero-extended to 64 bits.
+ */
+#ifndef FASTREMAP_B200_H
+#define FASTREMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FRB_U8 = 0, FRB_U16 = 1, FRB_U32 = 2, FRB_U64 = 3,
+  FRB_I8 = 4, FRB_I16 = 5, FRB_I32 = 6, FRB_I64 = 7
+} frb_dtype;
+
+enum { FRB_OK = 0, FRB_ERR_BAD_ARG = 4, FRB_ERR_CUDA = 3 };
+
+/* ---- label table ---------------------------------------------------------------------
+ * Replaces ska::flat_hash_map<T,T> (fastremap/ska_flat_hash_map.hpp:1373-1490) as used by
+ * _renumber / _remap / _mask_except / remap_from_array_kv.
+ * A table is `cap` slots of 16 bytes {uint64 key bits, uint64 value} plus a meta block of
+ * FRB_META_WORDS uint64.  cap is a power of two.  Tables for 8/16-bit dtypes are DIRECT
+ * (slot index == key, cap == 2^bits); wider dtypes use open addressing with linear probing.
+ * The all-ones key pattern is the EMPTY marker; a real all-ones key lives in the meta block.
+ */
+#define FRB_META_WORDS 16
+enum {
+  FRB_META_COUNT = 0,        /* number of distinct keys inserted                          */
+  FRB_META_OVERFLOW = 1,     /* !=0: a probe sequence exceeded the limit -> grow and retry */
+  FRB_META_SIDE_PRESENT = 2, /* the all-ones key is present                               */
+  FRB_META_SIDE_VAL = 3,     /* ... and this is its value                                 */
+  FRB_META_MISSING_INDEX = 4,/* smallest flat index whose label was not in the table      */
+  FRB_META_LIST_COUNT = 5,   /* entries written by export / rank / unique                 */
+  FRB_META_AUX0 = 6,
+  FRB_META_AUX1 = 7
+};
+enum { FRB_OP_MIN = 0, FRB_OP_MAX = 1, FRB_OP_ADD = 2, FRB_OP_SET = 3 };
+
+size_t frb_table_bytes(uint64_t cap);                 /* = cap * 16 */
+uint64_t frb_table_direct_cap(int dtype);             /* 256 / 65536 for 8/16-bit dtypes, else 0 */
+/* keys := EMPTY, values := init_val, meta := 0 (MISSING_INDEX := all-ones, SIDE_VAL := init_val) */
+int frb_table_init(void* slots, uint64_t cap, uint64_t* meta, uint64_t init_val, void* stream);
+/* insert L (key, value) pairs, combining values of equal keys with `op`.
+ * keys: elements of width key_width bytes (1,2,4,8).  vals: width val_width, or NULL to use
+ * the pair's position (0..L-1) + val_offset as the value.  direct != 0 selects a DIRECT table. */
+int frb_table_insert(const void* keys, int key_width, const void* vals, int val_width, uint64_t val_offset,
+                     size_t L, int op, int direct, void* slots, uint64_t cap, uint64_t* meta, void* stream);
+/* replace every stored value v (a position) by vals[v] -- "later duplicate wins" for
+ * remap_from_array_kv (fastremap.pyx:810-811) after an FRB_OP_MAX insert of positions. */
+int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream);
+/* write all (key bits, value) pairs to keys_out/vals_out (uint64 each, capacity `capacity`);
+ * meta[FRB_META_LIST_COUNT] receives the number of pairs (unordered). */
+int frb_table_export(const void* slots, uint64_t cap, uint64_t* meta, uint64_t* keys_out, uint64_t* vals_out,
+                     size_t capacity, void* stream);
+
+/* ---- scans ---------------------------------------------------------------------------
+ * Replaces _minmax (fastremap.pyx:77-93) and _pixel_pairs (:840-853) with ONE fused pass.
+ * out[0]=min, out[1]=max (raw bits sign-extended to 64 for signed dtypes), out[2]=#(a[i]==a[i-1]),
+ * out[3]=#(a[i]!=0).  out is 4 uint64 on the device, initialised by the call. */
+int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* stream);
+
+/* ---- renumber ------------------------------------------------------------------------
+ * K1 replaces the find/insert half of _renumber's loop (fastremap.pyx:236-251): for every
+ * run head a[i] != a[i-1] the table receives key a[i] with value min(i + flat_offset).
+ * skip_zero != 0 (preserve_zero) leaves label 0 out of the table. */
+int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset, int skip_zero,
+                       void* slots, uint64_t cap, uint64_t* meta, void* stream);
+/* K2 replaces the implicit `remap_id += 1` ordering (fastremap.pyx:244-246): labels are ranked
+ * by first index; label of rank r gets id (T)(start + r) (arithmetic wraps in the array dtype,
+ * :225) which overwrites the table value.  keys_out / ids_out (elements of the array dtype,
+ * capacity `capacity`) receive the mapping in ascending-id order; meta[FRB_META_LIST_COUNT] the
+ * count.  index_bits = number of significant bits in the stored first indices. */
+size_t frb_renumber_rank_ws_bytes(size_t capacity);
+int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, int index_bits,
+                      void* keys_out, void* ids_out, size_t capacity, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- relabel -------------------------------------------------------------------------
+ * K3 replaces the write half of _renumber (fastremap.pyx:240/:244/:248), _remap (:749-767),
+ * _mask_except (:516-525) and remap_from_array_kv (:817-825), with the refit astype
+ * (:301) fused in as an optional narrow store.
+ *   dst_wide   (nullable) receives results at the input width (may alias src: in place)
+ *   dst_narrow (nullable) receives results truncated to narrow_width bytes (<= input width)
+ *   policy: FRB_MISS_KEEP   missing label stays as it is           (preserve_missing_labels)
+ *           FRB_MISS_ERROR  missing label: meta[MISSING_INDEX] = min(flat index); value kept
+ *           FRB_MISS_FILL   missing label := fill; present labels stay as they are (mask_except)
+ *   zero_fixed != 0: label 0 maps to 0 without a lookup (renumber's preserve_zero). */
+enum { FRB_MISS_KEEP = 0, FRB_MISS_ERROR = 1, FRB_MISS_FILL = 2 };
+int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
+                const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill,
+                int zero_fixed, void* stream);
+/* single-pair compare-and-replace, the :721-729 fast path of _remap */
+int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream);
+/* remap_from_array (fastremap.pyx:771-791): dst[i] = src[i] < nvals ? vals[src[i]] : src[i] (unsigned dtypes) */
+int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals, size_t nvals, int dtype, void* stream);
+/* refit's astype (fastremap.pyx:301): integer width change, truncating or sign/zero extending */
+int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
+
+/* ---- unique(return_counts) -----------------------------------------------------------
+ * Replaces _unique_via_array (fastremap.pyx:1061-1138), _unique_via_shifted_array (:984-1001),
+ * _unique_via_renumber (:1003-1022) and _unique_via_sort (:1024-1059).
+ * dense:  counts[a[i]-min] += 1 over `bins` uint64 bins (caller-zeroed), then an ordered
+ *         compaction of the non-empty bins;
+ * hash:   (key,count) table + sort of the distinct keys;
+ * sort:   radix sort of all voxels + run-length encode. */
+int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, void* stream);
+/* ordered compaction of the non-empty bins, in two steps because the caller sizes the outputs:
+ * _count leaves the number of non-empty bins in meta[FRB_META_LIST_COUNT] (and per-CTA offsets in
+ * ws); _emit writes label = min + bin (array dtype) and its count for every non-empty bin. */
+size_t frb_compact_bins_ws_bytes(uint64_t bins);
+int frb_compact_bins_count(const uint64_t* counts, uint64_t bins, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
+int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint64_t min_bits, void* uniq_out,
+                          uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream);
+size_t frb_sort_pairs_ws_bytes(size_t L);
+/* sort L exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are
+ * clobbered) and emit typed keys + values */
+int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, void* uniq_out, uint64_t* vals_out,
+                         void* ws, size_t ws_bytes, void* stream);
+/* sort strategy, two steps: _count copies + radix sorts the voxels inside ws and leaves the number
+ * of distinct labels in meta[FRB_META_LIST_COUNT]; _emit run-length encodes the sorted copy. */
+size_t frb_unique_sort_ws_bytes(size_t n, int dtype);
+int frb_unique_sort_count(const void* a, size_t n, int dtype, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
+int frb_unique_sort_emit(size_t n, int dtype, void* uniq_out, uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
+
+/* ---- component_map -------------------------------------------------------------------
+ * Replaces _component_map (fastremap.pyx:565-587): at every run start of cc the table
+ * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])
+ * for the winning run start of every label.  count in meta[FRB_META_LIST_COUNT]. */
+int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
+                        uint64_t* meta, void* stream);
+int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
+                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream);
+
+/* ---- synthetic volumes (benchmark / test input) -------------------
+ * Blocky "connectomics-like" labels: a gz*gy*gx grid of cells with splitmix64 ids, nearest
+ * neighbour upsampled to (nz_total, ny, nx); this call fills planes [z0, z0+nz) in C order.
+ * cell_div > 1 merges cell_div consecutive cells into one label (a "parent" volume that is a
+ * function of the cell_div == 1 volume with the same grid). */
+int frb_synth_volume(void* out, int dtype, uint64_t nz, uint64_t ny, uint64_t nx, uint64_t z0, uint64_t nz_total,
+                     uint64_t gz, uint64_t gy, uint64_t gx, uint64_t seed, double zero_frac, double noise,
+                     uint64_t cell_div, void* stream);
+
+/* bind this library's (statically linked) CUDA runtime to `device`; call once per process/thread
+ * before the first launch when the caller's framework selected a device other than 0 */
+int frb_set_device(int device);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t frb_launch_count(void);
+const char* frb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
