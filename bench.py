@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark: renumber of a 1024^3 uint64 synthetic segmentation (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference --gpus N ...            the unmodified reference on host cores
+
+One "step" = one renumber (in_place=True semantics: ids written back at the old width + narrowed
+copy + label mapping) of one 1024^3 uint64 volume per GPU.  N>1 (torchrun, one rank per GPU) is
+WEAK scaling: every rank owns one 1024^3 z-slab of an (N*1024, 1024, 1024) volume and the per-shard
+key tables are merged with one NCCL all-gather (fastremap_b200/sharded.py).
+
+value   : Gvox/s with the input resident in HBM, CUDA-event time per step summed over K steps
+          (the un-timed restore of the input between steps rewrites 8 GiB, which also flushes L2)
+e2e     : Gvox/s through the public API fastremap_b200.renumber(numpy array, in_place=True) with
+          pinned host buffers: H2D of the volume, kernels, D2H of both result arrays, dict build
+roofline: the dominant kernel (K3 k_relabel: 8 B read + 8 B wide write + 4 B narrow write per
+          voxel = 20 algorithmic bytes/voxel), timed with CUDA events on the launching stream
+cpu_baseline: oracle/_ref (the compiled reference) renumber(in_place=True) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIDE = 1024
+GRID = 46                 # cells per 1024 voxels per axis  (~88 k labels per 1024^3, ~91 % equal neighbours)
+DTYPE = np.uint64
+SEED = 0
+ZERO_FRAC = 0.1
+SAMPLE_PLANES = 256       # CPU legs run on the first 256 z-planes (2^28 voxels, 2 GiB)
+ALG_BYTES_PER_VOXEL = 20  # 8 read + 8 in-place write + 4 narrow write
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index=0):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+          if v.lower().startswith("active"):
+            reasons.add(name)
+      except Exception:
+        pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def import_reference():
+  ref_dir = os.path.join(ROOT, "oracle", "_ref")
+  if not os.path.isdir(os.path.join(ref_dir, "fastremap")):
+    return None
+  import importlib.util
+  spec = importlib.util.spec_from_file_location("fastremap", os.path.join(ref_dir, "fastremap", "__init__.py"),
+                                                submodule_search_locations=[os.path.join(ref_dir, "fastremap")])
+  mod = importlib.util.module_from_spec(spec)
+  sys.modules["fastremap"] = mod
+  try:
+    spec.loader.exec_module(mod)
+  except Exception:
+    sys.modules.pop("fastremap", None)
+    return None
+  return mod
+
+
+def cpu_impl():
+  """(module, kind): the compiled reference if present, else the oracle port."""
+  ref = import_reference()
+  if ref is not None:
+    return ref, "reference"
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import oracle as orc
+  orc.build()
+  return orc, "port"
+
+
+def host_sample(planes=SAMPLE_PLANES):
+  """First `planes` z-planes of the 1024^3 workload volume, generated on the host (numpy twin)."""
+  from concurrent.futures import ThreadPoolExecutor
+  from fastremap_b200.synth import synth_numpy
+  out = np.empty((planes, SIDE, SIDE), dtype=DTYPE)
+  step = 16
+
+  def fill(z0):
+    out[z0:z0 + step] = synth_numpy((step, SIDE, SIDE), (GRID, GRID, GRID), DTYPE, seed=SEED, zero_frac=ZERO_FRAC,
+                                    z0=z0, nz_total=SIDE)
+  with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+    list(ex.map(fill, range(0, planes, step)))
+  return out
+
+
+def time_cpu(impl, sample, reps):
+  """Best-of-reps seconds of impl.renumber(in_place=True) on a fresh copy of `sample` (copy excluded)."""
+  best, out = None, None
+  for _ in range(reps):
+    work = np.copy(sample)
+    t0 = time.perf_counter()
+    out = impl.renumber(work, in_place=True)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return best, out
+
+
+def sample_desc():
+  return ("renumber(in_place=True) on the first %d z-planes (%d voxels, %.0f GiB) of the 1024^3 uint64 workload volume, "
+          "1 thread (the reference is single-threaded)" % (SAMPLE_PLANES, SAMPLE_PLANES * SIDE * SIDE,
+                                                           SAMPLE_PLANES * SIDE * SIDE * 8 / 2 ** 30))
+
+
+# ------------------------------------------------------------------------------------ reference arm
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  impl, kind = cpu_impl()
+  sample = host_sample()
+  nvox = sample.size
+  for _ in range(args.warmup):
+    impl.renumber(np.copy(sample), in_place=True)
+  total = 0.0
+  for _ in range(args.steps):
+    work = np.copy(sample)
+    t0 = time.perf_counter()
+    impl.renumber(work, in_place=True)
+    total += time.perf_counter() - t0
+  value = nvox * args.steps / total / 1e9
+  line = {
+    "impl": "reference", "metric": "renumber throughput, 1024^3 uint64 synthetic segmentation", "value": value,
+    "unit": "Gvox/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "u64", "data": "synthetic",
+    "config": {"workload": "renumber(in_place=True) 1024^3 uint64, grid 46^3 (~88k labels/1024^3), bounded sample",
+               "sample_voxels": int(nvox)},
+    "cpu_baseline": {"value": value, "unit": "Gvox/s", "cores": 1, "kind": kind, "sample": sample_desc(),
+                     "host_cores_available": os.cpu_count()},
+    "e2e": {"value": value, "unit": "Gvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  import fastremap_b200 as fr
+  from fastremap_b200 import _lib, api, sharded
+  from fastremap_b200 import device as D
+  from fastremap_b200.synth import synth_device
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  dev = D.dev()
+  n = SIDE ** 3
+  nz_total = SIDE * world
+  peak, peak_src = load_peaks()
+
+  pristine = synth_device((SIDE, SIDE, SIDE), (GRID * world, GRID, GRID), DTYPE, seed=SEED, zero_frac=ZERO_FRAC,
+                          z0=rank * SIDE, nz_total=nz_total).reshape(-1).view(torch.uint8)
+  work = torch.empty_like(pristine)
+  torch.cuda.synchronize()
+
+  timers = {}
+
+  def step_device():
+    if world > 1:
+      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True)
+    return api.renumber_device(work, n, DTYPE, write_wide=True, timers=timers)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(args.warmup):
+    work.copy_(pristine)
+    res = step_device()
+  torch.cuda.synchronize()
+  out_dtype = str(res.out_dtype)
+  n_labels = int(res.n_labels)
+  del res
+
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = _lib.launch_count()
+  step_ms, k3_ms, k1_ms = [], [], []
+  barrier()
+  for _ in range(args.steps):
+    work.copy_(pristine)          # un-timed restore (also rewrites 8 GiB: L2 holds nothing of the input)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms.append(e0.elapsed_time(e1))
+    if timers:
+      k1_ms.append(timers["k1"][0].elapsed_time(timers["k1"][1]))
+      k3_ms.append(timers["k3"][0].elapsed_time(timers["k3"][1]))
+    del res
+  barrier()
+  launches = _lib.launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+
+  total_ms = float(sum(step_ms))
+  if world > 1:
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+  value = n * world * args.steps / (total_ms / 1e3) / 1e9
+
+  # ---- end to end through the public API with pinned host buffers (every rank: its own slab)
+  e2e_steps = max(1, min(args.steps, 3))
+  host_src = torch.empty(n * 8, dtype=torch.uint8, pin_memory=True)
+  host_work = torch.empty(n * 8, dtype=torch.uint8, pin_memory=True)
+  host_src.copy_(pristine)
+  torch.cuda.synchronize()
+  work_np = host_work.numpy().view(DTYPE).reshape(SIDE, SIDE, SIDE)
+  e2e_s, d2h = 0.0, 0
+  for i in range(1 + e2e_steps):
+    host_work.copy_(host_src)
+    barrier()
+    t0 = time.perf_counter()
+    if world > 1:
+      v = D.ingest(work_np)
+      r = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True)
+      mapping = api._mapping_to_dict(r, v.dtype, True)
+      D.download_into(r.wide, v.nbytes, D.flat_view(work_np))
+      out = D.emit(r.out, r.out_dtype, v.shape, v.order, False)
+    else:
+      out, mapping = fr.renumber(work_np, in_place=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+      t = torch.tensor([dt], dtype=torch.float64, device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      dt = float(t.item())
+    if i > 0:
+      e2e_s += dt
+    d2h = n * 8 + out.nbytes + 2 * 8 * len(mapping)
+    del out, mapping
+  e2e_value = n * world * e2e_steps / e2e_s / 1e9
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- dominant-kernel roofline (N=1: CUDA events around K3 on the launching stream)
+  roofline = None
+  if k3_ms:
+    k3 = float(np.mean(k3_ms))
+    achieved = ALG_BYTES_PER_VOXEL * n / (k3 / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_relabel<8,4,wide> (K3)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL * n,
+                "k1_build_ms": float(np.mean(k1_ms)),
+                "whole_op": {"algorithmic_GBps": ALG_BYTES_PER_VOXEL * n / (total_ms / args.steps / 1e3) / 1e9,
+                             "frac": ALG_BYTES_PER_VOXEL * n / (total_ms / args.steps / 1e3) / 1e9 / peak}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+      try:
+        with open(prof) as f:
+          roofline["traffic"] = json.load(f).get("k_relabel_dram_bytes_per_launch")
+      except Exception:
+        pass
+
+  # ---- CPU baseline beside it (rank 0, N=1 only): the compiled reference on a bounded sample + parity
+  cpu_baseline = None
+  if world == 1 and not args.no_cpu:
+    impl, kind = cpu_impl()
+    sample = host_sample()
+    secs, (ref_out, ref_map) = time_cpu(impl, sample, reps=2)
+    g_out, g_map = fr.renumber(np.copy(sample), in_place=True)
+    parity = bool(g_out.dtype == ref_out.dtype and np.array_equal(g_out, ref_out) and g_map == ref_map)
+    cpu_baseline = {"value": sample.size / secs / 1e9, "unit": "Gvox/s", "cores": 1, "kind": kind, "sample": sample_desc(),
+                    "host_cores_available": os.cpu_count(), "seconds": secs, "parity_vs_gpu_on_sample": parity}
+    if not parity:
+      raise SystemExit("bench.py: GPU result differs from the CPU %s on the sample -- refusing to report a number" % kind)
+
+  line = {
+    "metric": "renumber throughput, 1024^3 uint64 synthetic segmentation", "value": value, "unit": "Gvox/s",
+    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+    "config": {"workload": "renumber(in_place=True) of one 1024^3 uint64 volume per GPU (8 GiB), grid 46^3 cells "
+                           "(~88k labels, ~91% equal neighbours), refit to %s" % out_dtype,
+               "labels": n_labels, "l2": "input 8 GiB >> 126 MB L2; the un-timed restore between steps rewrites it",
+               "parallelism": "z-slab x%d, NCCL all-gather key-table merge" % world if world > 1 else "single GPU",
+               "hbm_fraction_of_peak_whole_op": ALG_BYTES_PER_VOXEL * n * world * args.steps / (total_ms / 1e3) / 1e9 / (peak * world)},
+    "e2e": {"value": e2e_value, "unit": "Gvox/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(d2h),
+            "steps": e2e_steps, "api": "fastremap_b200.renumber(pinned numpy array, in_place=True)"},
+    "gpu_launches": int(launches), "clocks": clocks,
+  }
+  if roofline:
+    line["roofline"] = roofline
+  if cpu_baseline:
+    line["cpu_baseline"] = cpu_baseline
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

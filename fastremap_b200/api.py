@@ -213,12 +213,20 @@ class RenumberResult:
   __slots__ = ("out", "out_dtype", "keys", "ids", "n_labels", "table", "wide")
 
 
+def _ev(timers, name, which):
+  if timers is not None:
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    timers.setdefault(name, [None, None])[which] = e
+
+
 def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                    flat_offset=0, total_n=None, merge=None) -> RenumberResult:
+                    flat_offset=0, total_n=None, merge=None, timers=None) -> RenumberResult:
   """
   K1 -> K2 -> K3 on a flat device buffer.
     write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
     merge: optional callable(table) -> table run between K1 and K2 (multi-GPU key-table merge).
+    timers: optional dict; receives CUDA event pairs "k1" / "k2" / "k3" recorded on the launching stream.
   """
   dtype = np.dtype(dtype)
   w = dtype.itemsize
@@ -227,8 +235,10 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
   table = LabelTable(dtype, _default_entries(n, max_labels), _lib.EMPTY)
 
   def build(t):
+    _ev(timers, "k1", 0)
     _lib.check(L.frb_renumber_build(D.ptr(src_buf), n, c, flat_offset, 1 if preserve_zero else 0, D.ptr(t.slots), t.cap,
                                     D.ptr(t.meta), D.stream()), "frb_renumber_build")
+    _ev(timers, "k1", 1)
 
   meta = _run_build(build, table)
   if merge is not None:
@@ -241,8 +251,10 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
   ws_bytes = int(L.frb_renumber_rank_ws_bytes(nl))
   ws = D.alloc(ws_bytes)
   index_bits = max(int((total_n if total_n is not None else n + flat_offset)).bit_length(), 1)
+  _ev(timers, "k2", 0)
   _lib.check(L.frb_renumber_rank(D.ptr(table.slots), table.cap, D.ptr(table.meta), c, int(np.int64(start)), index_bits,
                                  D.ptr(keys), D.ptr(ids), nl, D.ptr(ws), ws_bytes, D.stream()), "frb_renumber_rank")
+  _ev(timers, "k2", 1)
 
   # fastremap.pyx:253-255: fit to the NEXT id (typed, so it wraps in the array dtype) unless |start| is larger
   factor = _to_py(int(np.int64(start)) + nl, dtype)
@@ -256,7 +268,9 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
   narrow = D.alloc(n * wo) if wo < w else None
   need_wide = write_wide or wo >= w
   wide_dst = src_buf if need_wide else None
+  _ev(timers, "k3", 0)
   _relabel(src_buf, n, dtype, table, _lib.MISS_ERROR, 0, preserve_zero, wide_dst, narrow, wo if narrow is not None else 0)
+  _ev(timers, "k3", 1)
   res.wide = src_buf if need_wide else None
   if wo < w:
     res.out = narrow

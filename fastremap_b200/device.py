@@ -116,7 +116,7 @@ def download_into(buf: torch.Tensor, nbytes: int, flat_np: np.ndarray):
 
 def download(buf: torch.Tensor, n: int, dtype) -> np.ndarray:
   dtype = np.dtype(dtype)
-  out = np.empty(n, dtype=dtype)
+  out = host_empty((n,), dtype)
   download_into(buf, n * dtype.itemsize, out)
   return out
 
@@ -189,6 +189,23 @@ def emit(buf: torch.Tensor, dtype, shape, order, as_torch: bool):
     if order == "F" and len(shape) > 1:
       return t.reshape(tuple(reversed(shape))).permute(tuple(reversed(range(len(shape)))))
     return t.reshape(shape)
-  out = np.empty(shape, dtype=dtype, order=order)
+  out = host_empty(shape, dtype, order)
   download_into(buf, n * dtype.itemsize, flat_view(out))
   return out
+
+
+PINNED_RESULT_MIN_BYTES = 1 << 20
+
+
+def host_empty(shape, dtype, order="C") -> np.ndarray:
+  """Result array on the host.  Large results live in page-locked memory from torch's caching
+  pinned allocator, so the device->host copy runs at PCIe speed and the block is recycled once the
+  caller drops the array."""
+  dtype = np.dtype(dtype)
+  n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+  nbytes = n * dtype.itemsize
+  if nbytes < PINNED_RESULT_MIN_BYTES:
+    return np.empty(shape, dtype=dtype, order=order)
+  t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+  flat = t.numpy().view(dtype)  # keeps `t` alive through .base
+  return flat.reshape(shape, order=order)

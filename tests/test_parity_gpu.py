@@ -1,0 +1,283 @@
+"""
+Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+Everything here needs a GPU (-m gpu).  Bit-exact for every integer dtype.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+import test_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = (np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64)
+
+
+def synth(*a, **k):
+  from fastremap_b200.synth import synth_numpy
+  return synth_numpy(*a, **k)
+
+
+# ------------------------------------------------------------------ committed fixtures of the compiled reference
+
+_SKIP_FNS = ()
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_golden_fixture(frb, name):
+  G.check_case(G.get_case(name), frb)
+
+
+# ------------------------------------------------------------------ the reference test-suite's own goldens
+
+
+def test_reference_suite_renumber(frb):
+  T.test_empty_renumber(frb)
+  T.test_1d_renumber(frb, False)
+  T.test_1d_renumber(frb, True)
+  T.test_2d_renumber(frb)
+  for dt in DTYPES:
+    T.test_3d_renumber(frb, dt)
+  T.test_renumber_no_preserve_zero(frb)
+  T.test_renumber_in_place_broken(frb)
+  T.test_readme_example(frb)
+  T.test_renumber_remap(frb)
+
+
+def test_reference_suite_remap_mask(frb):
+  for dt in DTYPES:
+    for ip in (False, True):
+      T.test_remap_1d(frb, dt, ip)
+      T.test_mask(frb, dt, ip)
+      T.test_mask_except(frb, dt, ip)
+    T.test_remap_2d(frb, dt)
+  T.test_remap_in_place_broken(frb)
+  labels = np.zeros((64, 64, 64), dtype=np.uint32)  # automated_test.py:207-214
+  labels[:50, :40, :30] = 2
+  labels[50:, 40:, 30:] = 5
+  assert np.all(frb.remap(labels, {5: 5}, preserve_missing_labels=True) == labels)
+
+
+def test_reference_suite_component_map(frb):
+  for dc in DTYPES:
+    for dp in DTYPES:
+      T.test_component_map(frb, dc, dp)
+
+
+def test_reference_suite_unique_minmax(frb):
+  rng = np.random.default_rng(2)  # automated_test.py:443-553, counts only
+  for labels in (rng.integers(0, 500, size=(32, 32, 32)), rng.integers(-500, 500, size=(32, 32, 32)),
+                 rng.integers(32 ** 3 - 500, 32 ** 3 + 500, size=(32, 32, 32)), rng.integers(-1000, 128 ** 3, size=(20, 20, 20))):
+    for arr in (labels, np.asfortranarray(labels)):
+      u_np, c_np = np.unique(arr, return_counts=True)
+      u, c = frb.unique(arr, return_counts=True)
+      assert u.dtype == arr.dtype and c.dtype == np.uint64
+      assert np.array_equal(u, u_np) and np.array_equal(c, c_np)
+  assert np.all(frb.unique([1, 1, 2, 3, 2, 4, 3]) == [1, 2, 3, 4])
+  T.test_minmax(frb)
+  big = rng.integers(0, (2 ** 64) - 1, size=(64, 64, 50), dtype=np.uint64)  # automated_test.py:132-136
+  out, _ = frb.renumber(big, preserve_zero=True, in_place=True)
+  assert 1 < out.dtype.itemsize <= 4
+
+
+# ------------------------------------------------------------------ differential vs the oracle
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_renumber_vs_oracle(frb, oracle, dtype):
+  a = synth((40, 48, 72), (9, 10, 11), dtype, seed=int(np.dtype(dtype).num) + 1, zero_frac=0.15, noise=0.08)
+  for arr in (a, np.asfortranarray(a)):
+    for pz in (True, False):
+      for start in (1, 0, 10):
+        e_out, e_map = oracle.renumber(np.copy(arr, order="K"), start=start, preserve_zero=pz)
+        g_out, g_map = frb.renumber(np.copy(arr, order="K"), start=start, preserve_zero=pz)
+        assert g_out.dtype == e_out.dtype and g_out.shape == e_out.shape
+        assert np.array_equal(g_out, e_out) and g_map == e_map
+        assert g_out.flags.f_contiguous == e_out.flags.f_contiguous
+  # in_place: the caller's buffer receives the ids at the old width
+  e_in, g_in = np.copy(a), np.copy(a)
+  e_out, _ = oracle.renumber(e_in, in_place=True)
+  g_out, _ = frb.renumber(g_in, in_place=True)
+  assert np.array_equal(e_in, g_in) and np.array_equal(e_out, g_out) and e_out.dtype == g_out.dtype
+  ro = np.copy(a)
+  ro.flags.writeable = False
+  g_out, _ = frb.renumber(ro, in_place=True)
+  assert np.array_equal(ro, a) and np.array_equal(g_out, e_out)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 15, 16, 17, 31, 33, 63, 255, 1023, 1025, 4097, 32769, 100003])
+def test_ragged_lengths(frb, oracle, n):
+  for dtype in (np.uint8, np.uint16, np.uint32, np.uint64):
+    a = synth((1, 1, n), (1, 1, max(n // 7, 1)), dtype, seed=n, zero_frac=0.2, noise=0.2).reshape(-1)
+    e_out, e_map = oracle.renumber(np.copy(a))
+    g_out, g_map = frb.renumber(np.copy(a))
+    assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+    eu, ec = oracle.unique(a, return_counts=True)
+    gu, gc = frb.unique(a, return_counts=True)
+    assert np.array_equal(eu, gu) and np.array_equal(ec.astype(np.uint64), gc.astype(np.uint64))
+    assert frb.pixel_pairs(a) == oracle.pixel_pairs(a) and frb.minmax(a) == oracle.minmax(a)
+    keep = [int(x) for x in np.unique(a)[::2]]
+    assert np.array_equal(frb.mask_except(np.copy(a), keep, value=3), oracle.mask_except(np.copy(a), keep, value=3))
+    par = (a.astype(np.uint64) % 11).astype(np.uint8)
+    assert frb.component_map(a, par) == oracle.component_map(a, par)
+
+
+def test_all_ones_key_and_extremes(frb, oracle):
+  a = np.array([2 ** 64 - 1, 5, 2 ** 64 - 1, 0, 2 ** 63, 5, 2 ** 64 - 1, 7] * 33, dtype=np.uint64)
+  for arr in (a, a.view(np.int64)):
+    for pz in (True, False):
+      e_out, e_map = oracle.renumber(np.copy(arr), preserve_zero=pz)
+      g_out, g_map = frb.renumber(np.copy(arr), preserve_zero=pz)
+      assert np.array_equal(g_out, e_out) and g_map == e_map and g_out.dtype == e_out.dtype
+    for strategy in ("hash", "sort", None):
+      eu, ec = oracle.unique(arr, return_counts=True)
+      gu, gc = frb.unique(arr, return_counts=True, strategy=strategy)
+      assert np.array_equal(eu, gu) and np.array_equal(ec, gc)
+    tbl = {int(arr[0]): 1, int(arr[4]): int(arr[0])}
+    assert np.array_equal(frb.remap(np.copy(arr), tbl, preserve_missing_labels=True),
+                          oracle.remap(np.copy(arr), tbl, preserve_missing_labels=True))
+    assert np.array_equal(frb.mask_except(np.copy(arr), [int(arr[0])]), oracle.mask_except(np.copy(arr), [int(arr[0])]))
+    par = np.arange(arr.size, dtype=np.uint32)
+    assert frb.component_map(arr, par) == oracle.component_map(arr, par)
+    assert frb.minmax(arr) == oracle.minmax(arr)
+
+
+def test_many_labels_and_table_growth(frb, oracle):
+  a = synth((48, 64, 64), (40, 50, 50), np.uint64, seed=9, zero_frac=0.05, noise=0.03)  # ~95k labels -> uint32
+  e_out, e_map = oracle.renumber(np.copy(a))
+  g_out, g_map = frb.renumber(np.copy(a))
+  assert g_out.dtype == np.uint32 == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+  g_out2, g_map2 = frb.renumber(np.copy(a), max_labels=100)  # undersized table: must grow and still be exact
+  assert np.array_equal(g_out2, e_out) and g_map2 == e_map
+  # no runs at all: every voxel is a table probe
+  rnd = synth((1, 300, 300), (1, 300, 300), np.uint32, seed=10, zero_frac=0.0)
+  rnd = (rnd % np.uint32(5000)).astype(np.uint32)
+  e_out, e_map = oracle.renumber(np.copy(rnd))
+  g_out, g_map = frb.renumber(np.copy(rnd))
+  assert np.array_equal(g_out, e_out) and g_map == e_map
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_unique_strategies_vs_oracle(frb, oracle, dtype):
+  sparse = synth((30, 40, 56), (7, 8, 9), dtype, seed=21, zero_frac=0.1, noise=0.05)
+  dense = (sparse.astype(np.uint64) % np.uint64(100)).astype(dtype)
+  for arr in (sparse, dense, np.asfortranarray(sparse)):
+    eu, ec = oracle.unique(arr, return_counts=True)
+    for strategy in (None, "dense", "hash", "sort"):
+      if strategy == "dense" and arr is not dense and np.dtype(dtype).itemsize > 2:
+        continue
+      gu, gc = frb.unique(arr, return_counts=True, strategy=strategy)
+      assert gu.dtype == eu.dtype and gc.dtype == np.uint64
+      assert np.array_equal(gu, eu), (strategy, dtype)
+      assert np.array_equal(gc, ec), (strategy, dtype)
+    assert np.array_equal(frb.unique(arr), eu)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_remap_family_vs_oracle(frb, oracle, dtype):
+  a = synth((24, 32, 40), (5, 6, 7), dtype, seed=31, zero_frac=0.1, noise=0.05)
+  labels = [int(x) for x in np.unique(a)]
+  info = np.iinfo(dtype)
+  table = {l: (l * 7 + 3) % int(info.max) for l in labels[::2]}
+  for arr in (a, np.asfortranarray(a)):
+    e = oracle.remap(np.copy(arr, order="K"), table, preserve_missing_labels=True)
+    g = frb.remap(np.copy(arr, order="K"), table, preserve_missing_labels=True)
+    assert g.dtype == e.dtype and np.array_equal(g, e) and g.flags.f_contiguous == e.flags.f_contiguous
+  with pytest.raises(KeyError) as ge:
+    frb.remap(np.copy(a), table, preserve_missing_labels=False)
+  with pytest.raises(KeyError) as ee:
+    oracle.remap(np.copy(a), table, preserve_missing_labels=False)
+  assert str(ge.value) == str(ee.value)  # names the FIRST missing label in memory order
+  full = {l: (l * 3 + 1) % int(info.max) for l in labels}
+  assert np.array_equal(frb.remap(np.copy(a), full), oracle.remap(np.copy(a), full))
+  buf = np.copy(a)
+  out = frb.remap(buf, full, in_place=True)
+  assert out is buf or np.shares_memory(out, buf)
+  assert np.array_equal(buf, oracle.remap(np.copy(a), full))
+  assert np.array_equal(frb.mask(np.copy(a), labels[1:40:3], value=5), oracle.mask(np.copy(a), labels[1:40:3], value=5))
+  for value in (0, 9, int(info.max)):
+    assert np.array_equal(frb.mask_except(np.copy(a), labels[::3], value=value),
+                          oracle.mask_except(np.copy(a), labels[::3], value=value))
+  flat = a.reshape(-1)
+  keys = np.array(labels[::2] + labels[:6], dtype=dtype)  # duplicates: the later one wins
+  vals = ((np.arange(keys.size) * 5 + 1) % int(info.max)).astype(dtype)
+  assert np.array_equal(frb.remap_from_array_kv(np.copy(flat), keys, vals), oracle.remap_from_array_kv(np.copy(flat), keys, vals))
+  with pytest.raises(KeyError) as ge:
+    frb.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
+  with pytest.raises(KeyError) as ee:
+    oracle.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
+  assert str(ge.value) == str(ee.value)
+  if np.issubdtype(dtype, np.unsignedinteger):
+    small = (flat.astype(np.uint64) % np.uint64(60)).astype(dtype)
+    v = ((np.arange(40) * 3 + 2) % 200).astype(dtype)
+    assert np.array_equal(frb.remap_from_array(np.copy(small), v), oracle.remap_from_array(np.copy(small), v))
+    assert np.array_equal(frb.remap_from_array(np.copy(small), v[:0]), small)
+  buf = np.copy(flat)
+  frb.remap_from_array_kv(buf, keys, vals)  # default in_place=True mutates the caller's array
+  assert np.array_equal(buf, oracle.remap_from_array_kv(np.copy(flat), keys, vals))
+
+
+@pytest.mark.parametrize("dtypes", [(np.uint64, np.uint32), (np.uint8, np.int64), (np.int32, np.uint16), (np.uint16, np.uint8)])
+def test_component_map_vs_oracle(frb, oracle, dtypes):
+  dc, dp = dtypes
+  cc = synth((24, 32, 40), (6, 7, 8), dc, seed=41, zero_frac=0.1, noise=0.1)
+  # non-functional parent: conflicting stores, the last run start in memory order must win
+  par = synth((24, 32, 40), (3, 4, 5), dp, seed=42, zero_frac=0.0, noise=0.2)
+  for c, p in ((cc, par), (np.asfortranarray(cc), np.asfortranarray(par)), (cc, np.asfortranarray(par))):
+    assert frb.component_map(c, p) == oracle.component_map(c, p)
+
+
+def test_refit_minmax_pairs_vs_oracle(frb, oracle):
+  for dtype in DTYPES:
+    a = synth((16, 20, 24), (4, 5, 6), dtype, seed=51, zero_frac=0.2)
+    small = (a.astype(np.uint64) % np.uint64(90)).astype(dtype)
+    for arr in (a, small, np.asfortranarray(small)):
+      assert frb.minmax(arr) == oracle.minmax(arr)
+      assert frb.pixel_pairs(arr) == oracle.pixel_pairs(arr)
+      e, g = oracle.refit(arr), frb.refit(arr)
+      assert e.dtype == g.dtype and np.array_equal(e, g)
+      e, g = oracle.refit(arr, 70000), frb.refit(arr, 70000)
+      assert e.dtype == g.dtype and np.array_equal(e, g)
+    if np.issubdtype(dtype, np.signedinteger):
+      neg = (small.astype(np.int64) - 40).astype(dtype)
+      assert frb.minmax(neg) == oracle.minmax(neg)
+      e, g = oracle.refit(neg, -40000), frb.refit(neg, -40000)
+      assert e.dtype == g.dtype and np.array_equal(e, g)
+
+
+# ------------------------------------------------------------------ device-resident API and generator twin
+
+
+def test_device_tensors(frb, oracle):
+  a = synth((32, 40, 48), (7, 8, 9), np.uint64, seed=61, zero_frac=0.1, noise=0.05)
+  t = torch.from_numpy(a.view(np.int64)).cuda().view(torch.uint64)
+  e_out, e_map = oracle.renumber(np.copy(a))
+  g_out, g_map = frb.renumber(t)
+  assert isinstance(g_out, torch.Tensor) and g_out.is_cuda and g_map == e_map
+  assert np.array_equal(g_out.cpu().numpy(), e_out)
+  assert np.array_equal(t.view(torch.int64).cpu().numpy().view(np.uint64), a)  # not in place: input untouched
+  g_out, _ = frb.renumber(t, in_place=True)
+  e_in = np.copy(a)
+  oracle.renumber(e_in, in_place=True)
+  assert np.array_equal(t.view(torch.int64).cpu().numpy().view(np.uint64), e_in)  # in place: ids at the old width
+  t32 = torch.from_numpy(e_out.view(np.int32)).cuda()
+  u, c = frb.unique(t32, return_counts=True)
+  eu, ec = oracle.unique(e_out.view(np.int32), return_counts=True)
+  assert np.array_equal(u.cpu().numpy(), eu) and np.array_equal(c.view(torch.int64).cpu().numpy().view(np.uint64), ec)
+  tf = torch.from_numpy(np.ascontiguousarray(a.view(np.int64).transpose(2, 1, 0))).cuda().permute(2, 1, 0)  # F-ordered tensor
+  g_out, g_map = frb.renumber(tf)
+  e_out, e_map = oracle.renumber(np.asfortranarray(a.view(np.int64)))
+  assert g_map == e_map and np.array_equal(g_out.cpu().numpy(), e_out)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_synth_device_equals_numpy_twin(frb, dtype):
+  from fastremap_b200.synth import synth_device
+  kw = dict(seed=71, zero_frac=0.15, noise=0.07)
+  d = synth_device((9, 17, 35), (3, 4, 5), dtype, z0=4, nz_total=20, **kw)
+  h = synth((9, 17, 35), (3, 4, 5), dtype, z0=4, nz_total=20, **kw)
+  assert np.array_equal(d.cpu().view(torch.uint8).numpy().view(dtype).reshape(h.shape), h)
+  dp = synth_device((9, 17, 35), (3, 4, 5), dtype, cell_div=4, **kw)
+  hp = synth((9, 17, 35), (3, 4, 5), dtype, cell_div=4, **kw)
+  assert np.array_equal(dp.cpu().view(torch.uint8).numpy().view(dtype).reshape(hp.shape), hp)
