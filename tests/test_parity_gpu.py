@@ -201,7 +201,7 @@ def test_remap_family_vs_oracle(frb, oracle, dtype):
                           oracle.mask_except(np.copy(a), labels[::3], value=value))
   flat = a.reshape(-1)
   keys = np.array(labels[::2] + labels[:6], dtype=dtype)  # duplicates: the later one wins
-  vals = ((np.arange(keys.size) * 5 + 1) % int(info.max)).astype(dtype)
+  vals = np.array([(i * 5 + 1) % int(info.max) for i in range(keys.size)], dtype=dtype)
   assert np.array_equal(frb.remap_from_array_kv(np.copy(flat), keys, vals), oracle.remap_from_array_kv(np.copy(flat), keys, vals))
   with pytest.raises(KeyError) as ge:
     frb.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
