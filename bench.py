@@ -49,42 +49,57 @@ def load_peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-       "clocks_event_reasons.sw_power_cap")
+  """SM clock / throttle reasons sampled through NVML every few ms DURING the timed region."""
 
   def __init__(self, index=0):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
 
   def start(self):
     try:
-      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                   stderr=subprocess.DEVNULL, text=True)
-      threading.Thread(target=self._read, daemon=True).start()
-    except Exception:
-      self.proc = None
+      import pynvml
+      pynvml.nvmlInit()
+      # CUDA_VISIBLE_DEVICES may remap indices; fall back to index 0 if out of range
+      try:
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+      except Exception:
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(0)
+      self.nv = pynvml
+      self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception as e:  # pragma: no cover
+      self.err = repr(e)
+      return
+    self.thread = threading.Thread(target=self._run, daemon=True)
+    self.thread.start()
 
-  def _read(self):
-    for line in self.proc.stdout:
-      self.rows.append([c.strip() for c in line.split(",")])
+  def _run(self):
+    nv = self.nv
+    while not self.stop_flag:
+      try:
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+          reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+          reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.rows.append((sm, int(reasons)))
+      except Exception as e:  # pragma: no cover
+        self.err = repr(e)
+        return
+      time.sleep(0.002)
 
   def stop(self):
-    if self.proc is None:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    self.proc.terminate()
-    sm, mx, reasons = [], [], set()
-    for r in self.rows:
-      try:
-        sm.append(float(r[1])); mx.append(float(r[2]))
-        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-          if v.lower().startswith("active"):
-            reasons.add(name)
-      except Exception:
-        pass
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons), "samples": len(sm)}
+    if self.thread is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+    self.stop_flag = True
+    self.thread.join(timeout=2)
+    nv = self.nv
+    names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+    reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+    sm = [r[0] for r in self.rows]
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+            "samples": len(sm)}
 
 
 def import_reference():

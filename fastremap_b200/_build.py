@@ -13,6 +13,13 @@ SO = os.path.join(HERE, "libfastremap_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+EXTRA = os.environ.get("FRB_CFLAGS", "").split()          # experiments: e.g. -DFRB_STREAM_ROWS=8
+if EXTRA:
+  tag = "_" + "_".join(f.replace("-D", "").replace("=", "") for f in EXTRA)
+  OBJ = os.path.join(HERE, "csrc", "_obj" + tag)
+  SO = os.path.join(HERE, "..", "build_variants", "libfastremap_b200%s.so" % tag)
+  os.makedirs(os.path.dirname(SO), exist_ok=True)
+  FLAGS = FLAGS + EXTRA
 
 
 def sources():

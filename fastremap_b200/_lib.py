@@ -9,7 +9,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libfastremap_b200.so")
+SO_PATH = os.environ.get("FASTREMAP_B200_SO") or os.path.join(HERE, "libfastremap_b200.so")
 
 # dtype codes (frb_dtype)
 U8, U16, U32, U64, I8, I16, I32, I64 = range(8)
@@ -57,7 +57,9 @@ SIGNATURES = {
   "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
+  "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),
   "frb_set_device": (_i, [_i]),
+  "frb_set_tile_run": (None, [_i]),
   "frb_launch_count": (_u64, []),
   "frb_last_error": (ctypes.c_char_p, []),
 }

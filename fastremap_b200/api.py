@@ -100,10 +100,10 @@ class LabelTable:
 
 def _default_entries(n: int, max_labels) -> int:
   """Initial sizing of a hash table for an n-voxel volume when the label count is unknown:
-  n/128 labels (8.4 M at 1024^3; a 256 MiB table), at least 32 Ki; grown x4 on overflow."""
+  n/256 labels (4.2 M at 1024^3; a 128 MiB table), at least 32 Ki; grown x4 on overflow."""
   if max_labels is not None:
     return int(max_labels) + 1
-  return int(min(max(n // 128, 1 << 15), 1 << 27))
+  return int(min(max(n // 256, 1 << 15), 1 << 27))
 
 
 def _run_build(fn, table: LabelTable):
@@ -551,20 +551,27 @@ def component_map_arrays(component_labels, parent_labels, max_labels=None):
     vc, vp = D.ingest(component_labels), D.ingest(parent_labels)
   _require_int(vc.dtype, "component_map")
   _require_int(vp.dtype, "component_map")
+  keys, pars, nl = component_map_device(vc.buf, vc.n, vc.dtype, vp.buf, vp.dtype, max_labels=max_labels)
+  return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
+
+
+def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None):
+  """K7 on flat device buffers: returns (keys_buf, parents_buf, n_labels), unordered."""
+  cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
   L = _L()
-  table = LabelTable(vc.dtype, _default_entries(vc.n, max_labels), 0)
+  table = LabelTable(cc_dtype, _default_entries(n, max_labels), 0)
 
   def build(t):
-    _lib.check(L.frb_component_build(D.ptr(vc.buf), vc.n, D.code(vc.dtype), 0, D.ptr(t.slots), t.cap, D.ptr(t.meta),
+    _lib.check(L.frb_component_build(D.ptr(cc_buf), n, D.code(cc_dtype), 0, D.ptr(t.slots), t.cap, D.ptr(t.meta),
                                      D.stream()), "frb_component_build")
 
   meta = _run_build(build, table)
   nl = int(meta[_lib.META_COUNT])
-  keys = D.alloc(nl * vc.dtype.itemsize)
-  pars = D.alloc(nl * vp.dtype.itemsize)
-  _lib.check(L.frb_component_gather(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.code(vc.dtype), D.ptr(vp.buf),
-                                    D.code(vp.dtype), 0, D.ptr(keys), D.ptr(pars), nl, D.stream()), "frb_component_gather")
-  return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
+  keys = D.alloc(nl * cc_dtype.itemsize)
+  pars = D.alloc(nl * parent_dtype.itemsize)
+  _lib.check(L.frb_component_gather(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.code(cc_dtype), D.ptr(parent_buf),
+                                    D.code(parent_dtype), 0, D.ptr(keys), D.ptr(pars), nl, D.stream()), "frb_component_gather")
+  return keys, pars, nl
 
 
 def component_map(component_labels, parent_labels):
@@ -604,13 +611,15 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
   w = dtype.itemsize
   c = D.code(dtype)
   L = _L()
-  mn = mx = None
-  if strategy is None or strategy == "dense":
-    mn, mx, _, _ = _scan(buf, n, dtype)
   if strategy is None:
-    strategy = "dense" if (mx - mn + 1) <= min(DENSE_MAX_BINS, max(4 * n, 1 << 16)) else "hash"
+    # The per-warp aggregating cache in front of the table makes the hash strategy as fast as the
+    # dense histogram, and it needs no min/max pre-pass over the volume.
+    strategy = "hash"
   if strategy == "dense":
+    mn, mx, _, _ = _scan(buf, n, dtype)
     bins = mx - mn + 1
+    if bins > DENSE_MAX_BINS:
+      raise ValueError("unique: dense strategy needs max - min < %d" % DENSE_MAX_BINS)
     min_bits = _to_bits(mn, dtype)
     counts = torch.zeros(bins, dtype=torch.int64, device=D.dev())
     _lib.check(L.frb_hist_dense(D.ptr(buf), n, c, min_bits, D.ptr(counts), bins, D.stream()), "frb_hist_dense")

@@ -91,6 +91,14 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
                : "l"(p));
   return r;
 }
+// same, for buffers that the kernel also writes (in-place relabel): no .nc
+__device__ __forceinline__ uint4 ld_stream16_rw(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 // streaming stores (written once, never re-read by this kernel)
 __device__ __forceinline__ void st_stream16(void* p, uint4 v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -273,6 +281,235 @@ __device__ __forceinline__ void block_add_to(u64* target, unsigned int v) {
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_sum, v);
   __syncthreads();
   if (threadIdx.x == 0 && s_sum) atomicAdd(target, (u64)s_sum);
+}
+
+}  // namespace frb
+
+// ------------------------------------------------------------------------------------------------
+// stream_rows: the common streaming loop of the volume kernels.
+//
+// HBM3e needs well over 100 KB of reads in flight per SM to run at full rate; registers cannot
+// hold that, so the volume is staged through shared memory by the TMA engine.  A CTA is 8 consumer
+// warps plus one producer warp.  The producer's elected lane issues one 1-D bulk copy
+// (cp.async.bulk, SASS UBLKCP) per 16 KiB tile -- large requests are what the TMA engine is fast
+// at -- into a STAGES-deep ring and arms the stage's "full" mbarrier with the byte count.  A
+// consumer warp waits on "full", reads its 4 rows of 32 x 16 B with conflict-free shared loads,
+// and arrives on the stage's "empty" mbarrier; the producer refills a stage once all 8 warps have
+// released it.  At 3-4 CTAs/SM x STAGES x 16 KiB this keeps 150-200 KB in flight per SM at no
+// register cost, and the copy carries the 16 bytes in front of the tile so that "the element
+// before mine" is always in the same staged bytes.
+//
+// Tile -> CTA assignment (TileMap): a CTA takes runs of `run` consecutive tiles (spatially
+// adjacent rows of the volume, which the per-warp label caches live on); consecutive runs of one
+// CTA are gridDim.x * run tiles apart, so all CTAs together stream through one compact window of
+// the array (DRAM page locality).
+//
+//   row_fn(u, cur, valid, i0, prev, has_prev)
+//     u        row of the warp-tile (0..STREAM_ROWS-1, a compile-time constant after unrolling)
+//     cur      the lane's 16-byte vector (V = 16/W elements)
+//     valid    false for lanes past the end of the array
+//     i0       flat element index of the lane's first element
+//     prev     the element preceding the lane's first element in memory order (exact across
+//              lanes, rows, tiles and CTAs: it comes out of the same staged bytes), valid iff has_prev
+//   tile_end(wstage, vb) is called once per warp-tile after its rows; `wstage` still holds the
+//     warp-tile (vector u*32+lane of it is what row_fn(u) saw), vb is its first vector index.
+//
+// REVERSE walks tiles and rows from the back (component_map keeps the LAST run start).
+// Kernels are launched with STREAM_THREADS threads; every lane of a consumer warp calls row_fn
+// (it may use warp-wide primitives); the producer warp returns from stream_rows without calling it.
+// ------------------------------------------------------------------------------------------------
+namespace frb {
+
+#ifndef FRB_STREAM_STAGES
+#define FRB_STREAM_STAGES 3
+#endif
+static constexpr int STREAM_ROWS = 4;
+static constexpr int STREAM_WARPS = 8;                                     // consumer warps
+static constexpr int STREAM_THREADS = (STREAM_WARPS + 1) * 32;             // + 1 producer warp
+static constexpr int STREAM_TILE_VECS = STREAM_WARPS * STREAM_ROWS * 32;   // 16-byte vectors per CTA tile (16 KiB)
+static constexpr int STREAM_STAGES = FRB_STREAM_STAGES;
+static constexpr int STREAM_STAGE_VECS = STREAM_TILE_VECS + 8;             // 128 B in front: predecessor vector + pad
+static constexpr int STREAM_SMEM_BYTES = STREAM_STAGES * STREAM_STAGE_VECS * 16 + 2 * STREAM_STAGES * 8;
+
+struct TileMap {
+  size_t tiles;   // tiles in the whole array
+  size_t run;     // consecutive tiles per run
+  size_t count;   // tiles owned by this CTA
+  __device__ __forceinline__ TileMap(size_t nvec, size_t run_) {
+    tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
+    run = run_ < 1 ? 1 : run_;
+    const size_t nruns = (tiles + run - 1) / run;
+    const size_t b = blockIdx.x, g = gridDim.x;
+    const size_t mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA
+    if (mine == 0) { count = 0; return; }
+    const size_t last_start = ((mine - 1) * g + b) * run;
+    const size_t last_len = tiles - last_start < run ? tiles - last_start : run;
+    count = (mine - 1) * run + last_len;
+  }
+};
+// walks the tiles of one CTA in ascending (or descending) order without divisions
+struct TileIter {
+  size_t r, o, run, last_len, nruns_mine;
+  template <bool REVERSE>
+  __device__ __forceinline__ void init(const TileMap& m) {
+    run = m.run;
+    nruns_mine = (m.count + m.run - 1) / m.run;
+    last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
+    if (REVERSE) { r = nruns_mine ? nruns_mine - 1 : 0; o = last_len ? last_len - 1 : 0; }
+    else { r = 0; o = 0; }
+  }
+  __device__ __forceinline__ size_t tile() const { return (r * gridDim.x + blockIdx.x) * run + o; }
+  template <bool REVERSE>
+  __device__ __forceinline__ void step() {
+    if (REVERSE) {
+      if (o == 0) { r--; o = run - 1; } else o--;
+    } else {
+      o++;
+      if (o == run) { o = 0; r++; }
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Polling an mbarrier is a shared-memory access; warps that spin on it steal shared-memory
+// bandwidth from the TMA engine that is trying to deliver their data, so back off between probes.
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned int ns = 32;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
+  }
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+                                            TileEndFn tile_end) {
+  constexpr int V = 16 / W;
+  constexpr int R = STREAM_ROWS;
+  constexpr int S = STREAM_STAGES;
+  extern __shared__ __align__(128) unsigned char frb_dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* ring = reinterpret_cast<uint4*>(frb_dyn_smem);
+  u64* full = reinterpret_cast<u64*>(frb_dyn_smem + (size_t)S * STREAM_STAGE_VECS * 16);
+  u64* empty = full + S;
+  const size_t ntiles = map.count;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], STREAM_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (ntiles == 0) return;
+
+  if (warp == STREAM_WARPS) {
+    // ---------------- producer: one elected lane feeds the ring
+    if (lane == 0) {
+      TileIter it;
+      it.template init<REVERSE>(map);
+      int s = 0;
+      uint32_t round = 0;
+      for (size_t k = 0; k < ntiles; k++) {
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);  // all 8 warps released the previous fill
+        const size_t vb = it.tile() * STREAM_TILE_VECS;
+        it.template step<REVERSE>();
+        size_t nv = nvec - vb < (size_t)STREAM_TILE_VECS ? nvec - vb : (size_t)STREAM_TILE_VECS;
+        uint4* dst = ring + (size_t)s * STREAM_STAGE_VECS + 8;
+        const uint4* src = a + vb;
+        if (NEED_PREV && vb > 0) { dst -= 1; src -= 1; nv += 1; }
+        const uint32_t bytes = (uint32_t)(nv * 16);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(dst, src, bytes, &full[s]);
+        if (++s == S) { s = 0; round++; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  TileIter it;
+  it.template init<REVERSE>(map);
+  int s = 0;
+  uint32_t round = 0;
+  for (size_t k = 0; k < ntiles; k++) {
+    const size_t t = it.tile();
+    it.template step<REVERSE>();
+    const size_t vb = t * STREAM_TILE_VECS + (size_t)warp * (R * 32);
+    mbar_wait(&full[s], round & 1u);
+    if (vb < nvec) {
+      const uint4* wstage = ring + (size_t)s * STREAM_STAGE_VECS + 8 + (size_t)warp * (R * 32);
+#pragma unroll
+      for (int uu = 0; uu < R; uu++) {
+        const int u = REVERSE ? R - 1 - uu : uu;
+        const int off = u * 32 + lane;
+        const size_t vi = vb + off;
+        const bool valid = vi < nvec;
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        u64 prev = 0;
+        bool has_prev = false;
+        if (valid) {
+          cur = wstage[off];
+          if (NEED_PREV && vi > 0) {
+            prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);  // element in front
+            has_prev = true;
+          }
+        }
+        row_fn(u, cur, valid, vi * V, prev, has_prev);
+      }
+      tile_end(wstage, vb);
+    }
+    __syncwarp();  // every lane of this warp is done with the stage
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == S) { s = 0; round++; }
+  }
+}
+
+// host side: tiles in an n-element array (+1 so that the CTA owning the scalar tail exists)
+inline size_t stream_tiles(size_t n, int w) { return (n / (16 / w) + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1; }
+int tile_run();  // tuning knob (frb_runtime.cu): consecutive tiles per CTA run
+
+// Persistent grid for a streaming kernel (STREAM_THREADS threads, STREAM_SMEM_BYTES of dynamic shared memory):
+// as many CTAs as are co-resident on the device, capped by the number of tiles.  Also opts the
+// kernel in to > 48 KiB of dynamic shared memory.
+template <typename Kernel>
+inline int stream_grid(Kernel kernel, size_t tiles) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, STREAM_THREADS, STREAM_SMEM_BYTES) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
+  size_t b = (size_t)per_sm * (size_t)sm_count();
+  if (tiles < 1) tiles = 1;
+  return (int)(b < tiles ? b : tiles);
 }
 
 }  // namespace frb

@@ -3,76 +3,19 @@
 // K7 replaces _component_map (fastremap.pyx:565-587).  The reference stores
 // remap[cc[i]] = parent[i] at every run start of cc in memory order, so for each label the LAST
 // run start wins.  Here every run start offers (i + 1) to the label's slot with atomicMax; the
-// gather pass then reads parent[] at the winning index.  CTAs walk the volume from the back so
-// that after the first few tiles almost every offer is already dominated and ends at the
-// 16-byte slot read without an atomic.
+// gather pass then reads parent[] at the winning index.  Warps walk their tiles from the back, so
+// the first offer a warp makes for a label is the largest it will ever make and the per-warp
+// "already offered" filter of frb_build.cuh drops the rest.
 #include "frb_internal.cuh"
+#include "frb_build.cuh"
 
 namespace frb {
 
-static constexpr int ROWS = 4;
-static constexpr int TILE_VECS = 8 * ROWS * 32;
-
 template <int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(STREAM_THREADS)
 k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
-                  u64* __restrict__ meta) {
-  constexpr int V = 16 / W;
-  const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
-  unsigned int inserted = 0;
-
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail first (it holds the largest indices)
-    for (size_t i = nvec * V; i < n; i++) {
-      const u64 key = ld_elem<W>(cc, i);
-      if (i == 0 || key != ld_elem<W>(cc, i - 1))
-        table_update<FRB_OP_MAX>(slots, mask, direct, meta, key, (u64)i + 1 + flat_offset, &inserted);
-    }
-  }
-  for (size_t tt = blockIdx.x; tt < tiles; tt += gridDim.x) {
-    u64 ovf = 0;
-    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
-    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) break;
-    const size_t t = tiles - 1 - tt;
-    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
-    uint4 v[ROWS];
-    bool valid[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const size_t vi = vbase + u * 32 + lane;
-      valid[u] = vi < nvec;
-      v[u] = valid[u] ? ld_stream16(cc + vi) : make_uint4(0, 0, 0, 0);
-    }
-    u64 carry = 0;
-    bool carry_ok = false;
-    if (vbase > 0 && vbase < nvec) {
-      carry = ld_elem<W>(cc, vbase * V - 1);
-      carry_ok = true;
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const u64 last = vec_get<W>(v[u], V - 1);
-      u64 prev = __shfl_up_sync(FRB_FULL_MASK, last, 1);
-      const u64 row_last = __shfl_sync(FRB_FULL_MASK, last, 31);
-      bool has_prev = true;
-      if (lane == 0) { prev = carry; has_prev = carry_ok; }
-      carry = row_last;
-      carry_ok = true;
-      if (valid[u]) {
-        const size_t i0 = (vbase + u * 32 + lane) * V;
-#pragma unroll
-        for (int j = 0; j < V; j++) {
-          const u64 key = vec_get<W>(v[u], j);
-          const bool head = !has_prev || key != prev;
-          prev = key;
-          has_prev = true;
-          if (head) table_update<FRB_OP_MAX>(slots, mask, direct, meta, key, (u64)(i0 + j) + 1 + flat_offset, &inserted);
-        }
-      }
-    }
-  }
-  block_add_to(&meta[FRB_META_COUNT], inserted);
+                  u64* __restrict__ meta, int run) {
+  build_pass<W, FRB_OP_MAX, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
 }
 
 template <int WC>
@@ -178,15 +121,15 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   const int direct = w <= 2 ? 1 : 0;
   if (direct && cap != frb_table_direct_cap(cc_dtype)) { set_error("frb_component_build: direct table needs cap == 2^bits"); return FRB_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)cc;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   switch (w) {
-    case 1: k_component_build<1><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
-    case 2: k_component_build<2><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
-    case 4: k_component_build<4><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
-    default: k_component_build<8><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, s, cap - 1, direct, m); break;
+    case 1: k_component_build<1><<<stream_grid(k_component_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
+    case 2: k_component_build<2><<<stream_grid(k_component_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
+    case 4: k_component_build<4><<<stream_grid(k_component_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
+    default: k_component_build<8><<<stream_grid(k_component_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
   }
   return check_launch("k_component_build");
 }

@@ -10,11 +10,9 @@
 // element is issued unconditionally so all V loads are in flight before the first compare.
 // The table is read-only here (ld.global.nc, L1-allocating); the volume streams past L1.
 #include "frb_internal.cuh"
+#include "frb_build.cuh"
 
 namespace frb {
-
-static constexpr int ROWS = 4;
-static constexpr int TILE_VECS = 8 * ROWS * 32;
 
 struct RelabelArgs {
   const Slot* slots;
@@ -50,40 +48,28 @@ __device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h,
 }
 
 template <int W, int WO, bool WIDE>
-__global__ void __launch_bounds__(256)
-k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A) {
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A, int run) {
   constexpr int V = 16 / W;
   const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
-  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
-    uint4 v[ROWS];
-    bool valid[ROWS];
+  auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
+    if (!valid) return;
+    u64 key[V], h[V], r[V];
+    Slot first[V];
 #pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const size_t vi = vbase + u * 32 + lane;
-      valid[u] = vi < nvec;
-      v[u] = valid[u] ? ld_stream16(src + vi) : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < V; j++) {
+      key[j] = vec_get<W>(cur, j);
+      h[j] = A.direct ? key[j] : (hash_key(key[j]) & A.mask);
+      first[j] = ld_slot_ro(A.slots + h[j]);
     }
 #pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      if (!valid[u]) continue;
-      const size_t i0 = (vbase + u * 32 + lane) * V;
-      u64 key[V], h[V], r[V];
-      Slot first[V];
-#pragma unroll
-      for (int j = 0; j < V; j++) {
-        key[j] = vec_get<W>(v[u], j);
-        h[j] = A.direct ? key[j] : (hash_key(key[j]) & A.mask);
-        first[j] = ld_slot_ro(A.slots + h[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < V; j++) r[j] = relabel_one(A, key[j], h[j], first[j], i0 + j);
-      if (WIDE) store_results<V, W>(dst_wide, i0, r);
-      if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
-    }
-  }
+    for (int j = 0; j < V; j++) r[j] = relabel_one(A, key[j], h[j], first[j], i0 + j);
+    if (WIDE) store_results<V, W>(dst_wide, i0, r);
+    if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, false, true>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(src, i);
@@ -98,8 +84,8 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
 
 template <int W, int WO, bool WIDE>
 static int launch_relabel(const void* src, void* dst_wide, void* dst_narrow, size_t n, const RelabelArgs& A, cudaStream_t st) {
-  Grid g = grid_for(n / (16 / W) + 1, TILE_VECS, 8);
-  k_relabel<W, WO, WIDE><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst_wide, dst_narrow, n, A);
+  const size_t tiles = stream_tiles(n, W);
+  k_relabel<W, WO, WIDE><<<stream_grid(k_relabel<W, WO, WIDE>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, dst_narrow, n, A, tile_run());
   return check_launch("k_relabel");
 }
 

@@ -7,21 +7,18 @@
 // numbering computed without the serial dependence: K1 records min(first index) per label with
 // 64-bit atomicMin, K2 sorts the L labels by that index.
 #include "frb_internal.cuh"
+#include "frb_build.cuh"
 
 namespace frb {
 
-static constexpr int ROWS = 4;                        // 16-byte rows per warp per tile
-static constexpr int TILE_VECS = 8 * ROWS * 32;       // 16-byte vectors per CTA tile (256 threads)
-
 // ------------------------------------------------------------------------------------------ K6
 template <int W, bool SIGNED>
-__global__ void __launch_bounds__(256)
-k_minmax_pairs(const uint4* __restrict__ a, size_t n, u64* __restrict__ out) {
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_minmax_pairs(const uint4* __restrict__ a, size_t n, u64* __restrict__ out, int run) {
   constexpr int V = 16 / W;
   typedef long long i64;
   const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
+  const int lane = threadIdx.x & 31;
   u64 umin = FRB_EMPTY, umax = 0;
   i64 smin = 0x7FFFFFFFFFFFFFFFll, smax = (i64)0x8000000000000000ull;
   unsigned long long pairs = 0, nonzero = 0;
@@ -38,43 +35,19 @@ k_minmax_pairs(const uint4* __restrict__ a, size_t n, u64* __restrict__ out) {
     pairs += (has_prev && key == prev) ? 1 : 0;
     nonzero += key != 0 ? 1 : 0;
   };
+  auto row_fn = [&](int, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const u64 key = vec_get<W>(cur, j);
+      consume(key, prev, has_prev);
+      prev = key;
+      has_prev = true;
+    }
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, true, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
 
-  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
-    uint4 v[ROWS];
-    bool valid[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const size_t vi = vbase + u * 32 + lane;
-      valid[u] = vi < nvec;
-      v[u] = valid[u] ? ld_stream16(a + vi) : make_uint4(0, 0, 0, 0);
-    }
-    u64 carry = 0;
-    bool carry_ok = false;
-    if (vbase > 0 && vbase < nvec) {
-      carry = ld_elem<W>(a, vbase * V - 1);
-      carry_ok = true;
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const u64 last = vec_get<W>(v[u], V - 1);
-      u64 prev = __shfl_up_sync(FRB_FULL_MASK, last, 1);
-      const u64 row_last = __shfl_sync(FRB_FULL_MASK, last, 31);
-      bool has_prev = true;
-      if (lane == 0) { prev = carry; has_prev = carry_ok; }
-      carry = row_last;
-      carry_ok = true;
-      if (valid[u]) {
-#pragma unroll
-        for (int j = 0; j < V; j++) {
-          const u64 key = vec_get<W>(v[u], j);
-          consume(key, prev, has_prev);
-          prev = key;
-          has_prev = true;
-        }
-      }
-    }
-  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(a, i);
@@ -119,72 +92,138 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 }
 
 // ------------------------------------------------------------------------------------------ K1
-// Every run head (a[i] != a[i-1], exact across lanes, rows and tiles) offers its flat index to
-// the table with atomicMin.  A head first reads its slot (16 B, L2-coherent): the common case
-// "label already present with a smaller index" ends there without an atomic.
+// First-index pass: the table receives, for every label, the minimum flat index at which it
+// occurs.  Offering ANY occurrence is correct (atomicMin); the work is in offering as few as
+// possible, because segmentation volumes repeat the same label for tens of voxels in every
+// direction.  Three filters sit between a voxel and the table, each exact:
+//   1. registers: a lane remembers the 16-byte vector it saw at the same position of its warp's
+//      previous tile (with the run-interleaved tile order that is the voxels one row up in y).  An
+//      element equal to the remembered one is dominated by an earlier offer of the same lane, and
+//      testing a whole vector costs 7 integer instructions for all V elements at once.
+//      Survivors get a second chance against their predecessor in memory (same argument).
+//   2. per-warp shared-memory set of labels the warp has already offered (phase-separated: all
+//      reads of a tile before all writes, so a hit always refers to an earlier tile = smaller index).
+//   3. the 16-byte slot itself: read first (L2-coherent), issued one tile ahead of its use so the
+//      round trip overlaps the streaming; "label present with a smaller index" ends there.
+// Only what survives all three reaches atomicCAS / atomicMin.
 template <int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
-                 u64 mask, int direct, u64* __restrict__ meta) {
+                 u64 mask, int direct, u64* __restrict__ meta, int run) {
   constexpr int V = 16 / W;
+  typedef typename UIntOf<W>::type T;
+  __shared__ u64 s_seen[8][BUILD_CACHE];
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
   unsigned int inserted = 0;
+  if (warp < STREAM_WARPS)
+    for (int i = lane; i < BUILD_CACHE; i += 32) s_seen[warp][i] = FRB_EMPTY;
+  __syncwarp();
 
-  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    // a full table aborts the pass (the host grows the table and retries)
-    u64 ovf = 0;
-    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
-    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) break;
-
-    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
-    uint4 v[ROWS];
-    bool valid[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const size_t vi = vbase + u * 32 + lane;
-      valid[u] = vi < nvec;
-      v[u] = valid[u] ? ld_stream16(a + vi) : make_uint4(0, 0, 0, 0);
-    }
-    u64 carry = 0;
-    bool carry_ok = false;
-    if (vbase > 0 && vbase < nvec) {
-      carry = ld_elem<W>(a, vbase * V - 1);
-      carry_ok = true;
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const u64 last = vec_get<W>(v[u], V - 1);
-      u64 prev = __shfl_up_sync(FRB_FULL_MASK, last, 1);
-      const u64 row_last = __shfl_sync(FRB_FULL_MASK, last, 31);
-      bool has_prev = true;
-      if (lane == 0) { prev = carry; has_prev = carry_ok; }
-      carry = row_last;
-      carry_ok = true;
-      if (valid[u]) {
-        const size_t i0 = (vbase + u * 32 + lane) * V;
-#pragma unroll
-        for (int j = 0; j < V; j++) {
-          const u64 key = vec_get<W>(v[u], j);
-          const bool head = !has_prev || key != prev;
-          prev = key;
-          has_prev = true;
-          if (head && !(skip_zero && key == 0))
-            table_update<FRB_OP_MIN>(slots, mask, direct, meta, key, (u64)(i0 + j) + flat_offset, &inserted);
-        }
-      }
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(a, i);
-      const bool head = i == 0 || key != ld_elem<W>(a, i - 1);
-      if (head && !(skip_zero && key == 0))
-        table_update<FRB_OP_MIN>(slots, mask, direct, meta, key, (u64)i + flat_offset, &inserted);
+      if (!(skip_zero && key == 0)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, (u64)i + flat_offset, &inserted);
     }
   }
+
+  uint4 last[STREAM_ROWS];
+  bool have_last = false;      // false until the warp has processed its first tile
+  u64 cand = 0;                // bit (u * V + j): element j of row u needs a closer look
+  bool aborted = false;
+  bool pend = false;           // one deferred offer per lane, resolved a tile later
+  u64 pkey = 0, pval = 0;
+  Slot pslot;
+  pslot.key = 0;
+  pslot.val = 0;
+
+  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
+    if (!valid) return;
+    const uint4 l = last[u];
+    last[u] = cur;
+    const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
+    if (d != 0 || !have_last) {
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        const u64 key = vec_get<W>(cur, j);
+        if ((!have_last || key != vec_get<W>(l, j)) && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
+      }
+    }
+  };
+
+  auto resolve_pending = [&]() {
+    if (pend) {
+      if (!(pslot.key == pkey && pslot.val <= pval)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, pkey, pval, &inserted);
+      pend = false;
+    }
+  };
+
+  auto tile_end = [&](const uint4* stage, size_t vb) {
+    have_last = true;
+    resolve_pending();
+    if (aborted) { cand = 0; }
+    // phase 1: which candidates has this warp not offered before?
+    u64 todo = 0;
+    for (u64 m = cand; m; m &= m - 1) {
+      const int b = __ffsll((long long)m) - 1;
+      const int u = b / V, j = b % V;
+      const T* ep = reinterpret_cast<const T*>(stage + u * 32 + lane) + j;
+      const u64 key = (u64)ep[0];
+      // second chance, independent of how rows of the volume line up with tiles: an element equal
+      // to its predecessor in memory is dominated by whatever happened to that predecessor
+      if ((vb + u * 32 + lane) * V + j > 0 && (u64)ep[-1] == key) continue;
+      const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
+      if (!hit) todo |= 1ull << b;
+    }
+    cand = 0;
+    __syncwarp();
+    // phase 2: remember them and queue / send the offers
+    for (u64 m = todo; m; m &= m - 1) {
+      const int b = __ffsll((long long)m) - 1;
+      const int u = b / V, j = b % V;
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
+      const u64 h = hash_key(key);
+      const u64 val = (u64)((vb + u * 32 + lane) * V + j) + flat_offset;
+      s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
+      if (!pend && key != FRB_EMPTY) {
+        pend = true;
+        pkey = key;
+        pval = val;
+        pslot = ld_slot_cg(slots + (direct ? key : (h & mask)));  // consumed at the next tile_end
+      } else {
+        offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, val, &inserted);
+      }
+    }
+    __syncwarp();
+    // a full table makes the rest of the pass pointless (the host grows the table and retries)
+    u64 ovf = 0;
+    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
+    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) aborted = true;
+  };
+
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, true, false>(a, nvec, map, row_fn, tile_end);
+  resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted);
+}
+
+// ------------------------------------------------------------------------------------------ probes
+// Calibration kernels: the same TMA-staged streaming loop with (almost) no arithmetic.
+// mode 0: read only (xor checksum); mode 1: read 16 B, write 16 B; mode 2: read 16 B, write 16 B + 8 B
+template <bool PREV>
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_stream_probe(const uint4* __restrict__ a, size_t nvec, void* wide, void* narrow, int mode, u64* out, int run) {
+  uint32_t acc = 0;
+  auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
+    if (!valid) return;
+    acc ^= cur.x ^ cur.y ^ cur.z ^ cur.w;
+    if (mode >= 1) st_stream16((char*)wide + i0 * 8, cur);
+    if (mode >= 2) st_stream8((char*)narrow + i0 * 4, make_uint2(cur.x, cur.z));
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<8, false, PREV, true>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
+  acc = __reduce_xor_sync(FRB_FULL_MASK, acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -224,12 +263,12 @@ int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* st
   k_minmax_init<<<1, 32, 0, st>>>((u64*)out, sg ? 1 : 0);
   int rc = check_launch("k_minmax_init");
   if (rc || n == 0) return rc;
-  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   u64* o = (u64*)out;
-#define FRB_LAUNCH(WW)                                                                     \
-  if (sg) k_minmax_pairs<WW, true><<<g.blocks, g.threads, 0, st>>>(p, n, o);               \
-  else k_minmax_pairs<WW, false><<<g.blocks, g.threads, 0, st>>>(p, n, o)
+#define FRB_LAUNCH(WW)                                                                                              \
+  if (sg) k_minmax_pairs<WW, true><<<stream_grid(k_minmax_pairs<WW, true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, tile_run());    \
+  else k_minmax_pairs<WW, false><<<stream_grid(k_minmax_pairs<WW, false>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, tile_run())
   switch (w) {
     case 1: FRB_LAUNCH(1); break;
     case 2: FRB_LAUNCH(2); break;
@@ -238,6 +277,19 @@ int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* st
   }
 #undef FRB_LAUNCH
   return check_launch("k_minmax_pairs");
+}
+
+int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_narrow, int mode, uint64_t* out, void* stream) {
+  if (!src || !out || !aligned16(src) || ((mode & 3) >= 1 && !dst_wide) || ((mode & 3) >= 2 && !dst_narrow)) { set_error("frb_stream_probe: bad arguments"); return FRB_ERR_BAD_ARG; }
+  const size_t nvec = nbytes / 16;
+  const size_t tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1;
+  if (mode & 4)
+    k_stream_probe<true><<<stream_grid(k_stream_probe<true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, tile_run());
+  else
+    k_stream_probe<false><<<stream_grid(k_stream_probe<false>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, tile_run());
+  return check_launch("k_stream_probe");
 }
 
 int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset, int skip_zero, void* slots,
@@ -251,15 +303,15 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   const int direct = w <= 2 ? 1 : 0;
   if (direct && cap != frb_table_direct_cap(dtype)) { set_error("frb_renumber_build: direct table needs cap == 2^bits"); return FRB_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   switch (w) {
-    case 1: k_renumber_build<1><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m); break;
-    case 2: k_renumber_build<2><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m); break;
-    case 4: k_renumber_build<4><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m); break;
-    default: k_renumber_build<8><<<g.blocks, g.threads, 0, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m); break;
+    case 1: k_renumber_build<1><<<stream_grid(k_renumber_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
+    case 2: k_renumber_build<2><<<stream_grid(k_renumber_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
+    case 4: k_renumber_build<4><<<stream_grid(k_renumber_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
+    default: k_renumber_build<8><<<stream_grid(k_renumber_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
   }
   return check_launch("k_renumber_build");
 }
@@ -294,7 +346,7 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
   if (rc) return rc;
   const int w = dtype_width(dtype);
   const u64 start_bits = trunc_width((u64)start, w);
-  Grid g = grid_for(capacity, 256 * 4, 8);
+  Grid g = grid_for(capacity, 256, 32);
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   switch (w) {

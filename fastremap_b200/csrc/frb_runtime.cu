@@ -27,6 +27,9 @@ int check_launch(const char* what) {
   return FRB_OK;
 }
 
+int g_tile_run = 64;
+int tile_run() { return g_tile_run; }
+
 int sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;
@@ -126,7 +129,7 @@ int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* 
 
 using namespace frb;
 
-namespace frb { extern int g_sm_count; }
+namespace frb { extern int g_sm_count; extern int g_tile_run; }
 
 extern "C" {
 
@@ -188,6 +191,8 @@ int frb_set_device(int device) {
   g_sm_count = 0;
   return FRB_OK;
 }
+
+void frb_set_tile_run(int run) { g_tile_run = run < 1 ? 1 : run; }
 
 uint64_t frb_launch_count(void) { return g_launches; }
 const char* frb_last_error(void) { return g_error; }

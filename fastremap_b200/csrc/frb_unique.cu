@@ -6,15 +6,12 @@
 //   dense  counts[label - min] += 1, then an ordered compaction of the non-empty bins
 //   hash   (label -> count) table, then a sort of the L distinct labels
 //   sort   radix sort of all N voxels, then run-length encode
-// The counting kernels aggregate before they touch memory: each lane first run-length encodes
-// its own 16-byte vector, then the warp merges equal labels with match.any + redux so that a
-// 512-byte row costs one atomic per distinct label instead of one per voxel.
+// The counting kernel aggregates before it touches memory (per-lane repeat counting in registers,
+// per-warp shared-memory (label, count) hash, then one global atomic per live entry): see k_hist.
 #include "frb_internal.cuh"
+#include "frb_build.cuh"
 
 namespace frb {
-
-static constexpr int ROWS = 4;
-static constexpr int TILE_VECS = 8 * ROWS * 32;
 
 struct DenseSink {
   u64* counts;
@@ -34,52 +31,103 @@ struct HashSink {
   }
 };
 
+static constexpr int HIST_CACHE = 256;        // (label, partial count) entries per warp
+static constexpr int HIST_FLUSH_TILES = 64;   // the per-warp table is flushed to memory this often
+
+// Counting pass.  Three levels of aggregation sit between a voxel and a global atomic:
+//   lane   remembers the 16-byte vector it saw at the same position of its warp's previous tile
+//          (one row up in the volume) and a repeat count; an identical vector just bumps the count
+//          (7 integer instructions for V voxels).  A different vector flushes the old one: equal
+//          neighbours inside the vector are merged and (label, multiplicity * repeats) is added to
+//   warp   a per-warp shared-memory hash of (label, partial count) updated with shared-memory
+//          atomics.  Entries are claimed with CAS and never change label between flushes, so a
+//          lane can add to an entry it has seen without locking; a label that finds its slot taken
+//          goes straight to memory.  Every HIST_FLUSH_TILES tiles (and at the end) the warp drains
+//          the table with one
+//   global atomic per live entry (dense bins or the label table, see the sinks above).
 template <int W, typename Sink>
-__global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target) {
+__global__ void __launch_bounds__(STREAM_THREADS) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
   constexpr int V = 16 / W;
+  __shared__ u64 s_key[8][HIST_CACHE];
+  __shared__ unsigned int s_cnt[8][HIST_CACHE];
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tiles = (nvec + TILE_VECS - 1) / TILE_VECS;
   unsigned int inserted = 0;
-  for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const size_t vbase = t * TILE_VECS + (size_t)warp * (ROWS * 32);
-    uint4 v[ROWS];
-    bool valid[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const size_t vi = vbase + u * 32 + lane;
-      valid[u] = vi < nvec;
-      v[u] = valid[u] ? ld_stream16(a + vi) : make_uint4(0, 0, 0, 0);
+  if (warp < STREAM_WARPS)
+    for (int i = lane; i < HIST_CACHE; i += 32) { s_key[warp][i] = FRB_EMPTY; s_cnt[warp][i] = 0; }
+  __syncwarp();
+
+  auto add = [&](u64 key, unsigned int c) {
+    const unsigned int e = (unsigned int)(hash_key(key) >> 48) & (HIST_CACHE - 1);
+    u64 ck = s_key[warp][e];
+    if (ck == FRB_EMPTY && key != FRB_EMPTY) {
+      const u64 old = atomicCAS(&s_key[warp][e], (u64)FRB_EMPTY, key);
+      ck = old == FRB_EMPTY ? key : old;
     }
+    if (ck == key && key != FRB_EMPTY) atomicAdd(&s_cnt[warp][e], c);
+    else sink(key, c, &inserted);
+  };
+  auto flush_vec = [&](const uint4& p, unsigned int reps) {
+    u64 key = vec_get<W>(p, 0);
+    unsigned int c = 1;
 #pragma unroll
-    for (int u = 0; u < ROWS; u++) {
-      const unsigned int m = __ballot_sync(FRB_FULL_MASK, valid[u]);
-      if (!valid[u]) continue;
-      // run-length encode the lane's V elements: the leading run is merged across the warp,
-      // later runs (label boundaries inside the vector, rare) go to the sink directly
-      const u64 k0 = vec_get<W>(v[u], 0);
-      u64 cur = k0;
-      unsigned int c = 1, lead = 0;
-      bool leading = true;
-#pragma unroll
-      for (int j = 1; j < V; j++) {
-        const u64 kj = vec_get<W>(v[u], j);
-        if (kj == cur) {
-          c++;
-        } else {
-          if (leading) { lead = c; leading = false; }
-          else sink(cur, c, &inserted);
-          cur = kj;
-          c = 1;
-        }
+    for (int j = 1; j < V; j++) {
+      const u64 kj = vec_get<W>(p, j);
+      if (kj == key) {
+        c++;
+      } else {
+        add(key, c * reps);
+        key = kj;
+        c = 1;
       }
-      if (leading) lead = c;
-      const unsigned int peers = __match_any_sync(m, k0);
-      const unsigned int total = __reduce_add_sync(peers, lead);
-      if (lane == __ffs(peers) - 1) sink(k0, total, &inserted);
-      if (!leading) sink(cur, c, &inserted);
     }
-  }
+    add(key, c * reps);
+  };
+
+  uint4 pat[STREAM_ROWS];
+  unsigned int rep[STREAM_ROWS];
+#pragma unroll
+  for (int u = 0; u < STREAM_ROWS; u++) { pat[u] = make_uint4(0, 0, 0, 0); rep[u] = 0; }
+  int tiles_since_flush = 0;
+
+  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
+    if (!valid) return;
+    const uint4 l = pat[u];
+    const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
+    if (d == 0 && rep[u] != 0) {
+      rep[u]++;
+    } else {
+      if (rep[u] != 0) flush_vec(l, rep[u]);
+      pat[u] = cur;
+      rep[u] = 1;
+    }
+  };
+  auto drain = [&]() {  // all lanes; no lane is inside add() while entries are reset
+    __syncwarp();
+    if (warp >= STREAM_WARPS) return;
+    for (int i = lane; i < HIST_CACHE; i += 32) {
+      const u64 k = s_key[warp][i];
+      if (k != FRB_EMPTY) {
+        sink(k, s_cnt[warp][i], &inserted);
+        s_key[warp][i] = FRB_EMPTY;
+        s_cnt[warp][i] = 0;
+      }
+    }
+    __syncwarp();
+  };
+  auto tile_end = [&](const uint4*, size_t) {
+    if (++tiles_since_flush == HIST_FLUSH_TILES) {
+      tiles_since_flush = 0;
+      drain();
+    }
+  };
+
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, false, false>(a, nvec, map, row_fn, tile_end);
+#pragma unroll
+  for (int u = 0; u < STREAM_ROWS; u++)
+    if (rep[u] != 0) flush_vec(pat[u], rep[u]);
+  drain();
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
   if (count_target) block_add_to(count_target, inserted);
@@ -240,13 +288,13 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   sink.min_bits = trunc_width(min_bits, w);
   sink.w = w;
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   switch (w) {
-    case 1: k_hist<1, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
-    case 2: k_hist<2, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
-    case 4: k_hist<4, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
-    default: k_hist<8, DenseSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, nullptr); break;
+    case 1: k_hist<1, DenseSink><<<stream_grid(k_hist<1, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
+    case 2: k_hist<2, DenseSink><<<stream_grid(k_hist<2, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
+    case 4: k_hist<4, DenseSink><<<stream_grid(k_hist<4, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
+    default: k_hist<8, DenseSink><<<stream_grid(k_hist<8, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
   }
   return check_launch("k_hist<dense>");
 }
@@ -262,14 +310,14 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   sink.meta = (u64*)meta;
   if (sink.direct && cap != frb_table_direct_cap(dtype)) { set_error("frb_hist_hash: direct table needs cap == 2^bits"); return FRB_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, TILE_VECS, 8);
+  const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
   switch (w) {
-    case 1: k_hist<1, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
-    case 2: k_hist<2, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
-    case 4: k_hist<4, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
-    default: k_hist<8, HashSink><<<g.blocks, g.threads, 0, st>>>(p, n, sink, ct); break;
+    case 1: k_hist<1, HashSink><<<stream_grid(k_hist<1, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
+    case 2: k_hist<2, HashSink><<<stream_grid(k_hist<2, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
+    case 4: k_hist<4, HashSink><<<stream_grid(k_hist<4, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
+    default: k_hist<8, HashSink><<<stream_grid(k_hist<8, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
   }
   return check_launch("k_hist<hash>");
 }

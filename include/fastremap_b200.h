@@ -160,9 +160,16 @@ int frb_synth_volume(void* out, int dtype, uint64_t nz, uint64_t ny, uint64_t nx
                      uint64_t gz, uint64_t gy, uint64_t gx, uint64_t seed, double zero_frac, double noise,
                      uint64_t cell_div, void* stream);
 
+/* calibration: the library's TMA-staged streaming loop with no arithmetic.  mode 0 reads nbytes
+ * (xor checksum into *out); mode 1 also writes them to dst_wide; mode 2 also writes half of them
+ * to dst_narrow (the 8 B read / 8 B + 4 B write shape of the renumber relabel pass). */
+int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_narrow, int mode, uint64_t* out, void* stream);
 /* bind this library's (statically linked) CUDA runtime to `device`; call once per process/thread
  * before the first launch when the caller's framework selected a device other than 0 */
 int frb_set_device(int device);
+/* tuning knob: consecutive 16 KiB tiles a CTA processes before it jumps ahead by gridDim.x runs
+ * (1 = grid-stride interleave, large = one contiguous chunk per CTA).  Default 64. */
+void frb_set_tile_run(int run);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t frb_launch_count(void);
 const char* frb_last_error(void);
