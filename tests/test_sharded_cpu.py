@@ -1,0 +1,102 @@
+"""
+N>1 host logic on CPU: world_size-2 gloo run of the sharded-renumber exchange
+(fastremap_b200/sharded.py: shard_offsets + allgather_varlen + merge-by-min + rank), with the
+per-shard kernels stood in by numpy, checked against the oracle's renumber of the whole volume.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _worker(rank, world, port, tmpdir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  sys.path.insert(0, ROOT)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from fastremap_b200 import sharded
+    from fastremap_b200.synth import synth_numpy
+    nz_total, ny, nx = 24, 20, 28
+    bounds = [0, 10, 24]  # unequal slabs: offsets must come from the exchanged counts
+    z0, z1 = bounds[rank], bounds[rank + 1]
+    slab = synth_numpy((z1 - z0, ny, nx), (5, 4, 6), np.uint64, seed=3, zero_frac=0.2, noise=0.1, z0=z0, nz_total=nz_total)
+    flat = slab.reshape(-1)
+    offset, total = sharded.shard_offsets(flat.size)
+    assert total == nz_total * ny * nx and offset == z0 * ny * nx
+
+    # stand-in for K1 + export: local (label, first global index), label 0 left out (preserve_zero)
+    keys, first = np.unique(flat, return_index=True)
+    keep = keys != 0
+    keys, first = keys[keep], first[keep] + offset
+    gk = sharded.allgather_varlen(torch.from_numpy(keys.view(np.int64)))
+    gv = sharded.allgather_varlen(torch.from_numpy(first.astype(np.int64)))
+    assert [t.numel() for t in gk] == [t.numel() for t in gv]
+    # stand-in for the merge (atomicMin per label) + K2 (rank by first index)
+    allk = np.concatenate([t.numpy().view(np.uint64) for t in gk])
+    allv = np.concatenate([t.numpy() for t in gv])
+    order = np.lexsort((allv, allk))
+    allk, allv = allk[order], allv[order]
+    lead = np.ones(allk.size, dtype=bool)
+    lead[1:] = allk[1:] != allk[:-1]
+    mk, mv = allk[lead], allv[lead]          # min first index per label
+    rank_order = np.argsort(mv, kind="stable")
+    ids = np.empty(mk.size, dtype=np.uint64)
+    ids[rank_order] = np.arange(1, mk.size + 1, dtype=np.uint64)
+    mapping = dict(zip(mk.tolist(), ids.tolist()))
+    mapping[0] = 0
+    # stand-in for K3 on the own slab
+    out = np.vectorize(mapping.get, otypes=[np.uint64])(flat)
+    np.save(os.path.join(tmpdir, "out_%d.npy" % rank), out)
+    if rank == 0:
+      np.save(os.path.join(tmpdir, "map_k.npy"), np.array(sorted(mapping), dtype=np.uint64))
+      np.save(os.path.join(tmpdir, "map_v.npy"), np.array([mapping[k] for k in sorted(mapping)], dtype=np.uint64))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_sharded_exchange_world2(oracle, tmp_path):
+  port = _free_port()
+  mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  from fastremap_b200.synth import synth_numpy
+  full = synth_numpy((24, 20, 28), (5, 4, 6), np.uint64, seed=3, zero_frac=0.2, noise=0.1)
+  e_out, e_map = oracle.renumber(np.copy(full))
+  got = np.concatenate([np.load(tmp_path / ("out_%d.npy" % r)) for r in range(2)]).reshape(full.shape)
+  assert np.array_equal(got.astype(e_out.dtype), e_out)
+  mk, mv = np.load(tmp_path / "map_k.npy"), np.load(tmp_path / "map_v.npy")
+  assert dict(zip(mk.tolist(), mv.tolist())) == e_map
+
+
+def test_allgather_varlen_handles_empty_rank(tmp_path):
+  port = _free_port()
+  mp.spawn(_empty_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _empty_worker(rank, world, port):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  sys.path.insert(0, ROOT)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from fastremap_b200 import sharded
+    t = torch.arange(5 * rank, dtype=torch.int64)  # rank 0 contributes nothing
+    parts = sharded.allgather_varlen(t)
+    assert [p.numel() for p in parts] == [0, 5]
+    assert parts[1].tolist() == [0, 1, 2, 3, 4]
+  finally:
+    dist.destroy_process_group()
