@@ -228,7 +228,7 @@ def run_ours(args):
 
   def step_device():
     if world > 1:
-      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True)
+      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True, offset=rank * n, total=world * n)
     return api.renumber_device(work, n, DTYPE, write_wide=True, timers=timers)
 
   def barrier():
@@ -297,7 +297,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     if world > 1:
       v = D.ingest(work_np)
-      r = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True)
+      r = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True, offset=rank * n, total=world * n)
       mapping = api._mapping_to_dict(r, v.dtype, True)
       D.download_into(r.wide, v.nbytes, D.flat_view(work_np))
       out = D.emit(r.out, r.out_dtype, v.shape, v.order, False)

@@ -46,14 +46,36 @@ def shard_offsets(n_local: int, group=None):
   return sum(c[:rank]), sum(c)
 
 
+def allgather_pairs(keys: torch.Tensor, vals: torch.Tensor, group=None):
+  """Variable-length all-gather of parallel (key, value) int64 lists with ONE count exchange and ONE
+  payload collective: every rank sends [keys | vals] padded to the longest list."""
+  world = dist.get_world_size(group)
+  n = keys.numel()
+  count = torch.tensor([n], dtype=torch.int64, device=keys.device)
+  counts = torch.zeros(world, dtype=torch.int64, device=keys.device)
+  dist.all_gather_into_tensor(counts, count, group=group)
+  counts_h = counts.cpu().tolist()
+  m = max(max(counts_h), 1)
+  packed = torch.zeros(2 * m, dtype=torch.int64, device=keys.device)
+  packed[:n] = keys
+  packed[m: m + n] = vals
+  out = torch.empty(world * 2 * m, dtype=torch.int64, device=keys.device)
+  dist.all_gather_into_tensor(out, packed, group=group)
+  ks = [out[r * 2 * m: r * 2 * m + counts_h[r]] for r in range(world)]
+  vs = [out[r * 2 * m + m: r * 2 * m + m + counts_h[r]] for r in range(world)]
+  return ks, vs
+
+
 def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                     group=None):
+                     group=None, offset=None, total=None):
   """Renumber this rank's slab consistently with the whole sharded volume.  Returns RenumberResult
-  (keys / ids hold the GLOBAL mapping, identical on every rank)."""
+  (keys / ids hold the GLOBAL mapping, identical on every rank).  offset / total (flat offset of the
+  slab, total voxels) are exchanged once here unless the caller already knows them."""
   from . import _lib
   from . import api
   from . import device as D
-  offset, total = shard_offsets(n_local, group)
+  if offset is None or total is None:
+    offset, total = shard_offsets(n_local, group)
 
   def merge(local: "api.LabelTable"):
     L = _lib.load()
@@ -61,8 +83,7 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     k64, v64 = D.alloc(nl * 8), D.alloc(nl * 8)
     _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), nl, D.stream()),
                "frb_table_export")
-    keys = allgather_varlen(k64[: nl * 8].view(torch.int64), group)
-    vals = allgather_varlen(v64[: nl * 8].view(torch.int64), group)
+    keys, vals = allgather_pairs(k64[: nl * 8].view(torch.int64), v64[: nl * 8].view(torch.int64), group)
     merged = api.LabelTable(dtype, sum(k.numel() for k in keys), _lib.EMPTY)
 
     def build(t):

@@ -98,5 +98,7 @@ def _empty_worker(rank, world, port):
     parts = sharded.allgather_varlen(t)
     assert [p.numel() for p in parts] == [0, 5]
     assert parts[1].tolist() == [0, 1, 2, 3, 4]
+    ks, vs = sharded.allgather_pairs(t, t * 10)
+    assert [k.tolist() for k in ks] == [[], [0, 1, 2, 3, 4]] and vs[1].tolist() == [0, 10, 20, 30, 40]
   finally:
     dist.destroy_process_group()
