@@ -15,7 +15,8 @@ SO_PATH = os.environ.get("FASTREMAP_B200_SO") or os.path.join(HERE, "libfastrema
 U8, U16, U32, U64, I8, I16, I32, I64 = range(8)
 OK, ERR_CUDA, ERR_BAD_ARG = 0, 3, 4
 META_WORDS = 16
-META_COUNT, META_OVERFLOW, META_SIDE_PRESENT, META_SIDE_VAL, META_MISSING_INDEX, META_LIST_COUNT = 0, 1, 2, 3, 4, 5
+META_COUNT, META_OVERFLOW, META_SIDE_PRESENT, META_SIDE_VAL, META_MISSING_INDEX, META_LIST_COUNT, META_ASSIGNED = 0, 1, 2, 3, 4, 5, 6
+RANK_TAG = 1 << 63
 OP_MIN, OP_MAX, OP_ADD, OP_SET = 0, 1, 2, 3
 MISS_KEEP, MISS_ERROR, MISS_FILL = 0, 1, 2
 EMPTY = 0xFFFFFFFFFFFFFFFF
@@ -39,8 +40,8 @@ SIGNATURES = {
   "frb_minmax_pairs": (_i, [_vp, _sz, _i, _vp, _vp]),
   "frb_renumber_build": (_i, [_vp, _sz, _i, _u64, _i, _vp, _u64, _vp, _vp]),
   "frb_renumber_rank_ws_bytes": (_sz, [_sz]),
-  "frb_renumber_rank": (_i, [_vp, _u64, _vp, _i, _i64, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
-  "frb_relabel": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _vp]),
+  "frb_renumber_rank": (_i, [_vp, _u64, _vp, _i, _i64, _u64, _u64, _vp, _vp, _sz, _vp, _sz, _vp]),
+  "frb_relabel": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _u64, _i, _vp]),
   "frb_replace_one": (_i, [_vp, _vp, _sz, _i, _u64, _u64, _vp]),
   "frb_remap_from_array": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
   "frb_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),

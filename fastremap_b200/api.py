@@ -92,6 +92,11 @@ class LabelTable:
   def read_meta(self) -> np.ndarray:
     return D.read_u64(self.meta)
 
+  def entries_max(self) -> int:
+    """Most labels this table is allowed to hold before it is grown (load factor 0.5; +1 for the
+    out-of-band all-ones key)."""
+    return self.cap + 1 if self.direct else self.cap // 2 + 2
+
   def overfull(self, meta) -> bool:
     if self.direct:
       return False
@@ -135,10 +140,10 @@ def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positio
 
 
 def _relabel(src_buf, n, dtype, table: LabelTable, policy, fill_bits=0, zero_fixed=False, dst_wide=None, dst_narrow=None,
-             narrow_width=0):
+             narrow_width=0, add=0, guard_overflow=False):
   _lib.check(_L().frb_relabel(D.ptr(src_buf), D.ptr(dst_wide), D.ptr(dst_narrow), narrow_width, n, D.code(dtype),
                               D.ptr(table.slots), table.cap, table.direct, D.ptr(table.meta), policy, fill_bits,
-                              1 if zero_fixed else 0, D.stream()), "frb_relabel")
+                              1 if zero_fixed else 0, add & _lib.EMPTY, 1 if guard_overflow else 0, D.stream()), "frb_relabel")
 
 
 def _cast(src_buf, src_dtype, dst_dtype, n):
@@ -220,6 +225,32 @@ def _ev(timers, name, which):
     timers.setdefault(name, [None, None])[which] = e
 
 
+class _RankBuffers:
+  """Mapping arrays (label / id, indexed by rank) and the K2 workspace, sized for a table."""
+
+  def __init__(self, table: LabelTable, dtype):
+    self.capacity = table.entries_max()
+    w = np.dtype(dtype).itemsize
+    self.keys = D.alloc(self.capacity * w)
+    self.ids = D.alloc(self.capacity * w)
+    self.ws_bytes = int(_L().frb_renumber_rank_ws_bytes(self.capacity))
+    self.ws = D.alloc(self.ws_bytes)
+
+
+def _rank(table: LabelTable, rb: _RankBuffers, dtype, start, index_base, index_count):
+  _lib.check(_L().frb_renumber_rank(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.code(dtype), int(np.int64(start)),
+                                    index_base, index_count, D.ptr(rb.keys), D.ptr(rb.ids), rb.capacity, D.ptr(rb.ws),
+                                    rb.ws_bytes, D.stream()), "frb_renumber_rank")
+
+
+def _out_dtype(dtype, start, nl):
+  """fastremap.pyx:253-255: fit to the NEXT id (typed, so it wraps in the array dtype) unless |start| is larger."""
+  factor = _to_py(int(np.int64(start)) + nl, dtype)
+  if abs(start) > abs(factor):
+    factor = start
+  return np.dtype(fit_dtype(dtype, factor))
+
+
 def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
                     flat_offset=0, total_n=None, merge=None, timers=None) -> RenumberResult:
   """
@@ -227,12 +258,15 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
     write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
     merge: optional callable(table) -> table run between K1 and K2 (multi-GPU key-table merge).
     timers: optional dict; receives CUDA event pairs "k1" / "k2" / "k3" recorded on the launching stream.
+  K1 and K2 are queued back to back (the label count stays on the device); the host reads the
+  table's meta block once, to choose the refit dtype before K3.
   """
   dtype = np.dtype(dtype)
   w = dtype.itemsize
   c = D.code(dtype)
   L = _L()
   table = LabelTable(dtype, _default_entries(n, max_labels), _lib.EMPTY)
+  index_count = max(int(total_n if total_n is not None else n + flat_offset), 1)
 
   def build(t):
     _ev(timers, "k1", 0)
@@ -240,36 +274,39 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
                                     D.ptr(t.meta), D.stream()), "frb_renumber_build")
     _ev(timers, "k1", 1)
 
-  meta = _run_build(build, table)
   if merge is not None:
+    _run_build(build, table)
     table = merge(table)
+    rb = _RankBuffers(table, dtype)
+    _ev(timers, "k2", 0)
+    _rank(table, rb, dtype, start, 0, index_count)
+    _ev(timers, "k2", 1)
     meta = table.read_meta()
-  nl = int(meta[_lib.META_COUNT])
+    if meta[_lib.META_OVERFLOW]:
+      raise FastremapB200Error("renumber: merged label table overflowed")
+  else:
+    while True:
+      rb = _RankBuffers(table, dtype)
+      build(table)
+      _ev(timers, "k2", 0)
+      _rank(table, rb, dtype, start, 0, index_count)
+      _ev(timers, "k2", 1)
+      meta = table.read_meta()
+      if not table.overfull(meta):
+        break
+      table.grow(int(meta[_lib.META_COUNT]))  # K3 has not run: the input is intact, start over
+  nl = int(meta[_lib.META_ASSIGNED])
 
-  keys = D.alloc(nl * w)
-  ids = D.alloc(nl * w)
-  ws_bytes = int(L.frb_renumber_rank_ws_bytes(nl))
-  ws = D.alloc(ws_bytes)
-  index_bits = max(int((total_n if total_n is not None else n + flat_offset)).bit_length(), 1)
-  _ev(timers, "k2", 0)
-  _lib.check(L.frb_renumber_rank(D.ptr(table.slots), table.cap, D.ptr(table.meta), c, int(np.int64(start)), index_bits,
-                                 D.ptr(keys), D.ptr(ids), nl, D.ptr(ws), ws_bytes, D.stream()), "frb_renumber_rank")
-  _ev(timers, "k2", 1)
-
-  # fastremap.pyx:253-255: fit to the NEXT id (typed, so it wraps in the array dtype) unless |start| is larger
-  factor = _to_py(int(np.int64(start)) + nl, dtype)
-  if abs(start) > abs(factor):
-    factor = start
-  out_dtype = np.dtype(fit_dtype(dtype, factor))
+  out_dtype = _out_dtype(dtype, start, nl)
   wo = out_dtype.itemsize
-
   res = RenumberResult()
-  res.keys, res.ids, res.n_labels, res.table, res.out_dtype = keys, ids, nl, table, out_dtype
+  res.keys, res.ids, res.n_labels, res.table, res.out_dtype = rb.keys, rb.ids, nl, table, out_dtype
   narrow = D.alloc(n * wo) if wo < w else None
   need_wide = write_wide or wo >= w
   wide_dst = src_buf if need_wide else None
   _ev(timers, "k3", 0)
-  _relabel(src_buf, n, dtype, table, _lib.MISS_ERROR, 0, preserve_zero, wide_dst, narrow, wo if narrow is not None else 0)
+  _relabel(src_buf, n, dtype, table, _lib.MISS_ERROR, 0, preserve_zero, wide_dst, narrow, wo if narrow is not None else 0,
+           add=int(np.int64(start)))
   _ev(timers, "k3", 1)
   res.wide = src_buf if need_wide else None
   if wo < w:
@@ -279,6 +316,131 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
   else:
     res.out = _cast(src_buf, dtype, out_dtype, n)
   return res
+
+
+# Host arrays at least this large are renumbered by the chunk pipeline below.
+STREAM_MIN_BYTES = 256 << 20
+STREAM_CHUNK_BYTES = 64 << 20
+STREAM_LOOKAHEAD = 2
+
+
+def _grow_rehash(table: LabelTable, dtype) -> LabelTable:
+  """A bigger table holding the same (label, value) pairs -- ranks and pending first indices alike."""
+  L = _L()
+  meta = table.read_meta()
+  count = int(meta[_lib.META_COUNT])
+  k64, v64 = D.alloc(count * 8), D.alloc(count * 8)
+  _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), count, D.stream()),
+             "frb_table_export")
+  new = LabelTable(dtype, 1, _lib.EMPTY)
+  new.cap = max(table.cap * 4, _pow2_at_least(4 * max(count, 1)))
+  new.slots = D.alloc(new.cap * 16)
+  new.clear()
+  _lib.check(L.frb_table_insert(D.ptr(k64), 8, D.ptr(v64), 8, 0, count, _lib.OP_SET, 0, D.ptr(new.slots), new.cap,
+                                D.ptr(new.meta), D.stream()), "frb_table_insert")
+  new.meta[_lib.META_ASSIGNED] = table.meta[_lib.META_ASSIGNED]
+  return new
+
+
+def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_labels):
+  """
+  renumber of a (large) host array as a chunk pipeline.  The id of a label depends only on the part
+  of the array in front of its first occurrence, so chunk c can be built, ranked and relabelled
+  (K1, K2, K3) as soon as it has arrived, while chunk c+1 is still on its way to the device and the
+  ids of chunk c-1 are on their way back: H2D, kernels and D2H run on three streams and the PCIe
+  link is busy in both directions.  Only the refit dtype needs the final label count, so the
+  narrowed copy is cast and downloaded at the end.
+  Returns (result array, mapping) like renumber().
+  """
+  L = _L()
+  dev = D.dev()
+  dtype = arr.dtype
+  w = dtype.itemsize
+  c = D.code(dtype)
+  n = arr.size
+  nbytes = n * w
+  order = "F" if arr.flags["F_CONTIGUOUS"] else "C"
+  host_u8 = D.as_torch_bytes(D.flat_view(arr))
+  chunk = max(STREAM_CHUNK_BYTES // 16 * 16, 16)
+  bounds = [(a, min(a + chunk, nbytes)) for a in range(0, nbytes, chunk)]
+  C = len(bounds)
+
+  cur = torch.cuda.current_stream()
+  s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+  dev_buf = D.alloc(nbytes)
+  table = LabelTable(dtype, _default_entries(n, max_labels), _lib.EMPTY)
+  rb = _RankBuffers(table, dtype)
+  flags = torch.zeros((C, _lib.META_WORDS), dtype=torch.int64, pin_memory=True)
+  s_in.wait_stream(cur)
+  s_out.wait_stream(cur)
+
+  ev_in, ev_meta, ev_k3 = [None] * C, [None] * C, [None] * C
+  with torch.cuda.stream(s_in):
+    for i, (a, b) in enumerate(bounds):
+      dev_buf[a:b].copy_(host_u8[a:b], non_blocking=True)
+      ev_in[i] = torch.cuda.Event()
+      ev_in[i].record(s_in)
+
+  add = int(np.int64(start))
+
+  def enqueue(i):
+    a, b = bounds[i]
+    ne = (b - a) // w
+    cur.wait_event(ev_in[i])
+    view = dev_buf[a:b]
+    _lib.check(L.frb_renumber_build(D.ptr(view), ne, c, a // w, 1 if preserve_zero else 0, D.ptr(table.slots), table.cap,
+                                    D.ptr(table.meta), D.stream()), "frb_renumber_build")
+    _rank(table, rb, dtype, start, a // w, ne)
+    flags[i].copy_(table.meta, non_blocking=True)
+    ev_meta[i] = torch.cuda.Event()
+    ev_meta[i].record(cur)
+    _relabel(view, ne, dtype, table, _lib.MISS_ERROR, 0, preserve_zero, view, None, 0, add=add, guard_overflow=True)
+    ev_k3[i] = torch.cuda.Event()
+    ev_k3[i].record(cur)
+
+  issued = done = 0
+  while done < C:
+    if issued < C and issued - done <= STREAM_LOOKAHEAD:
+      enqueue(issued)
+      issued += 1
+      continue
+    ev_meta[done].synchronize()
+    if int(flags[done, _lib.META_OVERFLOW]) != 0:
+      # table (or mapping arrays) too small: chunks >= done are untouched on the device (K2 / K3 are
+      # guarded by the overflow flag) -- move everything into a bigger table and redo from `done`
+      cur.synchronize()
+      table = _grow_rehash(table, dtype)
+      old = rb
+      rb = _RankBuffers(table, dtype)
+      rb.keys[: old.keys.numel()].copy_(old.keys)
+      rb.ids[: old.ids.numel()].copy_(old.ids)
+      issued = done
+      continue
+    if in_place_eff:
+      a, b = bounds[done]
+      s_out.wait_event(ev_k3[done])
+      with torch.cuda.stream(s_out):
+        host_u8[a:b].copy_(dev_buf[a:b], non_blocking=True)
+    done += 1
+
+  cur.synchronize()
+  meta = table.read_meta()
+  nl = int(meta[_lib.META_ASSIGNED])
+  res = RenumberResult()
+  res.keys, res.ids, res.n_labels, res.table = rb.keys, rb.ids, nl, table
+  res.out_dtype = out_dtype = _out_dtype(dtype, start, nl)
+  mapping = _mapping_to_dict(res, dtype, preserve_zero)
+  if out_dtype == dtype and in_place_eff:
+    s_out.synchronize()
+    return arr, mapping
+  out_buf = dev_buf if out_dtype == dtype else _cast(dev_buf, dtype, out_dtype, n)
+  out = D.host_empty(arr.shape, out_dtype, order)
+  out_u8 = D.as_torch_bytes(D.flat_view(out))
+  s_out.wait_stream(cur)
+  with torch.cuda.stream(s_out):
+    out_u8.copy_(out_buf[: out_u8.numel()], non_blocking=True)
+  s_out.synchronize()
+  return out, mapping
 
 
 def _mapping_to_dict(res: RenumberResult, dtype, preserve_zero) -> dict:
@@ -314,6 +476,10 @@ def renumber(arr, start=1, preserve_zero=True, in_place=False, *, max_labels=Non
     in_place_eff = v.aliases_input
   else:
     in_place_eff = bool(in_place) and (arr.flags["F_CONTIGUOUS"] or arr.flags["C_CONTIGUOUS"]) and arr.flags.writeable
+    if arr.nbytes >= STREAM_MIN_BYTES:
+      if not (arr.flags["F_CONTIGUOUS"] or arr.flags["C_CONTIGUOUS"]):
+        arr = np.copy(arr, order="C")
+      return _renumber_streamed(arr, start, preserve_zero, in_place_eff, max_labels)
     v = D.ingest(arr)
   res = renumber_device(v.buf, v.n, v.dtype, start=start, preserve_zero=preserve_zero, write_wide=in_place_eff,
                         max_labels=max_labels)

@@ -20,9 +20,11 @@ struct RelabelArgs {
   const u64* meta_ro;
   u64* meta;
   u64 fill;
+  u64 add;
   int direct;
   int policy;
   int zero_fixed;
+  int guard;
 };
 
 // result for one element whose home slot `first` has already been loaded
@@ -32,13 +34,14 @@ __device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h,
   u64 val = 0;
   if (first.key == key && key != FRB_EMPTY) {
     found = true;
-    val = first.val;
+    val = first.val + A.add;
   } else if (A.direct) {
     found = false;
   } else if (first.key == FRB_EMPTY && key != FRB_EMPTY) {
     found = false;
   } else {
     found = table_find_from(A.slots, A.mask, A.meta_ro, key, (h + (key == FRB_EMPTY ? 0 : 1)) & A.mask, &val);
+    val += A.add;
   }
   if (found) return A.policy == FRB_MISS_FILL ? key : val;
   if (A.policy == FRB_MISS_KEEP) return key;
@@ -52,6 +55,7 @@ __global__ void __launch_bounds__(STREAM_THREADS)
 k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A, int run) {
   constexpr int V = 16 / W;
   const size_t nvec = n / V;
+  if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;  // uniform: the flag is stable while this kernel runs
   auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
     if (!valid) return;
     u64 key[V], h[V], r[V];
@@ -193,7 +197,7 @@ extern "C" {
 
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill, int zero_fixed,
-                void* stream) {
+                uint64_t add, int guard_overflow, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (!dst_wide && !dst_narrow) ||
       (n && (!src || !aligned16(src) || (dst_wide && !aligned16(dst_wide)) || (dst_narrow && !aligned16(dst_narrow)))) ||
       policy < 0 || policy > 2) {
@@ -211,6 +215,8 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
   A.direct = direct ? 1 : 0;
   A.policy = policy;
   A.zero_fixed = zero_fixed ? 1 : 0;
+  A.add = add;
+  A.guard = guard_overflow ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (w) {
     case 1: return dispatch_relabel<1>(src, dst_wide, dst_narrow, narrow_width, n, A, st);

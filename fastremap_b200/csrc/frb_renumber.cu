@@ -5,7 +5,9 @@
 // find/insert half of _renumber :236-251.  The reference numbers labels in encounter order with
 // a serial counter; here id(label) = start + rank(first flat index of label), which is the same
 // numbering computed without the serial dependence: K1 records min(first index) per label with
-// 64-bit atomicMin, K2 sorts the L labels by that index.
+// 64-bit atomicMin, K2 (frb_rank.cu) sorts the labels by that index.  First indices are stored with
+// bit 63 set (FRB_RANK_TAG) so that they compare above every already assigned rank: ranking is
+// incremental and a volume may be built chunk by chunk.
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
 
@@ -123,7 +125,7 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(a, i);
-      if (!(skip_zero && key == 0)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, (u64)i + flat_offset, &inserted);
+      if (!(skip_zero && key == 0)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, FRB_RANK_TAG | ((u64)i + flat_offset), &inserted);
     }
   }
 
@@ -183,7 +185,7 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
       const int u = b / V, j = b % V;
       const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
       const u64 h = hash_key(key);
-      const u64 val = (u64)((vb + u * 32 + lane) * V + j) + flat_offset;
+      const u64 val = FRB_RANK_TAG | ((u64)((vb + u * 32 + lane) * V + j) + flat_offset);
       s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
       if (!pend && key != FRB_EMPTY) {
         pend = true;
@@ -224,29 +226,6 @@ k_stream_probe(const uint4* __restrict__ a, size_t nvec, void* wide, void* narro
   stream_rows<8, false, PREV, true>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
   acc = __reduce_xor_sync(FRB_FULL_MASK, acc);
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
-}
-
-// ------------------------------------------------------------------------------------------ K2
-// after the sort: rank r -> id; write the id into the table and emit the (label, id) mapping
-template <int W>
-__global__ void __launch_bounds__(256)
-k_assign_ids(const u64* __restrict__ payload, size_t L, Slot* __restrict__ slots, u64 cap, u64* __restrict__ meta,
-             u64 start_bits, void* __restrict__ keys_out, void* __restrict__ ids_out) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < L; r += stride) {
-    const u64 s = payload[r];
-    const u64 id = trunc_width(start_bits + (u64)r, W);  // counter arithmetic wraps in the array dtype
-    u64 key;
-    if (s == cap) {
-      key = FRB_EMPTY;
-      meta[FRB_META_SIDE_VAL] = id;
-    } else {
-      key = slots[s].key;
-      slots[s].val = id;
-    }
-    st_elem<W>(keys_out, r, key);
-    st_elem<W>(ids_out, r, id);
-  }
 }
 
 }  // namespace frb
@@ -314,48 +293,6 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
     default: k_renumber_build<8><<<stream_grid(k_renumber_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
   }
   return check_launch("k_renumber_build");
-}
-
-// workspace: 4 lists of `capacity` uint64 (sort key, payload, 2 ping-pong) + the radix histograms
-size_t frb_renumber_rank_ws_bytes(size_t capacity) {
-  const size_t c = capacity < 1 ? 1 : capacity;
-  return 4 * align_up(c * sizeof(u64), 256) + radix_hist_bytes(c);
-}
-
-int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, int index_bits,
-                      void* keys_out, void* ids_out, size_t capacity, void* ws, size_t ws_bytes, void* stream) {
-  if (!dtype_ok(dtype) || !slots || !meta || !ws || ws_bytes < frb_renumber_rank_ws_bytes(capacity) ||
-      (capacity && (!keys_out || !ids_out)) || index_bits < 1 || index_bits > 64) {
-    set_error("frb_renumber_rank: bad arguments");
-    return FRB_ERR_BAD_ARG;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t c = capacity < 1 ? 1 : capacity;
-  const size_t lb = align_up(c * sizeof(u64), 256);
-  char* base = (char*)ws;
-  u64* sort_keys = (u64*)(base);
-  u64* payload = (u64*)(base + lb);
-  u64* keys_alt = (u64*)(base + 2 * lb);
-  u64* pay_alt = (u64*)(base + 3 * lb);
-  void* hist = (void*)(base + 4 * lb);
-  int rc = launch_table_export((const Slot*)slots, cap, (u64*)meta, sort_keys, payload, capacity, 1, st);
-  if (rc) return rc;
-  // The caller sized `capacity` from meta[COUNT] after K1, so exactly `capacity` entries exist.
-  if (capacity == 0) return FRB_OK;
-  rc = radix_sort_u64(sort_keys, payload, keys_alt, pay_alt, capacity, 0, index_bits, hist, st);
-  if (rc) return rc;
-  const int w = dtype_width(dtype);
-  const u64 start_bits = trunc_width((u64)start, w);
-  Grid g = grid_for(capacity, 256, 32);
-  Slot* s = (Slot*)slots;
-  u64* m = (u64*)meta;
-  switch (w) {
-    case 1: k_assign_ids<1><<<g.blocks, g.threads, 0, st>>>(payload, capacity, s, cap, m, start_bits, keys_out, ids_out); break;
-    case 2: k_assign_ids<2><<<g.blocks, g.threads, 0, st>>>(payload, capacity, s, cap, m, start_bits, keys_out, ids_out); break;
-    case 4: k_assign_ids<4><<<g.blocks, g.threads, 0, st>>>(payload, capacity, s, cap, m, start_bits, keys_out, ids_out); break;
-    default: k_assign_ids<8><<<g.blocks, g.threads, 0, st>>>(payload, capacity, s, cap, m, start_bits, keys_out, ids_out); break;
-  }
-  return check_launch("k_assign_ids");
 }
 
 }  // extern "C"

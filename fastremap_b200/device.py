@@ -87,6 +87,14 @@ def read_u64(t: torch.Tensor) -> np.ndarray:
   return t.cpu().numpy().view(np.uint64)
 
 
+def as_torch_bytes(flat_np: np.ndarray) -> torch.Tensor:
+  """Zero-copy uint8 torch view of a contiguous 1-D numpy array (read-only arrays included)."""
+  b = flat_np.view(np.uint8) if flat_np.dtype != np.uint8 else flat_np
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    return torch.from_numpy(b)
+
+
 def upload_bytes(flat_np: np.ndarray) -> torch.Tensor:
   """Contiguous 1-D numpy array -> fresh 1-D uint8 device tensor (async when the source is pinned)."""
   b = flat_np.view(np.uint8) if flat_np.dtype != np.uint8 else flat_np

@@ -51,9 +51,12 @@ enum {
   FRB_META_SIDE_VAL = 3,     /* ... and this is its value                                 */
   FRB_META_MISSING_INDEX = 4,/* smallest flat index whose label was not in the table      */
   FRB_META_LIST_COUNT = 5,   /* entries written by export / rank / unique                 */
-  FRB_META_AUX0 = 6,
+  FRB_META_ASSIGNED = 6,     /* renumber: labels ranked so far (next rank to hand out)    */
   FRB_META_AUX1 = 7
 };
+/* renumber table values: FRB_RANK_TAG | first flat index while a label is unranked, its 0-based
+ * rank in encounter order afterwards (ranks compare below every tagged index). */
+#define FRB_RANK_TAG 0x8000000000000000ull
 enum { FRB_OP_MIN = 0, FRB_OP_MAX = 1, FRB_OP_ADD = 2, FRB_OP_SET = 3 };
 
 size_t frb_table_bytes(uint64_t cap);                 /* = cap * 16 */
@@ -85,14 +88,21 @@ int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* st
  * skip_zero != 0 (preserve_zero) leaves label 0 out of the table. */
 int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset, int skip_zero,
                        void* slots, uint64_t cap, uint64_t* meta, void* stream);
-/* K2 replaces the implicit `remap_id += 1` ordering (fastremap.pyx:244-246): labels are ranked
- * by first index; label of rank r gets id (T)(start + r) (arithmetic wraps in the array dtype,
- * :225) which overwrites the table value.  keys_out / ids_out (elements of the array dtype,
- * capacity `capacity`) receive the mapping in ascending-id order; meta[FRB_META_LIST_COUNT] the
- * count.  index_bits = number of significant bits in the stored first indices. */
+/* K2 replaces the implicit `remap_id += 1` ordering (fastremap.pyx:244-246).  Every label whose
+ * table value is still a tagged first index is ranked by that index; the label with the r-th
+ * smallest index gets rank meta[FRB_META_ASSIGNED] + r as its table value, and ASSIGNED advances.
+ * Ranking is incremental: build + rank may be repeated chunk by chunk in memory order (index_base =
+ * flat index of the chunk's first voxel, index_count = voxels in the chunk; only labels whose first
+ * index lies in [index_base, index_base + index_count) are ranked).
+ * keys_out / ids_out (elements of the array dtype, `capacity` entries, indexed by rank) receive
+ * label and id = (T)(start + rank) (arithmetic wraps in the array dtype, :225).  The count of newly
+ * ranked labels is left in meta[FRB_META_LIST_COUNT]; nothing is read back by the host.  If the
+ * table overflowed during the build, or capacity is too small, nothing is ranked and
+ * meta[FRB_META_OVERFLOW] is (left) set. */
 size_t frb_renumber_rank_ws_bytes(size_t capacity);
-int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, int index_bits,
-                      void* keys_out, void* ids_out, size_t capacity, void* ws, size_t ws_bytes, void* stream);
+int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, uint64_t index_base,
+                      uint64_t index_count, void* keys_out, void* ids_out, size_t capacity, void* ws, size_t ws_bytes,
+                      void* stream);
 
 /* ---- relabel -------------------------------------------------------------------------
  * K3 replaces the write half of _renumber (fastremap.pyx:240/:244/:248), _remap (:749-767),
@@ -103,11 +113,14 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
  *   policy: FRB_MISS_KEEP   missing label stays as it is           (preserve_missing_labels)
  *           FRB_MISS_ERROR  missing label: meta[MISSING_INDEX] = min(flat index); value kept
  *           FRB_MISS_FILL   missing label := fill; present labels stay as they are (mask_except)
- *   zero_fixed != 0: label 0 maps to 0 without a lookup (renumber's preserve_zero). */
+ *   zero_fixed != 0: label 0 maps to 0 without a lookup (renumber's preserve_zero).
+ *   add: added to every value found in the table (renumber: table value = rank, add = start).
+ *   guard_overflow != 0: do nothing if meta[FRB_META_OVERFLOW] is set (chunk pipelines launch the
+ *   relabel before the host has seen whether the build of that chunk overflowed). */
 enum { FRB_MISS_KEEP = 0, FRB_MISS_ERROR = 1, FRB_MISS_FILL = 2 };
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill,
-                int zero_fixed, void* stream);
+                int zero_fixed, uint64_t add, int guard_overflow, void* stream);
 /* single-pair compare-and-replace, the :721-729 fast path of _remap */
 int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream);
 /* remap_from_array (fastremap.pyx:771-791): dst[i] = src[i] < nvals ? vals[src[i]] : src[i] (unsigned dtypes) */

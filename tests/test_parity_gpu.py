@@ -281,3 +281,71 @@ def test_synth_device_equals_numpy_twin(frb, dtype):
   dp = synth_device((9, 17, 35), (3, 4, 5), dtype, cell_div=4, **kw)
   hp = synth((9, 17, 35), (3, 4, 5), dtype, cell_div=4, **kw)
   assert np.array_equal(dp.cpu().view(torch.uint8).numpy().view(dtype).reshape(hp.shape), hp)
+
+
+# ------------------------------------------------------------------ chunk pipeline of renumber (host arrays)
+
+
+@pytest.fixture
+def small_chunks(frb, monkeypatch):
+  """Force the H2D / K1-K2-K3 / D2H chunk pipeline on small arrays (chunks of 4 KiB)."""
+  from fastremap_b200 import api
+  monkeypatch.setattr(api, "STREAM_MIN_BYTES", 1)
+  monkeypatch.setattr(api, "STREAM_CHUNK_BYTES", 4096)
+  return api
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_renumber_streamed_vs_oracle(frb, oracle, small_chunks, dtype):
+  a = synth((24, 40, 56), (7, 9, 11), dtype, seed=int(np.dtype(dtype).num) + 40, zero_frac=0.15, noise=0.1)
+  for arr in (a, np.asfortranarray(a)):
+    for pz, start in ((True, 1), (False, 0), (True, 300), (False, -3 if np.issubdtype(dtype, np.signedinteger) else 7)):
+      for in_place in (False, True):
+        e_in, g_in = np.copy(arr, order="K"), np.copy(arr, order="K")
+        e_out, e_map = oracle.renumber(e_in, start=start, preserve_zero=pz, in_place=in_place)
+        g_out, g_map = frb.renumber(g_in, start=start, preserve_zero=pz, in_place=in_place)
+        assert g_out.dtype == e_out.dtype and g_out.shape == e_out.shape
+        assert np.array_equal(g_out, e_out) and g_map == e_map
+        assert g_out.flags.f_contiguous == e_out.flags.f_contiguous
+        assert np.array_equal(e_in, g_in)  # the caller's buffer: untouched, or ids at the old width
+
+
+def test_renumber_streamed_pinned_and_ragged(frb, oracle, small_chunks):
+  for n in (1, 17, 511, 512, 513, 4096 // 8 * 3 + 5, 100003):
+    a = synth((1, 1, n), (1, 1, max(n // 5, 1)), np.uint64, seed=n, zero_frac=0.1, noise=0.3).reshape(-1)
+    pinned = torch.empty(n, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    pinned[:] = a
+    e_in = np.copy(a)
+    e_out, e_map = oracle.renumber(e_in, in_place=True)
+    g_out, g_map = frb.renumber(pinned, in_place=True)
+    assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+    assert np.array_equal(pinned, e_in)
+
+
+def test_renumber_streamed_table_growth(frb, oracle, small_chunks):
+  """An undersized label table overflows in the middle of the pipeline: the table is rehashed into a
+  bigger one and the pipeline resumes from the chunk that overflowed."""
+  rng = np.random.default_rng(11)
+  a = rng.integers(0, 2 ** 63, size=40000, dtype=np.uint64)
+  a[3::3] = a[1:-2:3][: a[3::3].size]  # some repeats
+  for in_place in (False, True):
+    e_in, g_in = np.copy(a), np.copy(a)
+    e_out, e_map = oracle.renumber(e_in, in_place=in_place)
+    g_out, g_map = frb.renumber(g_in, in_place=in_place, max_labels=1)
+    assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+    assert np.array_equal(e_in, g_in)
+  # all-ones key and label 0 crossing chunk boundaries
+  b = np.full(5000, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+  b[1000:3000] = 0
+  b[2500:2600] = 5
+  e_out, e_map = oracle.renumber(np.copy(b), preserve_zero=False)
+  g_out, g_map = frb.renumber(np.copy(b), preserve_zero=False)
+  assert np.array_equal(g_out, e_out) and g_map == e_map
+
+
+def test_renumber_device_table_growth(frb, oracle):
+  rng = np.random.default_rng(12)
+  a = rng.integers(0, 2 ** 32, size=60000, dtype=np.uint32)
+  e_out, e_map = oracle.renumber(np.copy(a))
+  g_out, g_map = frb.renumber(np.copy(a), max_labels=1)
+  assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
