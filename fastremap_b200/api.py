@@ -320,7 +320,7 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
 
 # Host arrays at least this large are renumbered by the chunk pipeline below.
 STREAM_MIN_BYTES = 256 << 20
-STREAM_CHUNK_BYTES = 64 << 20
+STREAM_CHUNK_BYTES = 128 << 20
 STREAM_LOOKAHEAD = 2
 
 

@@ -31,6 +31,11 @@ __device__ __noinline__ void offer_slow(Slot* slots, u64 mask, int direct, u64* 
   table_update<OP>(slots, mask, direct, meta, key, v, inserted);
 }
 
+template <int OP>
+__device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v, unsigned int* inserted) {
+  return table_update<OP>(slots, mask, direct, meta, key, v, inserted);
+}
+
 // value offered for element i is i + bias  (MIN / forward: first occurrence; MAX / reverse: last run start)
 template <int W, int OP, bool REVERSE>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,

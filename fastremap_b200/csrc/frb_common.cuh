@@ -347,25 +347,36 @@ struct TileMap {
     count = (mine - 1) * run + last_len;
   }
 };
-// walks the tiles of one CTA in ascending (or descending) order without divisions
+// walks the tiles of one CTA in ascending (or descending) order with additions only
 struct TileIter {
-  size_t r, o, run, last_len, nruns_mine;
+  size_t t;      // current tile
+  size_t o;      // offset of the current tile inside its run
+  size_t run;    // tiles per run
+  size_t jump;   // distance from the last tile of a run to the first tile of this CTA's next run, minus 1
   template <bool REVERSE>
   __device__ __forceinline__ void init(const TileMap& m) {
     run = m.run;
-    nruns_mine = (m.count + m.run - 1) / m.run;
-    last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
-    if (REVERSE) { r = nruns_mine ? nruns_mine - 1 : 0; o = last_len ? last_len - 1 : 0; }
-    else { r = 0; o = 0; }
+    jump = ((size_t)gridDim.x - 1) * m.run;
+    const size_t nruns_mine = (m.count + m.run - 1) / m.run;
+    const size_t last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
+    if (REVERSE) {
+      const size_t r = nruns_mine ? nruns_mine - 1 : 0;
+      o = last_len ? last_len - 1 : 0;
+      t = (r * gridDim.x + blockIdx.x) * run + o;
+    } else {
+      o = 0;
+      t = (size_t)blockIdx.x * run;
+    }
   }
-  __device__ __forceinline__ size_t tile() const { return (r * gridDim.x + blockIdx.x) * run + o; }
+  __device__ __forceinline__ size_t tile() const { return t; }
   template <bool REVERSE>
   __device__ __forceinline__ void step() {
     if (REVERSE) {
-      if (o == 0) { r--; o = run - 1; } else o--;
+      if (o == 0) { o = run - 1; t -= jump + 1; } else { o--; t--; }
     } else {
       o++;
-      if (o == run) { o = 0; r++; }
+      t++;
+      if (o == run) { o = 0; t += jump; }
     }
   }
 };
@@ -466,8 +477,24 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     it.template step<REVERSE>();
     const size_t vb = t * STREAM_TILE_VECS + (size_t)warp * (R * 32);
     mbar_wait(&full[s], round & 1u);
-    if (vb < nvec) {
-      const uint4* wstage = ring + (size_t)s * STREAM_STAGE_VECS + 8 + (size_t)warp * (R * 32);
+    const uint4* wstage = ring + (size_t)s * STREAM_STAGE_VECS + 8 + (size_t)warp * (R * 32);
+    if (vb + R * 32 <= nvec) {
+      // whole warp-tile inside the array (all but the last tile): no per-lane bounds checks
+#pragma unroll
+      for (int uu = 0; uu < R; uu++) {
+        const int u = REVERSE ? R - 1 - uu : uu;
+        const int off = u * 32 + lane;
+        const uint4 cur = wstage[off];
+        u64 prev = 0;
+        bool has_prev = false;
+        if (NEED_PREV) {
+          has_prev = (vb + off) != 0;
+          if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);
+        }
+        row_fn(u, cur, true, (vb + off) * V, prev, has_prev);
+      }
+      tile_end(wstage, vb);
+    } else if (vb < nvec) {
 #pragma unroll
       for (int uu = 0; uu < R; uu++) {
         const int u = REVERSE ? R - 1 - uu : uu;

@@ -125,37 +125,51 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(a, i);
-      if (!(skip_zero && key == 0)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, FRB_RANK_TAG | ((u64)i + flat_offset), &inserted);
+      if (!(skip_zero && key == 0)) table_update_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, FRB_RANK_TAG | ((u64)i + flat_offset), &inserted);
     }
   }
 
   uint4 last[STREAM_ROWS];
   bool have_last = false;      // false until the warp has processed its first tile
   u64 cand = 0;                // bit (u * V + j): element j of row u needs a closer look
-  bool aborted = false;
+  // A full table makes the rest of the pass pointless (the host grows the table and retries): a lane
+  // stops offering once one of its own offers failed, or if the table had already overflowed when
+  // this launch started (chunk pipelines queue launches ahead of the host's overflow check).
+  bool aborted = *((volatile u64*)&meta[FRB_META_OVERFLOW]) != 0;
   bool pend = false;           // one deferred offer per lane, resolved a tile later
   u64 pkey = 0, pval = 0;
   Slot pslot;
   pslot.key = 0;
   pslot.val = 0;
 
-  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
+  auto offer = [&](u64 key, u64 val) {
+    if (!table_update_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, val, &inserted)) aborted = true;
+  };
+
+  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
     if (!valid) return;
     const uint4 l = last[u];
     last[u] = cur;
     const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
     if (d != 0 || !have_last) {
+      // rare path (a label boundary one row up, or the warp's first tile): keep the elements that
+      // differ from the remembered vector AND from their predecessor in memory -- an element equal
+      // to its predecessor is dominated by whatever happened to that predecessor
 #pragma unroll
       for (int j = 0; j < V; j++) {
         const u64 key = vec_get<W>(cur, j);
-        if ((!have_last || key != vec_get<W>(l, j)) && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
+        const bool differs_up = !have_last || key != vec_get<W>(l, j);
+        const bool differs_prev = !has_prev || key != prev;
+        if (differs_up && differs_prev && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
+        prev = key;
+        has_prev = true;
       }
     }
   };
 
   auto resolve_pending = [&]() {
     if (pend) {
-      if (!(pslot.key == pkey && pslot.val <= pval)) offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, pkey, pval, &inserted);
+      if (!(pslot.key == pkey && pslot.val <= pval)) offer(pkey, pval);
       pend = false;
     }
   };
@@ -163,17 +177,13 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
   auto tile_end = [&](const uint4* stage, size_t vb) {
     have_last = true;
     resolve_pending();
-    if (aborted) { cand = 0; }
+    if (aborted) cand = 0;
     // phase 1: which candidates has this warp not offered before?
     u64 todo = 0;
     for (u64 m = cand; m; m &= m - 1) {
-      const int b = __ffsll((long long)m) - 1;
-      const int u = b / V, j = b % V;
-      const T* ep = reinterpret_cast<const T*>(stage + u * 32 + lane) + j;
-      const u64 key = (u64)ep[0];
-      // second chance, independent of how rows of the volume line up with tiles: an element equal
-      // to its predecessor in memory is dominated by whatever happened to that predecessor
-      if ((vb + u * 32 + lane) * V + j > 0 && (u64)ep[-1] == key) continue;
+      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
+      const unsigned int u = b / V, j = b % V;
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
       const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
       if (!hit) todo |= 1ull << b;
     }
@@ -181,8 +191,8 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
     __syncwarp();
     // phase 2: remember them and queue / send the offers
     for (u64 m = todo; m; m &= m - 1) {
-      const int b = __ffsll((long long)m) - 1;
-      const int u = b / V, j = b % V;
+      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
+      const unsigned int u = b / V, j = b % V;
       const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
       const u64 h = hash_key(key);
       const u64 val = FRB_RANK_TAG | ((u64)((vb + u * 32 + lane) * V + j) + flat_offset);
@@ -193,14 +203,10 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
         pval = val;
         pslot = ld_slot_cg(slots + (direct ? key : (h & mask)));  // consumed at the next tile_end
       } else {
-        offer_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, val, &inserted);
+        offer(key, val);
       }
     }
     __syncwarp();
-    // a full table makes the rest of the pass pointless (the host grows the table and retries)
-    u64 ovf = 0;
-    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
-    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) aborted = true;
   };
 
   const TileMap map(nvec, (size_t)run);
