@@ -228,7 +228,7 @@ def run_ours(args):
 
   def step_device():
     if world > 1:
-      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True, offset=rank * n, total=world * n)
+      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True, offset=rank * n, total=world * n, timers=timers)
     return api.renumber_device(work, n, DTYPE, write_wide=True, timers=timers)
 
   def barrier():
@@ -248,7 +248,7 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   launches0 = _lib.launch_count()
-  step_ms, k3_ms, k1_ms, k2_ms = [], [], [], []
+  step_ms, k3_ms, k1_ms, k2_ms, merge_ms = [], [], [], [], []
   barrier()
   for _ in range(args.steps):
     work.copy_(pristine)          # un-timed restore (also rewrites 8 GiB: L2 holds nothing of the input)
@@ -263,6 +263,8 @@ def run_ours(args):
       k1_ms.append(timers["k1"][0].elapsed_time(timers["k1"][1]))
       k3_ms.append(timers["k3"][0].elapsed_time(timers["k3"][1]))
       k2_ms.append(timers["k2"][0].elapsed_time(timers["k2"][1]))
+      if "merge" in timers:
+        merge_ms.append(timers["merge"][0].elapsed_time(timers["merge"][1]))
     del res
   barrier()
   launches = _lib.launch_count() - launches0
@@ -280,6 +282,7 @@ def run_ours(args):
       print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": total_ms / args.steps,
                         "k1_ms": float(np.mean(k1_ms)) if k1_ms else None, "k3_ms": float(np.mean(k3_ms)) if k3_ms else None,
                         "k2_ms": float(np.mean(k2_ms)) if k2_ms else None,
+                        "merge_ms": float(np.mean(merge_ms)) if merge_ms else None,
                         "gpu_launches": int(launches), "labels": n_labels}))
     if world > 1:
       dist.destroy_process_group()
@@ -331,6 +334,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL * n,
                 "k1_build_ms": float(np.mean(k1_ms)), "k2_rank_ms": float(np.mean(k2_ms)),
+                "table_merge_ms": float(np.mean(merge_ms)) if merge_ms else None,
                 "whole_op": {"algorithmic_GBps": ALG_BYTES_PER_VOXEL * n / (total_ms / args.steps / 1e3) / 1e9,
                              "frac": ALG_BYTES_PER_VOXEL * n / (total_ms / args.steps / 1e3) / 1e9 / peak}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")

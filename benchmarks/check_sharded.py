@@ -48,6 +48,54 @@ def main():
       same = got.dtype == e_out.dtype and np.array_equal(got, e_out) and mapping == e_map
       print("sharded renumber %s world=%d labels=%d -> %s" % (np.dtype(dtype).name, world, len(e_map), "OK" if same else "MISMATCH"), flush=True)
       ok = ok and same
+
+    # ---- unique / component_map / remap / mask_except / minmax+pixel_pairs on the same slabs
+    from fastremap_b200 import _lib
+    n_local = (z1 - z0) * shape[1] * shape[2]
+    buf = slab.reshape(-1).view(torch.uint8).clone()
+    uniq, cts, nu = sharded.unique_sharded(buf, n_local, dtype)
+    g_u, g_c = D.download(uniq, nu, dtype), D.download(cts, nu, np.uint64)
+    pshape = shape
+    parent = synth_device((z1 - z0, shape[1], shape[2]), grid, np.uint32, seed=7, zero_frac=0.15, noise=0.0, z0=z0,
+                          nz_total=nz_total, cell_div=3).reshape(-1).view(torch.uint8).clone()
+    ck, cp, cn = sharded.component_map_sharded(buf, n_local, dtype, parent, np.uint32)
+    g_cm = dict(zip(D.download(ck, cn, dtype).tolist(), D.download(cp, cn, np.uint32).tolist()))
+    g_scan = sharded.scan_sharded(buf, n_local, dtype)
+    full = synth_numpy(shape, grid, dtype, seed=7, zero_frac=0.15, noise=0.05)
+    labels = np.unique(full)
+    keep = labels[::2]
+    kd = D.upload_array(keep)
+    work = buf.clone()
+    sharded.relabel_sharded(work, n_local, dtype, kd, kd, keep.size, _lib.MISS_FILL, fill_bits=0, offset=z0 * shape[1] * shape[2])
+    g_me = D.download(work, n_local, dtype)
+    vals = (keep.astype(np.uint64) % 251).astype(dtype)
+    vd = D.upload_array(vals)
+    work = buf.clone()
+    err = None
+    try:
+      sharded.relabel_sharded(work, n_local, dtype, kd, vd, keep.size, _lib.MISS_ERROR, offset=z0 * shape[1] * shape[2])
+    except KeyError as e:
+      err = e.args[0]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (g_me, err))
+    if rank == 0:
+      import oracle as orc
+      parent_full = synth_numpy(shape, grid, np.uint32, seed=7, zero_frac=0.15, noise=0.0, cell_div=3)
+      e_u, e_c = orc.unique(full, return_counts=True)
+      same_u = np.array_equal(g_u, e_u) and np.array_equal(g_c, e_c.astype(np.uint64))
+      same_cm = g_cm == orc.component_map(full, parent_full)
+      same_scan = g_scan[:3] == (*orc.minmax(full), orc.pixel_pairs(full))
+      e_me = orc.mask_except(np.copy(full), [int(x) for x in keep])
+      same_me = np.array_equal(np.concatenate([g[0] for g in gathered]).reshape(shape), e_me)
+      try:
+        orc.remap(np.copy(full), {int(k): int(v) for k, v in zip(keep, vals)}, preserve_missing_labels=False)
+        e_err = None
+      except KeyError as e:
+        e_err = e.args[0]
+      same_err = all(g[1] == e_err for g in gathered)
+      print("sharded unique/component_map/scan/mask_except/KeyError %s world=%d -> %s %s %s %s %s" % (
+        np.dtype(dtype).name, world, same_u, same_cm, same_scan, same_me, same_err), flush=True)
+      ok = ok and same_u and same_cm and same_scan and same_me and same_err
   flag = torch.tensor([1 if ok else 0], device="cuda")
   dist.broadcast(flag, 0)
   dist.destroy_process_group()

@@ -252,11 +252,10 @@ def _out_dtype(dtype, start, nl):
 
 
 def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                    flat_offset=0, total_n=None, merge=None, timers=None) -> RenumberResult:
+                    flat_offset=0, total_n=None, timers=None) -> RenumberResult:
   """
   K1 -> K2 -> K3 on a flat device buffer.
     write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
-    merge: optional callable(table) -> table run between K1 and K2 (multi-GPU key-table merge).
     timers: optional dict; receives CUDA event pairs "k1" / "k2" / "k3" recorded on the launching stream.
   K1 and K2 are queued back to back (the label count stays on the device); the host reads the
   table's meta block once, to choose the refit dtype before K3.
@@ -274,29 +273,23 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
                                     D.ptr(t.meta), D.stream()), "frb_renumber_build")
     _ev(timers, "k1", 1)
 
-  if merge is not None:
-    _run_build(build, table)
-    table = merge(table)
+  while True:
     rb = _RankBuffers(table, dtype)
+    build(table)
     _ev(timers, "k2", 0)
     _rank(table, rb, dtype, start, 0, index_count)
     _ev(timers, "k2", 1)
     meta = table.read_meta()
-    if meta[_lib.META_OVERFLOW]:
-      raise FastremapB200Error("renumber: merged label table overflowed")
-  else:
-    while True:
-      rb = _RankBuffers(table, dtype)
-      build(table)
-      _ev(timers, "k2", 0)
-      _rank(table, rb, dtype, start, 0, index_count)
-      _ev(timers, "k2", 1)
-      meta = table.read_meta()
-      if not table.overfull(meta):
-        break
-      table.grow(int(meta[_lib.META_COUNT]))  # K3 has not run: the input is intact, start over
-  nl = int(meta[_lib.META_ASSIGNED])
+    if not table.overfull(meta):
+      break
+    table.grow(int(meta[_lib.META_COUNT]))  # K3 has not run: the input is intact, start over
+  return _renumber_finish(src_buf, n, dtype, start, preserve_zero, write_wide, table, rb, meta, timers)
 
+
+def _renumber_finish(src_buf, n, dtype, start, preserve_zero, write_wide, table, rb, meta, timers=None) -> RenumberResult:
+  """K3 of renumber once the table holds ranks: pick the refit dtype, relabel (+ fused narrow store)."""
+  w = dtype.itemsize
+  nl = int(meta[_lib.META_ASSIGNED])
   out_dtype = _out_dtype(dtype, start, nl)
   wo = out_dtype.itemsize
   res = RenumberResult()

@@ -67,33 +67,232 @@ def allgather_pairs(keys: torch.Tensor, vals: torch.Tensor, group=None):
 
 
 def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                     group=None, offset=None, total=None):
+                     group=None, offset=None, total=None, timers=None):
   """Renumber this rank's slab consistently with the whole sharded volume.  Returns RenumberResult
   (keys / ids hold the GLOBAL mapping, identical on every rank).  offset / total (flat offset of the
-  slab, total voxels) are exchanged once here unless the caller already knows them."""
+  slab, total voxels) are exchanged once here unless the caller already knows them.
+
+  Two host round trips per call: one for the per-rank label counts (sizes of the exchange), one for
+  the merged label count (refit dtype) -- everything else is queued on the stream."""
   from . import _lib
   from . import api
   from . import device as D
+  L = _lib.load()
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  c = D.code(dtype)
+  world = dist.get_world_size(group)
   if offset is None or total is None:
     offset, total = shard_offsets(n_local, group)
 
-  def merge(local: "api.LabelTable"):
-    L = _lib.load()
-    nl = int(local.read_meta()[_lib.META_COUNT])
-    k64, v64 = D.alloc(nl * 8), D.alloc(nl * 8)
-    _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), nl, D.stream()),
-               "frb_table_export")
-    keys, vals = allgather_pairs(k64[: nl * 8].view(torch.int64), v64[: nl * 8].view(torch.int64), group)
-    merged = api.LabelTable(dtype, sum(k.numel() for k in keys), _lib.EMPTY)
+  local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), _lib.EMPTY)
+  while True:
+    cap_pairs = local.entries_max()
+    k64, v64 = D.alloc(cap_pairs * 8), D.alloc(cap_pairs * 8)
+    api._ev(timers, "k1", 0)
+    _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
+                                    local.cap, D.ptr(local.meta), D.stream()), "frb_renumber_build")
+    api._ev(timers, "k1", 1)
+    api._ev(timers, "merge", 0)
+    _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), cap_pairs,
+                                  D.stream()), "frb_table_export")
+    # every rank learns every rank's (count, overflow flag, exported pairs) in one small collective
+    metas = torch.empty(world * _lib.META_WORDS, dtype=torch.int64, device=local.meta.device)
+    dist.all_gather_into_tensor(metas, local.meta, group=group)
+    metas_h = metas.cpu().view(world, _lib.META_WORDS).tolist()            # host round trip 1
+    counts = [int(r[_lib.META_COUNT]) for r in metas_h]
+    overfull = [bool(r[_lib.META_OVERFLOW]) or (not local.direct and 2 * cnt > local.cap) for r, cnt in zip(metas_h, counts)]
+    if not any(overfull):
+      break
+    local.grow(max(counts))  # all ranks take the same decision: tables stay the same size everywhere
 
-    def build(t):
-      for k, v in zip(keys, vals):
-        if k.numel():
-          _lib.check(L.frb_table_insert(D.ptr(k), 8, D.ptr(v), 8, 0, k.numel(), _lib.OP_MIN, t.direct, D.ptr(t.slots),
-                                        t.cap, D.ptr(t.meta), D.stream()), "frb_table_insert")
+  m = max(max(counts), 1)
+  packed = torch.empty(2 * m * 8, dtype=torch.uint8, device=k64.device)
+  packed[: m * 8] = k64[: m * 8]
+  packed[m * 8:] = v64[: m * 8]
+  gathered = torch.empty(world * 2 * m * 8, dtype=torch.uint8, device=k64.device)
+  dist.all_gather_into_tensor(gathered, packed, group=group)
 
-    api._run_build(build, merged)
-    return merged
+  merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY)
+  for r in range(world):
+    if counts[r]:
+      kr = gathered[r * 2 * m * 8: r * 2 * m * 8 + counts[r] * 8]
+      vr = gathered[r * 2 * m * 8 + m * 8: r * 2 * m * 8 + m * 8 + counts[r] * 8]
+      _lib.check(L.frb_table_insert(D.ptr(kr), 8, D.ptr(vr), 8, 0, counts[r], _lib.OP_MIN, merged.direct, D.ptr(merged.slots),
+                                    merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert")
+  api._ev(timers, "merge", 1)
+  rb = api._RankBuffers(merged, dtype)
+  api._ev(timers, "k2", 0)
+  api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
+  api._ev(timers, "k2", 1)
+  meta = merged.read_meta()                                                # host round trip 2
+  if meta[_lib.META_OVERFLOW]:
+    raise api.FastremapB200Error("renumber_sharded: merged label table overflowed")
+  return api._renumber_finish(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, rb, meta, timers)
 
-  return api.renumber_device(src_buf, n_local, dtype, start=start, preserve_zero=preserve_zero, write_wide=write_wide,
-                             max_labels=max_labels, flat_offset=offset, total_n=total, merge=merge)
+
+# ------------------------------------------------------------------------------------ other ops
+# SURVEY 8(e): unique merges per-shard (label, count) lists by SUM, component_map per-shard
+# (label, parent) lists by "last shard wins" (= MAX of the run-start index, because every voxel of
+# rank r precedes every voxel of rank r+1), the remap family needs no data exchange (every rank
+# builds the same table; only the first-missing-index status is reduced), minmax / pixel_pairs
+# reduce a few scalars.
+
+
+def _export_pairs(table):
+  """All (key bits, value) pairs of a label table as two int64 device tensors."""
+  from . import _lib
+  from . import device as D
+  L = _lib.load()
+  nl = int(table.read_meta()[_lib.META_COUNT])
+  k64, v64 = D.alloc(nl * 8), D.alloc(nl * 8)
+  _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), nl, D.stream()),
+             "frb_table_export")
+  return k64[: nl * 8].view(torch.int64), v64[: nl * 8].view(torch.int64)
+
+
+def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
+  """unique(return_counts=True) of the whole sharded volume, replicated on every rank.
+  Returns (uniq_buf, counts_buf, n_unique) like api.unique_counts_device."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  L = _lib.load()
+  dtype = np.dtype(dtype)
+  local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), 0)
+
+  def build_local(t):
+    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()),
+               "frb_hist_hash")
+
+  api._run_build(build_local, local)
+  keys, counts = allgather_pairs(*_export_pairs(local), group)
+  merged = api.LabelTable(dtype, sum(k.numel() for k in keys), 0)
+
+  def build(t):
+    for k, v in zip(keys, counts):
+      if k.numel():
+        _lib.check(L.frb_table_insert(D.ptr(k), 8, D.ptr(v), 8, 0, k.numel(), _lib.OP_ADD, t.direct, D.ptr(t.slots),
+                                      t.cap, D.ptr(t.meta), D.stream()), "frb_table_insert")
+
+  meta = api._run_build(build, merged)
+  nu = int(meta[_lib.META_COUNT])
+  k64, v64 = _export_pairs(merged)
+  ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
+  ws = D.alloc(ws_bytes)
+  uniq, cts = D.alloc(nu * dtype.itemsize), D.alloc(nu * 8)
+  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, D.code(dtype), D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes,
+                                    D.stream()), "frb_sort_table_pairs")
+  return uniq, cts, nu
+
+
+def component_map_sharded(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=None, group=None):
+  """component_map of the whole sharded pair of volumes, replicated on every rank.
+  Returns (keys_buf, parents_buf, n_labels), unordered, like api.component_map_device."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  L = _lib.load()
+  cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
+  keys_l, pars_l, nl = api.component_map_device(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=max_labels)
+  # widen the raw bit patterns to 64 bits for the exchange
+  ucc, upar = np.dtype("u%d" % cc_dtype.itemsize), np.dtype("u%d" % parent_dtype.itemsize)
+  k64 = api._cast(keys_l, ucc, np.uint64, nl)[: nl * 8].view(torch.int64)
+  p64 = api._cast(pars_l, upar, np.uint64, nl)[: nl * 8].view(torch.int64)
+  keys, pars = allgather_pairs(k64, p64, group)
+  allk, allp = torch.cat(keys), torch.cat(pars)
+  total = allk.numel()
+  if total == 0:
+    return D.alloc(0), D.alloc(0), 0
+  # rank-major concatenation: the LAST occurrence of a label comes from the highest rank that saw
+  # it, i.e. from the largest run-start index -- positions + MAX, then resolve (like remap_from_array_kv)
+  t = api.table_from_arrays(allk, allp, total, np.uint64, op=_lib.OP_MAX, positions=True)
+  mk, mp = _export_pairs(t)
+  n = mk.numel()
+  keys_out = api._cast(mk.view(torch.uint8), np.uint64, ucc, n)
+  pars_out = api._cast(mp.view(torch.uint8), np.uint64, upar, n)
+  return keys_out, pars_out, n
+
+
+def relabel_sharded(buf, n_local, dtype, keys_dev, vals_dev, n_keys, policy, fill_bits=0, offset=0, message="{} was not in the remap table.",
+                    group=None):
+  """remap / mask / mask_except / remap_from_array_kv of this rank's slab, in place.  Every rank builds
+  the same table from the same (keys, values); no data is exchanged.  With the error policy the
+  first missing flat index is reduced (min) over the ranks and every rank raises the same KeyError."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  dtype = np.dtype(dtype)
+  t = api.table_from_arrays(keys_dev, vals_dev, n_keys, dtype, op=_lib.OP_SET) if n_keys else api.LabelTable(dtype, 1, 0)
+  api._relabel(buf, n_local, dtype, t, policy, fill_bits=fill_bits, dst_wide=buf)
+  if policy != _lib.MISS_ERROR:
+    return
+  idx = int(t.read_meta()[_lib.META_MISSING_INDEX])
+  label = 0
+  if idx != _lib.EMPTY:
+    w = dtype.itemsize
+    label = int(D.download(buf[idx * w:(idx + 1) * w], 1, np.dtype("u%d" % w))[0])
+    idx += offset
+  first = allreduce_first_missing(idx if idx != _lib.EMPTY else -1, label, group)
+  if first is not None:
+    raise KeyError(message.format(api._to_py(first, dtype)))
+
+
+def allreduce_first_missing(global_index: int, label_bits: int, group=None):
+  """Min-reduce of (first missing flat index, its label) over the ranks; global_index < 0 = none.
+  Returns the label bits of the globally first missing voxel, or None."""
+  world = dist.get_world_size(group)
+  dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+  big = (1 << 62)
+  mine = torch.tensor([global_index if global_index >= 0 else big, label_bits & 0x7FFFFFFFFFFFFFFF, (label_bits >> 63) & 1],
+                      dtype=torch.int64, device=dev)
+  allv = torch.zeros(world * 3, dtype=torch.int64, device=dev)
+  dist.all_gather_into_tensor(allv, mine, group=group)
+  rows = allv.cpu().view(world, 3).tolist()
+  best = min(rows, key=lambda r: r[0])
+  if best[0] >= big:
+    return None
+  return best[1] | (best[2] << 63)
+
+
+def scan_sharded(buf, n_local, dtype, group=None):
+  """(min, max, pixel_pairs, nonzero) of the whole sharded volume: local fused scan + a reduction of
+  the scalars; a pair that straddles a slab boundary is added from the exchanged edge voxels."""
+  from . import api
+  from . import device as D
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+  if n_local:
+    mn, mx, pairs, nz = api._scan(buf, n_local, dtype)
+    first = int(D.download(buf[:w], 1, np.dtype("u%d" % w))[0])
+    last = int(D.download(buf[(n_local - 1) * w: n_local * w], 1, np.dtype("u%d" % w))[0])
+  else:
+    mn = mx = pairs = nz = first = last = 0
+  return reduce_scan(mn, mx, pairs, nz, first, last, n_local, np.issubdtype(dtype, np.signedinteger), dev, group)
+
+
+def reduce_scan(mn, mx, pairs, nz, first_bits, last_bits, n_local, signed, dev, group=None):
+  """Reduction step of scan_sharded (device-agnostic: testable with gloo).  Returns
+  (min, max, pixel_pairs, nonzero) of the whole volume, (None, None, 0, 0) if it is empty."""
+  world = dist.get_world_size(group)
+
+  def split(v):  # two non-negative int64 halves of a 64-bit pattern (or of a signed value)
+    v &= 0xFFFFFFFFFFFFFFFF
+    return [v & 0xFFFFFFFF, v >> 32]
+
+  def join(lo, hi):
+    v = lo | (hi << 32)
+    return v - (1 << 64) if signed and v >> 63 else v
+
+  mine = torch.tensor([n_local, pairs, nz] + split(mn) + split(mx) + split(first_bits) + split(last_bits),
+                      dtype=torch.int64, device=dev)
+  allv = torch.zeros(world * mine.numel(), dtype=torch.int64, device=dev)
+  dist.all_gather_into_tensor(allv, mine, group=group)
+  live = [r for r in allv.cpu().view(world, mine.numel()).tolist() if r[0] > 0]
+  if not live:
+    return None, None, 0, 0
+  gmn = min(join(r[3], r[4]) for r in live)
+  gmx = max(join(r[5], r[6]) for r in live)
+  straddling = sum(1 for a, b in zip(live[:-1], live[1:]) if (a[9], a[10]) == (b[7], b[8]))
+  return gmn, gmx, sum(r[1] for r in live) + straddling, sum(r[2] for r in live)

@@ -102,3 +102,55 @@ def _empty_worker(rank, world, port):
     assert [k.tolist() for k in ks] == [[], [0, 1, 2, 3, 4]] and vs[1].tolist() == [0, 10, 20, 30, 40]
   finally:
     dist.destroy_process_group()
+
+
+def _reduce_worker(rank, world, port):
+  """unique (sum merge), component_map (last shard wins), KeyError status and minmax / pixel_pairs
+  reductions of fastremap_b200/sharded.py with the per-shard kernels stood in by numpy."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  sys.path.insert(0, ROOT)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from fastremap_b200 import sharded
+    rng = np.random.default_rng(5)
+    full = rng.integers(-40, 40, size=3000).astype(np.int64)
+    full[1000:1500] = full[999]          # a run that straddles the slab boundary at 1200
+    bounds = [0, 1200, 3000]
+    mine = full[bounds[rank]:bounds[rank + 1]]
+    dev = torch.device("cpu")
+    # minmax / pixel_pairs / nonzero
+    pairs = int(np.count_nonzero(mine[1:] == mine[:-1]))
+    got = sharded.reduce_scan(int(mine.min()), int(mine.max()), pairs, int(np.count_nonzero(mine)),
+                              int(mine[0]) & 0xFFFFFFFFFFFFFFFF, int(mine[-1]) & 0xFFFFFFFFFFFFFFFF, mine.size, True, dev)
+    assert got == (int(full.min()), int(full.max()), int(np.count_nonzero(full[1:] == full[:-1])), int(np.count_nonzero(full)))
+    u64 = np.array([2 ** 64 - 1, 5, 2 ** 63], dtype=np.uint64) if rank else np.array([7, 7], dtype=np.uint64)
+    got = sharded.reduce_scan(int(u64.min()), int(u64.max()), int(np.count_nonzero(u64[1:] == u64[:-1])), int(u64.size),
+                              int(u64[0]), int(u64[-1]), u64.size, False, dev)
+    assert got == (5, 2 ** 64 - 1, 1, 5)
+    # an empty shard takes no part
+    got = sharded.reduce_scan(3 if rank else 0, 9 if rank else 0, 2 if rank else 0, 4 if rank else 0, 3, 9, 4 if rank else 0, False, dev)
+    assert got == (3, 9, 2, 4)
+    # unique: per-shard (label, count) lists, merged by sum
+    k, c = np.unique(mine, return_counts=True)
+    ks, cs = sharded.allgather_pairs(torch.from_numpy(k), torch.from_numpy(c.astype(np.int64)))
+    merged = {}
+    for kk, cc in zip(ks, cs):
+      for a, b in zip(kk.tolist(), cc.tolist()):
+        merged[a] = merged.get(a, 0) + b
+    eu, ec = np.unique(full, return_counts=True)
+    assert merged == dict(zip(eu.tolist(), ec.tolist()))
+    # KeyError status: the globally first missing voxel wins on every rank
+    missing_local = np.flatnonzero(mine == 13)
+    gi = int(missing_local[0]) + bounds[rank] if missing_local.size else -1
+    first = sharded.allreduce_first_missing(gi, 13, None)
+    assert (first == 13) == bool(np.any(full == 13))
+    assert sharded.allreduce_first_missing(-1, 0, None) is None
+    assert sharded.allreduce_first_missing(10 - rank, (2 ** 64 - 1) if rank else 3, None) == 2 ** 64 - 1
+  finally:
+    dist.destroy_process_group()
+
+
+def test_sharded_reductions_world2():
+  port = _free_port()
+  mp.spawn(_reduce_worker, args=(2, port), nprocs=2, join=True)
