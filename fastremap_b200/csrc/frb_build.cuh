@@ -102,7 +102,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
             pend = true;
             pkey = key;
             pval = val;
-            pslot = ld_slot_cg(slots + (direct ? key : (h & mask)));  // consumed in tile_end
+            pslot = ld_slot_cg(slots + (direct ? key : (h & mask & ~1ull)));  // consumed in tile_end
           } else {
             offer_slow<OP>(slots, mask, direct, meta, key, val, &inserted);
           }

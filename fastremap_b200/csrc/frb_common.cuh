@@ -170,6 +170,10 @@ __device__ __forceinline__ u64 hash_key(u64 k) {
   k *= 0x9E3779B97F4A7C15ull;
   return k ^ (k >> 32);
 }
+// Home slot of a key.  Homes are EVEN: a probe sequence starts on a 32-byte pair of slots, so the
+// first two probes of a lookup are one 32-byte sector (one 256-bit load) -- the table behaves like
+// a bucketed table with 2 slots per bucket and linear probing over buckets.
+__device__ __forceinline__ u64 home_slot(u64 key, u64 mask) { return hash_key(key) & mask & ~1ull; }
 __host__ __device__ __forceinline__ u64 sign_extend(u64 v, int w) {
   const int sh = 64 - 8 * w;
   return (u64)(((long long)(v << sh)) >> sh);
@@ -189,6 +193,29 @@ __device__ __forceinline__ Slot ld_slot_cg(const Slot* s) {
 __device__ __forceinline__ Slot ld_slot_ro(const Slot* s) {
   Slot r;
   asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.key), "=l"(r.val) : "l"(s));
+  return r;
+}
+
+// L2-coherent one-shot slot read that the compiler may schedule early / batch (never use it to poll)
+__device__ __forceinline__ Slot ld_slot_cg_batch(const Slot* s) {
+  Slot r;
+  asm("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.key), "=l"(r.val) : "l"(s));
+  return r;
+}
+// same, but free to be scheduled early / batched by the compiler (pure load of a constant table)
+__device__ __forceinline__ Slot ld_slot_ro_batch(const Slot* s) {
+  Slot r;
+  asm("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.key), "=l"(r.val) : "l"(s));
+  return r;
+}
+
+// both slots of an (even-aligned) pair with one 256-bit load
+struct SlotPair {
+  Slot a, b;
+};
+__device__ __forceinline__ SlotPair ld_pair_ro(const Slot* s) {
+  SlotPair r;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a.key), "=l"(r.a.val), "=l"(r.b.key), "=l"(r.b.val) : "l"(s));
   return r;
 }
 
@@ -229,9 +256,9 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
     op_apply<OP>(&meta[FRB_META_SIDE_VAL], v);
     return true;
   }
-  u64 h = hash_key(key) & mask;
+  u64 h = home_slot(key, mask);
 #pragma unroll 1
-  for (int probe = 0; probe < FRB_MAX_PROBE; probe++) {
+  for (int probe = 0; probe < FRB_MAX_PROBE; probe++, h = (h + 1) & mask) {
     Slot* s = slots + h;
     Slot cur = ld_slot_cg(s);
     if (cur.key == key) {
@@ -250,13 +277,13 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
         return true;
       }
     }
-    h = (h + 1) & mask;
   }
   atomicExch(&meta[FRB_META_OVERFLOW], 1ull);
   return false;
 }
 
-// Read-only lookup.  Returns true and *val if found.
+// Read-only lookup, continuing at slot h of the key's (linear) probe sequence.  Returns true and
+// *val if found.
 __device__ __forceinline__ bool table_find_from(const Slot* slots, u64 mask, const u64* meta, u64 key, u64 h, u64* val) {
   if (key == FRB_EMPTY) {
     if (meta[FRB_META_SIDE_PRESENT]) { *val = meta[FRB_META_SIDE_VAL]; return true; }

@@ -27,47 +27,73 @@ struct RelabelArgs {
   int guard;
 };
 
-// result for one element whose home slot `first` has already been loaded
-__device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h, const Slot& first, size_t idx) {
-  if (A.zero_fixed && key == 0) return 0;
-  bool found;
-  u64 val = 0;
-  if (first.key == key && key != FRB_EMPTY) {
-    found = true;
-    val = first.val + A.add;
-  } else if (A.direct) {
-    found = false;
-  } else if (first.key == FRB_EMPTY && key != FRB_EMPTY) {
-    found = false;
-  } else {
-    found = table_find_from(A.slots, A.mask, A.meta_ro, key, (h + (key == FRB_EMPTY ? 0 : 1)) & A.mask, &val);
-    val += A.add;
-  }
-  if (found) return A.policy == FRB_MISS_FILL ? key : val;
+// what to store for a label that is / is not in the table
+__device__ __forceinline__ u64 relabel_hit(const RelabelArgs& A, u64 key, u64 val) {
+  return A.policy == FRB_MISS_FILL ? key : val + A.add;
+}
+__device__ __forceinline__ u64 relabel_miss(const RelabelArgs& A, u64 key, size_t idx) {
   if (A.policy == FRB_MISS_KEEP) return key;
   if (A.policy == FRB_MISS_FILL) return A.fill;
   atomicMin(&A.meta[FRB_META_MISSING_INDEX], (u64)idx);
   return key;
 }
 
+// The first load of a lookup: one 16-byte slot of a direct table, or the 32-byte home PAIR of a
+// hashed table (homes are even, see home_slot): the first two probes for the price of one sector.
+struct Probe {
+  Slot a, b;
+};
+template <bool HASHED>
+__device__ __forceinline__ Probe first_probe(const RelabelArgs& A, u64 key, u64* h) {
+  Probe p;
+  if (!HASHED || A.direct) {
+    *h = key;
+    p.a = ld_slot_ro(A.slots + key);
+    p.b.key = FRB_EMPTY;
+    p.b.val = 0;
+  } else {
+    *h = home_slot(key, A.mask);
+    const SlotPair sp = ld_pair_ro(A.slots + *h);
+    p.a = sp.a;
+    p.b = sp.b;
+  }
+  return p;
+}
+
+// result for one element whose first probe has already been loaded
+template <bool HASHED>
+__device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h, const Probe& p, size_t idx) {
+  if (A.zero_fixed && key == 0) return 0;
+  if (key != FRB_EMPTY) {
+    if (p.a.key == key) return relabel_hit(A, key, p.a.val);
+    if (!HASHED || A.direct || p.a.key == FRB_EMPTY) return relabel_miss(A, key, idx);
+    if (p.b.key == key) return relabel_hit(A, key, p.b.val);
+    if (p.b.key == FRB_EMPTY) return relabel_miss(A, key, idx);
+  }
+  // rare: the all-ones key (meta block) or a probe sequence longer than the home pair
+  u64 val = 0;
+  if (table_find_from(A.slots, A.mask, A.meta_ro, key, key == FRB_EMPTY ? h : ((h + 2) & A.mask), &val)) return relabel_hit(A, key, val);
+  return relabel_miss(A, key, idx);
+}
+
 template <int W, int WO, bool WIDE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A, int run) {
   constexpr int V = 16 / W;
+  constexpr bool HASHED = W >= 4;  // 8/16-bit dtypes use direct tables
   const size_t nvec = n / V;
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;  // uniform: the flag is stable while this kernel runs
   auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
     if (!valid) return;
     u64 key[V], h[V], r[V];
-    Slot first[V];
+    Probe first[V];
 #pragma unroll
     for (int j = 0; j < V; j++) {
       key[j] = vec_get<W>(cur, j);
-      h[j] = A.direct ? key[j] : (hash_key(key[j]) & A.mask);
-      first[j] = ld_slot_ro(A.slots + h[j]);
+      first[j] = first_probe<HASHED>(A, key[j], &h[j]);
     }
 #pragma unroll
-    for (int j = 0; j < V; j++) r[j] = relabel_one(A, key[j], h[j], first[j], i0 + j);
+    for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
     if (WIDE) store_results<V, W>(dst_wide, i0, r);
     if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
   };
@@ -77,9 +103,9 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(src, i);
-      const u64 h = A.direct ? key : (hash_key(key) & A.mask);
-      const Slot first = ld_slot_ro(A.slots + h);
-      const u64 r = relabel_one(A, key, h, first, i);
+      u64 h;
+      const Probe first = first_probe<HASHED>(A, key, &h);
+      const u64 r = relabel_one<HASHED>(A, key, h, first, i);
       if (WIDE) st_elem<W>(dst_wide, i, r);
       if (WO > 0) st_elem<(WO > 0 ? WO : 1)>(dst_narrow, i, r);
     }

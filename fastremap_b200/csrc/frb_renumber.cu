@@ -201,7 +201,7 @@ k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int ski
         pend = true;
         pkey = key;
         pval = val;
-        pslot = ld_slot_cg(slots + (direct ? key : (h & mask)));  // consumed at the next tile_end
+        pslot = ld_slot_cg(slots + (direct ? key : (h & mask & ~1ull)));  // consumed at the next tile_end
       } else {
         offer(key, val);
       }

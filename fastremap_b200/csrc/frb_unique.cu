@@ -20,6 +20,9 @@ struct DenseSink {
   __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int*) const {
     atomicAdd(&counts[trunc_width(key - min_bits, w)], (u64)c);
   }
+  // two-step form used by the drain: nothing to look up for a dense bin
+  __device__ __forceinline__ Slot peek(u64) const { Slot s; s.key = 0; s.val = 0; return s; }
+  __device__ __forceinline__ void commit(u64 key, unsigned int c, const Slot&, unsigned int* ins) const { (*this)(key, c, ins); }
 };
 struct HashSink {
   Slot* slots;
@@ -29,10 +32,21 @@ struct HashSink {
   __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int* inserted) const {
     table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
   }
+  // two-step form used by the drain: the home slots of all of a lane's entries are read first (the
+  // L2 round trips overlap), then a label already sitting in its home slot costs one fire-and-forget
+  // atomic; anything else takes the probing path
+  __device__ __forceinline__ Slot peek(u64 key) const {
+    return ld_slot_cg_batch(slots + (direct ? key : home_slot(key, mask)));
+  }
+  __device__ __forceinline__ void commit(u64 key, unsigned int c, const Slot& home, unsigned int* inserted) const {
+    if (home.key == key && key != FRB_EMPTY) atomicAdd(&slots[direct ? key : home_slot(key, mask)].val, (u64)c);
+    else table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
+  }
 };
 
 static constexpr int HIST_CACHE = 256;        // (label, partial count) entries per warp
-static constexpr int HIST_FLUSH_TILES = 64;   // the per-warp table is flushed to memory this often
+static constexpr int HIST_FLUSH_TILES = 64;   // the per-warp table is flushed to memory at least this often
+static constexpr int HIST_FLUSH_CLAIMS = 160; // ... and as soon as this many of its entries are taken
 
 // Counting pass.  Three levels of aggregation sit between a voxel and a global atomic:
 //   lane   remembers the 16-byte vector it saw at the same position of its warp's previous tile
@@ -46,7 +60,7 @@ static constexpr int HIST_FLUSH_TILES = 64;   // the per-warp table is flushed t
 //          the table with one
 //   global atomic per live entry (dense bins or the label table, see the sinks above).
 template <int W, typename Sink>
-__global__ void __launch_bounds__(STREAM_THREADS) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
+__global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
   constexpr int V = 16 / W;
   __shared__ u64 s_key[8][HIST_CACHE];
   __shared__ unsigned int s_cnt[8][HIST_CACHE];
@@ -57,12 +71,14 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_hist(const uint4* __restrict
     for (int i = lane; i < HIST_CACHE; i += 32) { s_key[warp][i] = FRB_EMPTY; s_cnt[warp][i] = 0; }
   __syncwarp();
 
+  unsigned int claimed = 0;  // entries this lane has claimed since the last drain
   auto add = [&](u64 key, unsigned int c) {
     const unsigned int e = (unsigned int)(hash_key(key) >> 48) & (HIST_CACHE - 1);
     u64 ck = s_key[warp][e];
     if (ck == FRB_EMPTY && key != FRB_EMPTY) {
       const u64 old = atomicCAS(&s_key[warp][e], (u64)FRB_EMPTY, key);
       ck = old == FRB_EMPTY ? key : old;
+      claimed += old == FRB_EMPTY ? 1u : 0u;
     }
     if (ck == key && key != FRB_EMPTY) atomicAdd(&s_cnt[warp][e], c);
     else sink(key, c, &inserted);
@@ -105,18 +121,35 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_hist(const uint4* __restrict
   auto drain = [&]() {  // all lanes; no lane is inside add() while entries are reset
     __syncwarp();
     if (warp >= STREAM_WARPS) return;
-    for (int i = lane; i < HIST_CACHE; i += 32) {
-      const u64 k = s_key[warp][i];
-      if (k != FRB_EMPTY) {
-        sink(k, s_cnt[warp][i], &inserted);
-        s_key[warp][i] = FRB_EMPTY;
-        s_cnt[warp][i] = 0;
+    constexpr int BATCH = 4;  // home-slot reads in flight per lane (registers: 7 per entry)
+#pragma unroll 1
+    for (int q0 = 0; q0 < HIST_CACHE / 32; q0 += BATCH) {
+      u64 k[BATCH];
+      unsigned int cnt[BATCH];
+      Slot home[BATCH];
+#pragma unroll
+      for (int q = 0; q < BATCH; q++) {
+        const int e = (q0 + q) * 32 + lane;
+        k[q] = s_key[warp][e];
+        cnt[q] = s_cnt[warp][e];
+        if (k[q] != FRB_EMPTY) {
+          home[q] = sink.peek(k[q]);
+          s_key[warp][e] = FRB_EMPTY;
+          s_cnt[warp][e] = 0;
+        }
       }
+#pragma unroll
+      for (int q = 0; q < BATCH; q++)
+        if (k[q] != FRB_EMPTY) sink.commit(k[q], cnt[q], home[q], &inserted);
     }
+    claimed = 0;
     __syncwarp();
   };
   auto tile_end = [&](const uint4*, size_t) {
-    if (++tiles_since_flush == HIST_FLUSH_TILES) {
+    // a label that finds its entry taken goes straight to memory, so the table must not fill up:
+    // drain on a schedule AND when the warp has claimed most of the entries
+    const unsigned int taken = __reduce_add_sync(FRB_FULL_MASK, claimed);
+    if (++tiles_since_flush == HIST_FLUSH_TILES || taken >= HIST_FLUSH_CLAIMS) {
       tiles_since_flush = 0;
       drain();
     }

@@ -40,7 +40,10 @@ enum { FRB_OK = 0, FRB_ERR_BAD_ARG = 4, FRB_ERR_CUDA = 3 };
  * _renumber / _remap / _mask_except / remap_from_array_kv.
  * A table is `cap` slots of 16 bytes {uint64 key bits, uint64 value} plus a meta block of
  * FRB_META_WORDS uint64.  cap is a power of two.  Tables for 8/16-bit dtypes are DIRECT
- * (slot index == key, cap == 2^bits); wider dtypes use open addressing with linear probing.
+ * (slot index == key, cap == 2^bits); wider dtypes use open addressing with linear probing from an
+ * EVEN home slot, so the first two probes of a lookup are one 32-byte sector (one 256-bit load).
+ * Tables that are only looked up (remap / mask / mask_except) are sized for a load factor <= 1/8:
+ * on this workload a lookup's cost is the length of its dependent probe chain, not the table's size.
  * The all-ones key pattern is the EMPTY marker; a real all-ones key lives in the meta block.
  */
 #define FRB_META_WORDS 16
