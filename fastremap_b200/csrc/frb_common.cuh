@@ -338,6 +338,8 @@ __device__ __forceinline__ void block_add_to(u64* target, unsigned int v) {
 //     i0       flat element index of the lane's first element
 //     prev     the element preceding the lane's first element in memory order (exact across
 //              lanes, rows, tiles and CTAs: it comes out of the same staged bytes), valid iff has_prev
+//   after_tile(k) (optional) is called by every consumer warp after it has released tile number k
+//     of the CTA -- also by warps whose part of the last tile lies past the end of the array.
 //   tile_end(wstage, vb) is called once per warp-tile after its rows; `wstage` still holds the
 //     warp-tile (vector u*32+lane of it is what row_fn(u) saw), vb is its first vector index.
 //
@@ -449,9 +451,9 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn>
+template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
-                                            TileEndFn tile_end) {
+                                            TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
   constexpr int S = STREAM_STAGES;
@@ -545,8 +547,16 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     __syncwarp();  // every lane of this warp is done with the stage
     if (lane == 0) mbar_arrive(&empty[s]);
     if (++s == S) { s = 0; round++; }
+    after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
+template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+                                            TileEndFn tile_end) {
+  stream_rows<W, REVERSE, NEED_PREV, RW>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+}
+// barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }
 
 // host side: tiles in an n-element array (+1 so that the CTA owning the scalar tail exists)
 inline size_t stream_tiles(size_t n, int w) { return (n / (16 / w) + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1; }

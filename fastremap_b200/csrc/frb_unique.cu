@@ -44,44 +44,57 @@ struct HashSink {
   }
 };
 
-static constexpr int HIST_CACHE = 256;        // (label, partial count) entries per warp
-static constexpr int HIST_FLUSH_TILES = 64;   // the per-warp table is flushed to memory at least this often
-static constexpr int HIST_FLUSH_CLAIMS = 160; // ... and as soon as this many of its entries are taken
+static constexpr int HIST_CACHE = 2048;        // (label, partial count) entries per CTA
+static constexpr int HIST_SYNC_TILES = 8;      // the consumer warps meet this often ...
+static constexpr int HIST_FLUSH_SYNCS = 8;     // ... and flush the table to memory at least every 8th time
+static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its entries are taken
 
 // Counting pass.  Three levels of aggregation sit between a voxel and a global atomic:
 //   lane   remembers the 16-byte vector it saw at the same position of its warp's previous tile
 //          (one row up in the volume) and a repeat count; an identical vector just bumps the count
 //          (7 integer instructions for V voxels).  A different vector flushes the old one: equal
 //          neighbours inside the vector are merged and (label, multiplicity * repeats) is added to
-//   warp   a per-warp shared-memory hash of (label, partial count) updated with shared-memory
-//          atomics.  Entries are claimed with CAS and never change label between flushes, so a
-//          lane can add to an entry it has seen without locking; a label that finds its slot taken
-//          goes straight to memory.  Every HIST_FLUSH_TILES tiles (and at the end) the warp drains
-//          the table with one
-//   global atomic per live entry (dense bins or the label table, see the sinks above).
+//   CTA    a shared-memory hash of (label, partial count) shared by the 8 consumer warps (they walk
+//          adjacent rows of the volume, i.e. the same labels), updated with shared-memory atomics.
+//          Entries are claimed with CAS and never change label between flushes, so a lane can add
+//          to an entry it has seen without locking; a label that finds both of its two candidate
+//          entries taken goes straight to memory.  Every few tiles the consumer warps meet at a
+//          named barrier and, on a schedule or when the table is filling up, drain it with one
+//   global atomic per live entry (dense bins or the label table, see the sinks above); the home-slot
+//          reads of a thread's entries are issued together so their L2 round trips overlap.
 template <int W, typename Sink>
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
   constexpr int V = 16 / W;
-  __shared__ u64 s_key[8][HIST_CACHE];
-  __shared__ unsigned int s_cnt[8][HIST_CACHE];
+  __shared__ u64 s_key[HIST_CACHE];
+  __shared__ unsigned int s_cnt[HIST_CACHE];
+  __shared__ unsigned int s_claims;
   const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  const bool consumer = warp < STREAM_WARPS;
   unsigned int inserted = 0;
-  if (warp < STREAM_WARPS)
-    for (int i = lane; i < HIST_CACHE; i += 32) { s_key[warp][i] = FRB_EMPTY; s_cnt[warp][i] = 0; }
-  __syncwarp();
+  for (int i = threadIdx.x; i < HIST_CACHE; i += STREAM_THREADS) { s_key[i] = FRB_EMPTY; s_cnt[i] = 0; }
+  if (threadIdx.x == 0) s_claims = 0;
+  __syncthreads();
 
-  unsigned int claimed = 0;  // entries this lane has claimed since the last drain
+  unsigned int claimed = 0;  // entries this lane has claimed since the consumer warps last met
   auto add = [&](u64 key, unsigned int c) {
-    const unsigned int e = (unsigned int)(hash_key(key) >> 48) & (HIST_CACHE - 1);
-    u64 ck = s_key[warp][e];
-    if (ck == FRB_EMPTY && key != FRB_EMPTY) {
-      const u64 old = atomicCAS(&s_key[warp][e], (u64)FRB_EMPTY, key);
-      ck = old == FRB_EMPTY ? key : old;
-      claimed += old == FRB_EMPTY ? 1u : 0u;
+    if (key != FRB_EMPTY) {
+      unsigned int e = (unsigned int)(hash_key(key) >> 48) & (HIST_CACHE - 1);
+#pragma unroll
+      for (int attempt = 0; attempt < 2; attempt++, e ^= 1u) {
+        u64 ck = s_key[e];
+        if (ck == FRB_EMPTY) {
+          const u64 old = atomicCAS(&s_key[e], (u64)FRB_EMPTY, key);
+          ck = old == FRB_EMPTY ? key : old;
+          claimed += old == FRB_EMPTY ? 1u : 0u;
+        }
+        if (ck == key) {
+          atomicAdd(&s_cnt[e], c);
+          return;
+        }
+      }
     }
-    if (ck == key && key != FRB_EMPTY) atomicAdd(&s_cnt[warp][e], c);
-    else sink(key, c, &inserted);
+    sink(key, c, &inserted);
   };
   auto flush_vec = [&](const uint4& p, unsigned int reps) {
     u64 key = vec_get<W>(p, 0);
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
   unsigned int rep[STREAM_ROWS];
 #pragma unroll
   for (int u = 0; u < STREAM_ROWS; u++) { pat[u] = make_uint4(0, 0, 0, 0); rep[u] = 0; }
-  int tiles_since_flush = 0;
+  int syncs_since_flush = 0;
 
   auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
     if (!valid) return;
@@ -118,49 +131,54 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
       rep[u] = 1;
     }
   };
-  auto drain = [&]() {  // all lanes; no lane is inside add() while entries are reset
-    __syncwarp();
-    if (warp >= STREAM_WARPS) return;
-    constexpr int BATCH = 4;  // home-slot reads in flight per lane (registers: 7 per entry)
+  // all consumer threads, between two consumer barriers: nobody is inside add()
+  auto drain = [&]() {
+    constexpr int BATCH = 4;  // home-slot reads in flight per thread (registers: 7 per entry)
+    constexpr int NCONS = STREAM_WARPS * 32;
 #pragma unroll 1
-    for (int q0 = 0; q0 < HIST_CACHE / 32; q0 += BATCH) {
+    for (int q0 = 0; q0 < HIST_CACHE / NCONS; q0 += BATCH) {
       u64 k[BATCH];
       unsigned int cnt[BATCH];
       Slot home[BATCH];
 #pragma unroll
       for (int q = 0; q < BATCH; q++) {
-        const int e = (q0 + q) * 32 + lane;
-        k[q] = s_key[warp][e];
-        cnt[q] = s_cnt[warp][e];
+        const int e = (q0 + q) * NCONS + threadIdx.x;
+        k[q] = s_key[e];
+        cnt[q] = s_cnt[e];
         if (k[q] != FRB_EMPTY) {
           home[q] = sink.peek(k[q]);
-          s_key[warp][e] = FRB_EMPTY;
-          s_cnt[warp][e] = 0;
+          s_key[e] = FRB_EMPTY;
+          s_cnt[e] = 0;
         }
       }
 #pragma unroll
       for (int q = 0; q < BATCH; q++)
         if (k[q] != FRB_EMPTY) sink.commit(k[q], cnt[q], home[q], &inserted);
     }
-    claimed = 0;
-    __syncwarp();
   };
-  auto tile_end = [&](const uint4*, size_t) {
-    // a label that finds its entry taken goes straight to memory, so the table must not fill up:
-    // drain on a schedule AND when the warp has claimed most of the entries
-    const unsigned int taken = __reduce_add_sync(FRB_FULL_MASK, claimed);
-    if (++tiles_since_flush == HIST_FLUSH_TILES || taken >= HIST_FLUSH_CLAIMS) {
-      tiles_since_flush = 0;
+  auto after_tile = [&](size_t k) {
+    if ((k % HIST_SYNC_TILES) != HIST_SYNC_TILES - 1) return;
+    if (claimed) { atomicAdd(&s_claims, claimed); claimed = 0; }
+    consumer_bar();
+    const bool flush = s_claims >= HIST_FLUSH_CLAIMS || ++syncs_since_flush >= HIST_FLUSH_SYNCS;  // the same in every warp
+    consumer_bar();
+    if (flush) {
       drain();
+      if (threadIdx.x == 0) s_claims = 0;
+      syncs_since_flush = 0;
+      consumer_bar();
     }
   };
 
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, false>(a, nvec, map, row_fn, tile_end);
+  stream_rows<W, false, false, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  if (consumer) {
 #pragma unroll
-  for (int u = 0; u < STREAM_ROWS; u++)
-    if (rep[u] != 0) flush_vec(pat[u], rep[u]);
-  drain();
+    for (int u = 0; u < STREAM_ROWS; u++)
+      if (rep[u] != 0) flush_vec(pat[u], rep[u]);
+    consumer_bar();
+    drain();
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
   if (count_target) block_add_to(count_target, inserted);
