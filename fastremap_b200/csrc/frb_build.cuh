@@ -1,129 +1,154 @@
-// frb_build.cuh -- the shared "run heads -> label table" pass behind K1 (renumber, atomicMin of the
-// first index) and K7 (component_map, atomicMax of the last run start).
+// frb_build.cuh -- the filtered "volume -> label table" pass behind K1 (renumber: atomicMin of the
+// first index of every label) and K7 (component_map: atomicMax of the last run start).
 //
-// Streaming structure (stream_rows, frb_common.cuh): a CTA of 8 warps owns a CONTIGUOUS range of
-// tiles, so consecutive tiles of one warp are spatially adjacent rows of the volume and see the
-// same few labels; a warp keeps 4 x 512 B of 16-byte streaming loads in flight, finds the run
-// heads (a[i] != a[i-1], exact across lanes / rows / tiles / CTAs) and offers (label, index) to
-// the table.
-//
-// Two things keep the table off the critical path:
-//  1. A per-warp shared-memory set of recently offered labels.  A warp walks its voxels in index
-//     order (ascending for MIN, descending for MAX), so once it has offered a label every later
-//     offer of that label by the same warp is dominated and is dropped without touching the table
-//     (~90 % of the run heads on segmentation data).  The set is race free by construction: within
-//     a row all reads (phase 1) are separated from all writes (phase 2) by __syncwarp, entries are
-//     single 8-byte words, and a dropped offer is always dominated by one this warp already sent.
-//  2. Surviving offers are deferred: the 16-byte slot read is issued when the head is found and
-//     consumed at the end of the tile, after the next tile's streaming loads are in flight, so the
-//     L2 round trip overlaps the HBM latency the warp has to wait for anyway.  The common outcome
-//     ("label present with a better index") ends there without an atomic.
+// Offering ANY occurrence (K1) / ANY run start (K7) of a label is correct -- the table combines
+// with MIN / MAX -- so the work is in offering as few as possible: segmentation volumes repeat the
+// same label for tens of voxels in every direction.  Three filters sit between a voxel and the
+// table, each exact:
+//   1. registers: a lane remembers the 16-byte vector it saw at the same position of its warp's
+//      previous tile (with the run-interleaved tile order that is the voxels one or two rows up in
+//      y; tiles are walked backwards for MAX, so "previous" always means "already offered something
+//      at least as good").  K1: an element equal to the remembered one, or to its predecessor in
+//      memory, is dominated.  K7 (HEADS): if the vector AND the element in front of it are the same
+//      as remembered, every run start in it has a twin one tile later.  Testing a whole vector costs
+//      7 integer instructions for all V elements.
+//   2. a per-warp shared-memory set of labels the warp has already offered (phase-separated: all
+//      reads of a tile before all writes, so a hit always refers to an earlier tile).
+//   3. the 16-byte home slot itself: read first (L2-coherent), issued one tile ahead of its use so
+//      the round trip overlaps the streaming; "label present with a better value" ends there.
+// Only what survives all three reaches atomicCAS / atomicMin / atomicMax.
 #pragma once
 #include "frb_common.cuh"
 
 namespace frb {
 
-static constexpr int BUILD_TILE_VECS = STREAM_TILE_VECS;      // 16-byte vectors per CTA tile
-static constexpr int BUILD_CACHE = 256;                       // entries in the per-warp label set
+static constexpr int BUILD_CACHE = 256;  // entries in the per-warp set of labels already offered
 
-template <int OP>
-__device__ __noinline__ void offer_slow(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v, unsigned int* inserted) {
-  table_update<OP>(slots, mask, direct, meta, key, v, inserted);
-}
-
+// out-of-line find-or-insert + combine (the rare path of the build kernels; keeps their hot loops small)
 template <int OP>
 __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v, unsigned int* inserted) {
   return table_update<OP>(slots, mask, direct, meta, key, v, inserted);
 }
 
-// value offered for element i is i + bias  (MIN / forward: first occurrence; MAX / reverse: last run start)
-template <int W, int OP, bool REVERSE>
+// value offered for element i is bias + i.  HEADS: only run starts (a[i] != a[i-1]) are offered.
+template <int W, int OP, bool REVERSE, bool HEADS>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run) {
   constexpr int V = 16 / W;
+  typedef typename UIntOf<W>::type T;
   __shared__ u64 s_seen[8][BUILD_CACHE];
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int inserted = 0;
-
   if (warp < STREAM_WARPS)
     for (int i = lane; i < BUILD_CACHE; i += 32) s_seen[warp][i] = FRB_EMPTY;
   __syncwarp();
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // scalar tail (< V elements at the very end); never filtered, so its order does not matter
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
     for (size_t i = nvec * V; i < n; i++) {
       const u64 key = ld_elem<W>(a, i);
-      if ((i == 0 || key != ld_elem<W>(a, i - 1)) && !(skip_zero && key == 0))
-        offer_slow<OP>(slots, mask, direct, meta, key, (u64)i + bias, &inserted);
+      const bool head = !HEADS || i == 0 || key != ld_elem<W>(a, i - 1);
+      if (head && !(skip_zero && key == 0)) table_update_slow<OP>(slots, mask, direct, meta, key, bias + (u64)i, &inserted);
     }
   }
 
-  const TileMap map(nvec, (size_t)run);
-  // a table that overflowed in an earlier launch attempt cannot happen (the host re-inits), but a
-  // table that overflows during this pass makes the rest of the pass pointless: checked per tile
-  bool aborted = false;
-
-  // one deferred offer per lane per tile
-  bool pend = false;
+  uint4 last[STREAM_ROWS];
+  u64 last_prev[HEADS ? STREAM_ROWS : 1];
+  bool have_last = false;      // false until the warp has processed its first tile
+  u64 cand = 0;                // bit (u * V + j): element j of row u needs a closer look
+  // A full table makes the rest of the pass pointless (the host grows the table and retries): a lane
+  // stops offering once one of its own offers failed, or if the table had already overflowed when
+  // this launch started (chunk pipelines queue launches ahead of the host's overflow check).
+  bool aborted = *((volatile u64*)&meta[FRB_META_OVERFLOW]) != 0;
+  bool pend = false;           // one deferred offer per lane, resolved a tile later
   u64 pkey = 0, pval = 0;
   Slot pslot;
   pslot.key = 0;
   pslot.val = 0;
 
-  auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64 prev, bool has_prev) {
-    if (aborted) return;
-    // phase 1: heads of this row that the warp has not offered before
-    unsigned int todo = 0;
-    if (valid) {
+  auto offer = [&](u64 key, u64 val) {
+    if (!table_update_slow<OP>(slots, mask, direct, meta, key, val, &inserted)) aborted = true;
+  };
+
+  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
+    if (!valid) return;
+    const uint4 l = last[u];
+    last[u] = cur;
+    const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
+    if (HEADS) {
+      const u64 lp = last_prev[u];
+      last_prev[u] = prev;
+      if (d != 0 || !have_last || !has_prev || prev != lp) {
+        // not a copy of the remembered row: every run start in it is a candidate
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          const u64 key = vec_get<W>(cur, j);
+          if ((!has_prev || key != prev) && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
+          prev = key;
+          has_prev = true;
+        }
+      }
+    } else if (d != 0 || !have_last) {
+      // rare path (a label boundary one row up, or the warp's first tile): keep the elements that
+      // differ from the remembered vector AND from their predecessor in memory -- an element equal
+      // to its predecessor is dominated by whatever happened to that predecessor
 #pragma unroll
       for (int j = 0; j < V; j++) {
         const u64 key = vec_get<W>(cur, j);
-        const bool head = (!has_prev || key != prev) && !(skip_zero && key == 0);
+        const bool differs_up = !have_last || key != vec_get<W>(l, j);
+        const bool differs_prev = !has_prev || key != prev;
+        if (differs_up && differs_prev && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
         prev = key;
         has_prev = true;
-        if (head) {
-          const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
-          if (!hit) todo |= 1u << j;
-        }
       }
     }
-    __syncwarp();
-    // phase 2: remember, and queue (or send) the offer
-    if (todo) {
-#pragma unroll
-      for (int j = 0; j < V; j++) {
-        if (todo & (1u << j)) {
-          const u64 key = vec_get<W>(cur, j);
-          const u64 h = hash_key(key);
-          const u64 val = (u64)(i0 + j) + bias;
-          s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
-          if (!pend && key != FRB_EMPTY) {
-            pend = true;
-            pkey = key;
-            pval = val;
-            pslot = ld_slot_cg(slots + (direct ? key : (h & mask & ~1ull)));  // consumed in tile_end
-          } else {
-            offer_slow<OP>(slots, mask, direct, meta, key, val, &inserted);
-          }
-        }
-      }
-    }
-    __syncwarp();
   };
 
-  auto tile_end = [&](const uint4*, size_t) {
+  auto resolve_pending = [&]() {
     if (pend) {
-      if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval)))
-        offer_slow<OP>(slots, mask, direct, meta, pkey, pval, &inserted);
+      if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval))) offer(pkey, pval);
       pend = false;
     }
-    u64 ovf = 0;
-    if (lane == 0) ovf = *((volatile u64*)&meta[FRB_META_OVERFLOW]);
-    if (__shfl_sync(FRB_FULL_MASK, ovf, 0)) aborted = true;
   };
 
+  auto tile_end = [&](const uint4* stage, size_t vb) {
+    have_last = true;
+    resolve_pending();
+    if (aborted) cand = 0;
+    // phase 1: which candidates has this warp not offered before?
+    u64 todo = 0;
+    for (u64 m = cand; m; m &= m - 1) {
+      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
+      const unsigned int u = b / V, j = b % V;
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
+      const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
+      if (!hit) todo |= 1ull << b;
+    }
+    cand = 0;
+    __syncwarp();
+    // phase 2: remember them and queue / send the offers
+    for (u64 m = todo; m; m &= m - 1) {
+      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
+      const unsigned int u = b / V, j = b % V;
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
+      const u64 h = hash_key(key);
+      const u64 val = bias + (u64)((vb + u * 32 + lane) * V + j);
+      s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
+      if (!pend && key != FRB_EMPTY) {
+        pend = true;
+        pkey = key;
+        pval = val;
+        pslot = ld_slot_cg(slots + (direct ? key : (h & mask & ~1ull)));  // consumed at the next tile_end
+      } else {
+        offer(key, val);
+      }
+    }
+    __syncwarp();
+  };
+
+  const TileMap map(nvec, (size_t)run);
   stream_rows<W, REVERSE, true, false>(a, nvec, map, row_fn, tile_end);
+  resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted);
 }
 

@@ -4,8 +4,8 @@
 // remap[cc[i]] = parent[i] at every run start of cc in memory order, so for each label the LAST
 // run start wins.  Here every run start offers (i + 1) to the label's slot with atomicMax; the
 // gather pass then reads parent[] at the winning index.  Warps walk their tiles from the back, so
-// the first offer a warp makes for a label is the largest it will ever make and the per-warp
-// "already offered" filter of frb_build.cuh drops the rest.
+// the first offer a warp makes for a label is the largest it will ever make, and the register /
+// shared-memory / home-slot filters of frb_build.cuh drop the rest.
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
 
@@ -15,7 +15,7 @@ template <int W>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
                   u64* __restrict__ meta, int run) {
-  build_pass<W, FRB_OP_MAX, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
+  build_pass<W, FRB_OP_MAX, true, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
 }
 
 template <int WC>

@@ -94,125 +94,13 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 }
 
 // ------------------------------------------------------------------------------------------ K1
-// First-index pass: the table receives, for every label, the minimum flat index at which it
-// occurs.  Offering ANY occurrence is correct (atomicMin); the work is in offering as few as
-// possible, because segmentation volumes repeat the same label for tens of voxels in every
-// direction.  Three filters sit between a voxel and the table, each exact:
-//   1. registers: a lane remembers the 16-byte vector it saw at the same position of its warp's
-//      previous tile (with the run-interleaved tile order that is the voxels one row up in y).  An
-//      element equal to the remembered one is dominated by an earlier offer of the same lane, and
-//      testing a whole vector costs 7 integer instructions for all V elements at once.
-//      Survivors get a second chance against their predecessor in memory (same argument).
-//   2. per-warp shared-memory set of labels the warp has already offered (phase-separated: all
-//      reads of a tile before all writes, so a hit always refers to an earlier tile = smaller index).
-//   3. the 16-byte slot itself: read first (L2-coherent), issued one tile ahead of its use so the
-//      round trip overlaps the streaming; "label present with a smaller index" ends there.
-// Only what survives all three reaches atomicCAS / atomicMin.
+// First-index pass: the table receives, for every label, the minimum flat index at which it occurs
+// (tagged: see FRB_RANK_TAG).  The filtered build pass is shared with K7: frb_build.cuh.
 template <int W>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
                  u64 mask, int direct, u64* __restrict__ meta, int run) {
-  constexpr int V = 16 / W;
-  typedef typename UIntOf<W>::type T;
-  __shared__ u64 s_seen[8][BUILD_CACHE];
-  const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned int inserted = 0;
-  if (warp < STREAM_WARPS)
-    for (int i = lane; i < BUILD_CACHE; i += 32) s_seen[warp][i] = FRB_EMPTY;
-  __syncwarp();
-
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
-    for (size_t i = nvec * V; i < n; i++) {
-      const u64 key = ld_elem<W>(a, i);
-      if (!(skip_zero && key == 0)) table_update_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, FRB_RANK_TAG | ((u64)i + flat_offset), &inserted);
-    }
-  }
-
-  uint4 last[STREAM_ROWS];
-  bool have_last = false;      // false until the warp has processed its first tile
-  u64 cand = 0;                // bit (u * V + j): element j of row u needs a closer look
-  // A full table makes the rest of the pass pointless (the host grows the table and retries): a lane
-  // stops offering once one of its own offers failed, or if the table had already overflowed when
-  // this launch started (chunk pipelines queue launches ahead of the host's overflow check).
-  bool aborted = *((volatile u64*)&meta[FRB_META_OVERFLOW]) != 0;
-  bool pend = false;           // one deferred offer per lane, resolved a tile later
-  u64 pkey = 0, pval = 0;
-  Slot pslot;
-  pslot.key = 0;
-  pslot.val = 0;
-
-  auto offer = [&](u64 key, u64 val) {
-    if (!table_update_slow<FRB_OP_MIN>(slots, mask, direct, meta, key, val, &inserted)) aborted = true;
-  };
-
-  auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
-    if (!valid) return;
-    const uint4 l = last[u];
-    last[u] = cur;
-    const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
-    if (d != 0 || !have_last) {
-      // rare path (a label boundary one row up, or the warp's first tile): keep the elements that
-      // differ from the remembered vector AND from their predecessor in memory -- an element equal
-      // to its predecessor is dominated by whatever happened to that predecessor
-#pragma unroll
-      for (int j = 0; j < V; j++) {
-        const u64 key = vec_get<W>(cur, j);
-        const bool differs_up = !have_last || key != vec_get<W>(l, j);
-        const bool differs_prev = !has_prev || key != prev;
-        if (differs_up && differs_prev && !(skip_zero && key == 0)) cand |= 1ull << (u * V + j);
-        prev = key;
-        has_prev = true;
-      }
-    }
-  };
-
-  auto resolve_pending = [&]() {
-    if (pend) {
-      if (!(pslot.key == pkey && pslot.val <= pval)) offer(pkey, pval);
-      pend = false;
-    }
-  };
-
-  auto tile_end = [&](const uint4* stage, size_t vb) {
-    have_last = true;
-    resolve_pending();
-    if (aborted) cand = 0;
-    // phase 1: which candidates has this warp not offered before?
-    u64 todo = 0;
-    for (u64 m = cand; m; m &= m - 1) {
-      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
-      const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
-      const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
-      if (!hit) todo |= 1ull << b;
-    }
-    cand = 0;
-    __syncwarp();
-    // phase 2: remember them and queue / send the offers
-    for (u64 m = todo; m; m &= m - 1) {
-      const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
-      const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
-      const u64 h = hash_key(key);
-      const u64 val = FRB_RANK_TAG | ((u64)((vb + u * 32 + lane) * V + j) + flat_offset);
-      s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
-      if (!pend && key != FRB_EMPTY) {
-        pend = true;
-        pkey = key;
-        pval = val;
-        pslot = ld_slot_cg(slots + (direct ? key : (h & mask & ~1ull)));  // consumed at the next tile_end
-      } else {
-        offer(key, val);
-      }
-    }
-    __syncwarp();
-  };
-
-  const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, true, false>(a, nvec, map, row_fn, tile_end);
-  resolve_pending();
-  block_add_to(&meta[FRB_META_COUNT], inserted);
+  build_pass<W, FRB_OP_MIN, false, false>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run);
 }
 
 // ------------------------------------------------------------------------------------------ probes
