@@ -129,8 +129,10 @@ def _run_build(fn, table: LabelTable):
 LOOKUP_SLOTS_PER_ENTRY = 8
 
 
-def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positions=False) -> LabelTable:
-  """Build a lookup table from device arrays of L keys / values of `dtype` (K: frb_table_insert)."""
+def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positions=False, resolve=True) -> LabelTable:
+  """Build a lookup table from device arrays of L keys / values of `dtype` (K: frb_table_insert).
+  positions: the value of a key is its position in the list (combined with `op`), which `resolve`
+  then replaces by vals[position]."""
   dtype = np.dtype(dtype)
   w = dtype.itemsize
   init = 0
@@ -141,7 +143,7 @@ def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positio
                                      t.direct, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()), "frb_table_insert")
 
   _run_build(build, table)
-  if positions:
+  if positions and resolve:
     _lib.check(_L().frb_table_resolve(D.ptr(vals_dev), w, D.ptr(table.slots), table.cap, D.ptr(table.meta), D.stream()),
                "frb_table_resolve")
   return table
@@ -837,39 +839,164 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
   raise ValueError("unknown unique strategy %r" % (strategy,))
 
 
+def _first_indices_sorted(buf, n, dtype, nu):
+  """First flat index (memory order) of every label, ordered like the sorted labels: K1 with no
+  label skipped, export, sort by label.  Returns a uint64 device buffer of nu entries."""
+  L = _L()
+  dtype = np.dtype(dtype)
+  table = LabelTable(dtype, nu, _lib.EMPTY)
+
+  def build(t):
+    _lib.check(L.frb_renumber_build(D.ptr(buf), n, D.code(dtype), 0, 0, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()),
+               "frb_renumber_build")
+
+  meta = _run_build(build, table)
+  cnt = int(meta[_lib.META_COUNT])
+  if cnt != nu:
+    raise FastremapB200Error("unique: first-index pass found %d labels, counting pass %d" % (cnt, nu))
+  k64, v64 = D.alloc(nu * 8), D.alloc(nu * 8)
+  _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), nu, D.stream()),
+             "frb_table_export")
+  ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
+  ws = D.alloc(ws_bytes)
+  uniq, idx = D.alloc(nu * dtype.itemsize), D.alloc(nu * 8)
+  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, D.code(dtype), D.ptr(uniq), D.ptr(idx), D.ptr(ws), ws_bytes,
+                                    D.stream()), "frb_sort_table_pairs")
+  return idx  # values still carry FRB_RANK_TAG: the caller masks it
+
+
+def _inverse_positions(buf, n, dtype, uniq_buf, nu):
+  """For every voxel the position of its label in the sorted label list, as a uint64 device buffer:
+  a lookup table label -> position, one relabel pass, and a widening cast for narrow dtypes."""
+  dtype = np.dtype(dtype)
+  w = dtype.itemsize
+  t = table_from_arrays(uniq_buf, None, nu, dtype, op=_lib.OP_SET, positions=True, resolve=False)
+  out = D.alloc(n * w)
+  _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_wide=out)
+  if w == 8:
+    return out
+  return _cast(out, np.dtype("u%d" % w), np.uint64, n)  # positions < nu <= 2^(8w): they fit the label width
+
+
+def _two_axis_unique(labels):
+  """np.unique(labels, axis=0) for a C-contiguous (N, 2) array of < 8-byte integers, by packing every
+  row into one integer of twice the width (reference: fastremap.pyx:967-982)."""
+  from .dtypes import widen_dtype
+  is_t = isinstance(labels, torch.Tensor)
+  dtype = D.numpy_dtype(labels.dtype) if is_t else labels.dtype
+  wide = np.dtype(widen_dtype(dtype))
+  nrows = int(labels.shape[0])
+  if nrows == 0:
+    return labels
+  v = D.ingest(labels, alias_ok=True)
+  L = _L()
+  packed = D.alloc(nrows * wide.itemsize)
+  # row (a, b) read as one little-endian wide integer has b in its high half; the reference sorts
+  # with a in the high half (it swaps the columns first, :976)
+  _lib.check(L.frb_swap_halves(D.ptr(v.buf), D.ptr(packed), nrows, wide.itemsize, D.stream()), "frb_swap_halves")
+  if nrows == 1:
+    uniq, nu = packed, 1
+  else:
+    uniq, _, nu = unique_counts_device(packed, nrows, wide)
+  _lib.check(L.frb_swap_halves(D.ptr(uniq), D.ptr(uniq), nu, wide.itemsize, D.stream()), "frb_swap_halves")
+  if is_t:
+    return uniq[: nu * wide.itemsize].view(D.torch_dtype(dtype)).reshape(nu, 2)
+  # the reference's result is the fancy-indexed labels[:, [1, 0]], which numpy lays out column-major
+  return np.asfortranarray(D.download(uniq, nu * 2, dtype).reshape((nu, 2)))
+
+
 def unique(labels, return_index=False, return_inverse=False, return_counts=False, axis=None, *, strategy=None):
   """
-  Sorted unique labels, optionally with counts (reference: fastremap.pyx:855-965).
-  return_index / return_inverse / axis are on the "next" list of this build and raise
-  NotImplementedError rather than fall back to a CPU implementation.
+  Sorted unique labels, optionally with first index, inverse and counts, in numpy's order
+  (uniq, index, inverse, counts).  Reference: fastremap.pyx:855-965.
+
+  The reference picks one of four strategies from the label range and the fraction of equal
+  neighbours (:941-952); that choice is visible in the dtypes of the optional outputs and, for
+  Fortran-ordered input, in which occurrence counts as "first" -- so the same rule is evaluated
+  here (one fused min / max / pixel-pairs pass) whenever index or inverse are requested.  Where the
+  reference defers to numpy (floats, axis other than the (N,2) edge-list case) this build raises:
+  there is no CPU fallback.
   """
   is_t = isinstance(labels, torch.Tensor)
   if not is_t and not isinstance(labels, np.ndarray):
     labels = np.array(labels)
-  if return_index or return_inverse or axis is not None:
-    raise NotImplementedError("fastremap_b200.unique: return_index / return_inverse / axis are not built yet "
-                              "(no CPU fallback by design)")
   adtype = D.numpy_dtype(labels.dtype) if is_t else labels.dtype
-  _require_int(adtype, "unique")
+  is_int = D.is_int_dtype(adtype)
+  if axis is not None or not is_int:
+    c_contig = labels.is_contiguous() if is_t else labels.flags.c_contiguous
+    if (axis == 0 and labels.ndim == 2 and labels.shape[1] == 2 and adtype.itemsize < 8 and is_int
+        and not (return_index or return_inverse or return_counts) and c_contig):
+      return _two_axis_unique(labels)
+    if not is_int:
+      _require_int(adtype, "unique")
+    raise NotImplementedError("fastremap_b200.unique: axis=%r is handled by numpy in the reference "
+                              "(fastremap.pyx:902-908); no CPU fallback here" % (axis,))
   voxels = labels.numel() if is_t else labels.size
+  shape = tuple(labels.shape)
 
-  def wrap(u_np, c_np):
-    if is_t:
-      u = torch.from_numpy(u_np).to(labels.device) if u_np.size else torch.empty(0, dtype=labels.dtype, device=labels.device)
-      cc = torch.from_numpy(c_np).to(labels.device)
-      return (u, cc) if return_counts else u
-    return (u_np, c_np) if return_counts else u_np
+  def to_out(a_np):
+    return torch.from_numpy(a_np).to(labels.device) if is_t else a_np
 
-  if voxels == 0:
-    return wrap(np.array([], dtype=adtype), np.array([], dtype=np.uint32))
+  if voxels == 0 or voxels == 1:
+    if voxels == 0:
+      uniq = np.array([], dtype=adtype)
+      counts, index, inverse = np.array([], dtype=np.uint32), np.array([], dtype=np.uint64), np.array([], dtype=np.uintp)
+    else:
+      v = D.ingest(labels, alias_ok=True)
+      uniq = D.download(v.buf, 1, adtype)
+      counts, index, inverse = np.array([1], dtype=np.uint32), np.array([0], dtype=np.uint64), np.array([0], dtype=np.uintp)
+    results = [to_out(uniq)]
+    if return_index:
+      fortran = labels.permute(tuple(reversed(range(labels.dim())))).is_contiguous() if is_t else labels.flags.f_contiguous
+      if len(shape) > 1 and fortran:  # :923-929 applies to the degenerate sizes too (and makes the dtype intp)
+        index = np.ravel_multi_index(np.unravel_index(index, shape, order="F"), shape, order="C")
+      results.append(to_out(index))
+    if return_inverse:
+      results.append(to_out(inverse.reshape(shape)))
+    if return_counts:
+      results.append(to_out(counts))
+    return tuple(results) if len(results) > 1 else results[0]
+
   v = D.ingest(labels, alias_ok=True)
-  if voxels == 1:
-    return wrap(D.download(v.buf, 1, adtype), np.array([1], dtype=np.uint32))
+  branch = "fast"
+  if return_index or return_inverse:
+    mn, mx, pairs, _ = _scan(v.buf, v.n, v.dtype)
+    if mn >= 0 and mx < voxels:
+      branch = "array"
+    elif mx - mn <= voxels:
+      branch = "array"
+    elif float(pairs) / float(voxels) > 0.66:
+      branch = "renumber"
+    else:
+      branch = "numpy"  # :947-948: numpy semantics -- first occurrence in C order, intp outputs
+      if v.order == "F" and len(shape) > 1:
+        v = D.ingest(labels.contiguous() if is_t else np.ascontiguousarray(labels), alias_ok=True)
+
   uniq, cts, nu = unique_counts_device(v.buf, v.n, v.dtype, strategy=strategy)
+  intp = branch == "numpy"
+  results = []
   if is_t:
-    u = uniq[: nu * adtype.itemsize].view(D.torch_dtype(adtype))
-    return (u, cts[: nu * 8].view(torch.uint64)) if return_counts else u
-  u_np = D.download(uniq, nu, adtype)
+    results.append(uniq[: nu * adtype.itemsize].view(D.torch_dtype(adtype)))
+  else:
+    results.append(D.download(uniq, nu, adtype))
+
+  if return_index:
+    idx_buf = _first_indices_sorted(v.buf, v.n, v.dtype, nu)
+    idx = D.download(idx_buf, nu, np.uint64) & np.uint64(_lib.RANK_TAG - 1)
+    if v.order == "F" and len(shape) > 1:  # :923-929: report the C-order index of that voxel
+      idx = np.ravel_multi_index(np.unravel_index(idx, shape, order="F"), shape, order="C")
+    elif intp:
+      idx = idx.astype(np.intp)
+    results.append(to_out(idx))
+  if return_inverse:
+    inv_buf = _inverse_positions(v.buf, v.n, v.dtype, uniq, nu)
+    inv_dtype = np.dtype(np.uintp) if branch == "array" else np.dtype(np.intp)
+    order = "C" if branch == "numpy" else v.order
+    results.append(D.emit(inv_buf, inv_dtype, shape, order, is_t))
   if return_counts:
-    return u_np, D.download(cts, nu, np.uint64)
-  return u_np
+    cdtype = np.dtype(np.intp) if intp else np.dtype(np.uint64)
+    if is_t:
+      results.append(cts[: nu * 8].view(D.torch_dtype(cdtype)))
+    else:
+      results.append(D.download(cts, nu, cdtype))
+  return tuple(results) if len(results) > 1 else results[0]

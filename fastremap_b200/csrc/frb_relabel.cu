@@ -186,6 +186,21 @@ k_remap_from_array(const uint4* src, void* dst, size_t n, const void* __restrict
     }
 }
 
+// ---------------------------------------------------------------------- swap halves (edge lists)
+// dst[i] = src[i] with its low and high halves exchanged: an (N, 2) C-order array of w-byte ints,
+// read as N ints of 2w bytes, becomes "column 0 is the high half" -- sorting those ints sorts the
+// rows lexicographically.  The (N,2) packing trick of _two_axis_unique (fastremap.pyx:967-982).
+template <int W>
+__global__ void __launch_bounds__(256) k_swap_halves(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  constexpr int H = 4 * W;  // bits in a half
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 v = ld_elem<W>(src, i);
+    const u64 lo = v & ((1ull << H) - 1ull);
+    st_elem<W>(dst, i, (lo << H) | (v >> H));
+  }
+}
+
 // ---------------------------------------------------------------------- cast (refit astype)
 template <int WI, int WO, bool SIGNED_IN>
 __global__ void __launch_bounds__(256) k_cast(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
@@ -284,6 +299,19 @@ int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals,
     default: k_remap_from_array<8><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
   }
   return check_launch("k_remap_from_array");
+}
+
+int frb_swap_halves(const void* src, void* dst, size_t n, int width, void* stream) {
+  if ((n && (!src || !dst)) || (width != 2 && width != 4 && width != 8)) { set_error("frb_swap_halves: bad arguments (width 2, 4 or 8)"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = grid_for(n, 256 * 4, 16);
+  switch (width) {
+    case 2: k_swap_halves<2><<<g.blocks, g.threads, 0, st>>>(src, dst, n); break;
+    case 4: k_swap_halves<4><<<g.blocks, g.threads, 0, st>>>(src, dst, n); break;
+    default: k_swap_halves<8><<<g.blocks, g.threads, 0, st>>>(src, dst, n); break;
+  }
+  return check_launch("k_swap_halves");
 }
 
 int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {

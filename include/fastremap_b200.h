@@ -128,6 +128,9 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
 int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream);
 /* remap_from_array (fastremap.pyx:771-791): dst[i] = src[i] < nvals ? vals[src[i]] : src[i] (unsigned dtypes) */
 int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals, size_t nvals, int dtype, void* stream);
+/* exchange the low and high halves of n elements of `width` bytes (2, 4, 8): the (N,2) edge-list
+ * packing of _two_axis_unique (fastremap.pyx:967-982), src may equal dst */
+int frb_swap_halves(const void* src, void* dst, size_t n, int width, void* stream);
 /* refit's astype (fastremap.pyx:301): integer width change, truncating or sign/zero extending */
 int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

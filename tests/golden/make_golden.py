@@ -222,6 +222,31 @@ if True:
   case("unique_big_u64_sparse", "unique", [Synth(shape=[64, 64, 64], grid=[30, 30, 30], dtype="uint64", seed=543, zero_frac=0.1, noise=0.05)],
        {"return_counts": True}, big=True)
 
+# ---------------------------------------------------------------- unique: index / inverse / axis=0
+for i, dt in enumerate(DTYPES):
+  dense = vol(dt, seed=600 + i, small_ids=100)
+  sparse = vol(dt, seed=620 + i)
+  allf = {"return_index": True, "return_inverse": True, "return_counts": True}
+  case("unique_all_dense_%s" % dt, "unique", [dense], allf)
+  case("unique_all_dense_F_%s" % dt, "unique", [np.asfortranarray(dense)], allf)
+  case("unique_all_sparse_%s" % dt, "unique", [sparse], allf)
+  case("unique_all_sparse_F_%s" % dt, "unique", [np.asfortranarray(sparse)], allf)
+  case("unique_index_%s" % dt, "unique", [sparse], {"return_index": True})
+  case("unique_inverse_F_%s" % dt, "unique", [np.asfortranarray(sparse)], {"return_inverse": True})
+  if np.dtype(dt).itemsize < 8:
+    info = np.iinfo(dt)
+    edges = (synth_numpy((1, 300, 2), (1, 300, 2), "uint64", seed=640 + i, zero_frac=0.0) % 23).astype(np.int64)
+    edges = (edges + max(int(info.min), -11)).astype(dt).reshape(300, 2)
+    case("unique_axis0_%s" % dt, "unique", [edges], {"axis": 0})
+if True:
+  rnd = (synth_numpy((9, 11, 13), (9, 11, 13), "uint64", seed=660, zero_frac=0.0)).astype(np.uint64)  # iid: the numpy branch (:947-948)
+  allf = {"return_index": True, "return_inverse": True, "return_counts": True}
+  case("unique_all_random_u64", "unique", [rnd], allf)
+  case("unique_all_random_u64_F", "unique", [np.asfortranarray(rnd)], allf)
+  case("unique_all_random_i64", "unique", [rnd.view(np.int64)], allf)
+  case("unique_all_single", "unique", [np.array([[777]], dtype=np.int64)], allf)
+  case("unique_all_empty", "unique", [np.array([], dtype=np.uint8)], allf)
+
 np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)
 with open(os.path.join(HERE, "golden_manifest.json"), "w") as f:
   json.dump(manifest, f, indent=1, sort_keys=True)

@@ -349,3 +349,71 @@ def test_renumber_device_table_growth(frb, oracle):
   e_out, e_map = oracle.renumber(np.copy(a))
   g_out, g_map = frb.renumber(np.copy(a), max_labels=1)
   assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+
+
+# ------------------------------------------------------------------ unique: index / inverse / axis=0
+
+
+def _same_arrays(got, exp):
+  got = got if isinstance(got, tuple) else (got,)
+  exp = exp if isinstance(exp, tuple) else (exp,)
+  assert len(got) == len(exp)
+  for g, e in zip(got, exp):
+    assert g.dtype == e.dtype, (g.dtype, e.dtype)
+    assert g.shape == e.shape and np.array_equal(g, e)
+    assert g.flags.f_contiguous == e.flags.f_contiguous or g.ndim < 2
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_unique_index_inverse_vs_oracle(frb, oracle, dtype):
+  info = np.iinfo(dtype)
+  rng = np.random.default_rng(int(np.dtype(dtype).num) + 90)
+  blocky = synth((20, 24, 36), (5, 6, 7), dtype, seed=5, zero_frac=0.2, noise=0.05)          # "array" / "renumber" branches
+  dense = rng.integers(0, min(int(info.max), 200), size=(16, 20, 12)).astype(dtype)          # dense histogram branch
+  lo, hi = max(int(info.min), -2 ** 62), min(int(info.max), 2 ** 62)
+  sparse = rng.integers(lo, hi, size=(11, 13, 17), dtype=np.int64).astype(dtype)             # numpy branch for wide dtypes
+  for a in (blocky, dense, sparse, sparse.reshape(-1), blocky[:, :, 0]):
+    for arr in (a, np.asfortranarray(a)):
+      for flags in ({"return_index": True}, {"return_inverse": True}, {"return_index": True, "return_inverse": True, "return_counts": True},
+                    {"return_counts": True, "return_inverse": True}):
+        _same_arrays(frb.unique(arr, **flags), oracle.unique(arr, **flags))
+
+
+def test_unique_order_golden(frb):
+  """automated_test.py:720-796 (first indices and counts of a 700-element example with runs)."""
+  rng = np.random.default_rng(7)
+  arr = np.repeat(rng.integers(0, 40, size=70), 10).astype(np.uint32)
+  u, idx, inv, cts = frb.unique(arr, return_index=True, return_inverse=True, return_counts=True)
+  u2, idx2, inv2, cts2 = np.unique(arr, return_index=True, return_inverse=True, return_counts=True)
+  assert np.array_equal(u, u2) and np.array_equal(idx, idx2) and np.array_equal(inv, inv2) and np.array_equal(cts, cts2)
+  # automated_test.py:798-803: inverse of an array whose labels need the shifted histogram
+  arr = np.array([5, 5, 7, 1000, 7, 5], dtype=np.int64) - 3
+  u, inv = frb.unique(arr, return_inverse=True)
+  assert np.array_equal(u[inv], arr)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.int8, np.int16, np.int32])
+def test_unique_axis0_vs_oracle(frb, oracle, dtype):
+  """automated_test.py:420-440: (N, 2) edge lists."""
+  info = np.iinfo(dtype)
+  rng = np.random.default_rng(3)
+  for n in (1, 2, 50, 4000):
+    pairs = rng.integers(max(int(info.min), -30), min(int(info.max), 30) + 1, size=(n, 2)).astype(dtype)
+    got = frb.unique(pairs, axis=0)
+    exp = oracle.unique(pairs, axis=0)
+    assert got.dtype == exp.dtype and got.shape == exp.shape and np.array_equal(got, exp)
+    if np.issubdtype(dtype, np.unsignedinteger):
+      assert np.array_equal(got, np.unique(pairs, axis=0))
+  with pytest.raises(NotImplementedError):
+    frb.unique(np.zeros((4, 3), dtype=dtype), axis=0)
+
+
+def test_unique_torch_outputs(frb):
+  a = synth((12, 16, 20), (3, 4, 5), np.uint64, seed=2, zero_frac=0.1)
+  t = torch.from_numpy(a.view(np.int64)).cuda().view(torch.uint64)
+  u, idx, inv, cts = frb.unique(t, return_index=True, return_inverse=True, return_counts=True)
+  u2, idx2, inv2, cts2 = np.unique(a, return_index=True, return_inverse=True, return_counts=True)
+  assert np.array_equal(u.cpu().view(torch.int64).numpy().view(np.uint64), u2)
+  assert np.array_equal(idx.cpu().view(torch.int64).numpy().astype(np.int64), idx2)
+  assert np.array_equal(inv.cpu().view(torch.int64).numpy().astype(np.int64), inv2.reshape(a.shape))
+  assert np.array_equal(cts.cpu().view(torch.int64).numpy().astype(np.int64), cts2)
