@@ -9,6 +9,8 @@ there is no CPU fallback anywhere in this package.
 """
 from .api import (  # noqa: F401
   component_map,
+  foreground,
+  indices,
   mask,
   mask_except,
   minmax,
@@ -35,8 +37,6 @@ def _out_of_scope(name):
 
 ascontiguousarray = _out_of_scope("ascontiguousarray")
 asfortranarray = _out_of_scope("asfortranarray")
-foreground = _out_of_scope("foreground")
-indices = _out_of_scope("indices")
 inverse_component_map = _out_of_scope("inverse_component_map")
 point_cloud = _out_of_scope("point_cloud")
 tobytes = _out_of_scope("tobytes")

@@ -56,6 +56,9 @@ SIGNATURES = {
   "frb_unique_sort_ws_bytes": (_sz, [_sz, _i]),
   "frb_unique_sort_count": (_i, [_vp, _sz, _i, _vp, _vp, _sz, _vp]),
   "frb_unique_sort_emit": (_i, [_sz, _i, _vp, _vp, _sz, _vp, _vp]),
+  "frb_indices_ws_bytes": (_sz, [_sz]),
+  "frb_indices_count": (_i, [_vp, _sz, _i, _u64, _vp, _vp, _sz, _vp]),
+  "frb_indices_emit": (_i, [_vp, _sz, _i, _u64, _vp, _sz, _vp, _vp]),
   "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),

@@ -199,6 +199,57 @@ def pixel_pairs(labels):
   return _scan(v.buf, v.n, v.dtype)[2]
 
 
+def foreground(arr):
+  """Number of non-zero voxels (reference: fastremap.pyx:1407-1421); integer dtypes only."""
+  is_t = isinstance(arr, torch.Tensor)
+  if not is_t:
+    arr = np.asarray(arr)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  if not D.is_int_dtype(adtype):
+    raise TypeError("No matching signature found")
+  if (arr.numel() if is_t else arr.size) == 0:
+    return 0
+  v = D.ingest(arr, alias_ok=True)
+  return _scan(v.buf, v.n, v.dtype)[3]
+
+
+def indices(arr, value):
+  """Ascending positions i with arr[i] == value, as uint64 (reference: fastremap.pyx:104-119).
+  1-D integer (or bool) arrays; a value the dtype cannot hold raises OverflowError like the reference."""
+  is_t = isinstance(arr, torch.Tensor)
+  if not is_t:
+    arr = np.asarray(arr)
+  nd = arr.dim() if is_t else arr.ndim
+  if nd != 1:
+    raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d)" % nd)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  if adtype == np.dtype("bool"):
+    arr = arr.view(torch.uint8) if is_t else arr.view(np.uint8)
+    adtype = np.dtype("u1")
+  _require_int(adtype, "indices")
+  bits = _to_bits(value, adtype)
+  n = arr.numel() if is_t else arr.size
+
+  def wrap(a_np):
+    return torch.from_numpy(a_np.view(np.int64)).to(arr.device).view(torch.uint64) if is_t else a_np
+
+  if n == 0:
+    return wrap(np.zeros(0, dtype=np.uint64))
+  v = D.ingest(arr, alias_ok=True)
+  L = _L()
+  meta = D.alloc_meta()
+  ws_bytes = int(L.frb_indices_ws_bytes(n))
+  ws = D.alloc(ws_bytes)
+  _lib.check(L.frb_indices_count(D.ptr(v.buf), n, D.code(adtype), bits, D.ptr(meta), D.ptr(ws), ws_bytes, D.stream()),
+             "frb_indices_count")
+  cnt = int(D.read_u64(meta)[_lib.META_LIST_COUNT])
+  out = D.alloc(cnt * 8)
+  _lib.check(L.frb_indices_emit(D.ptr(v.buf), n, D.code(adtype), bits, D.ptr(out), cnt, D.ptr(ws), D.stream()), "frb_indices_emit")
+  if is_t:
+    return out[: cnt * 8].view(torch.uint64)
+  return D.download(out, cnt, np.uint64)
+
+
 def refit(arr, value=None, increase_only=False, exotics=False):
   """Resize to the smallest dtype of the same kind that fits `value` (reference: fastremap.pyx:259-301)."""
   is_t = isinstance(arr, torch.Tensor)

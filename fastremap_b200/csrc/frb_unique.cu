@@ -255,6 +255,42 @@ k_bins_emit(const u64* __restrict__ counts, u64 bins, size_t chunk, const u64* _
   }
 }
 
+// ------------------------------------------------------------------ indices(arr, value): ordered positions of a value
+template <int W>
+__global__ void __launch_bounds__(256)
+k_match_count(const void* __restrict__ a, size_t n, size_t chunk, u64 value, u64* __restrict__ block_counts) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  unsigned int c = 0;
+  for (size_t i = beg + threadIdx.x; i < end; i += 256) c += ld_elem<W>(a, i) == value ? 1 : 0;
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  c = __reduce_add_sync(FRB_FULL_MASK, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_match_emit(const void* __restrict__ a, size_t n, size_t chunk, u64 value, const u64* __restrict__ block_offs,
+             u64* __restrict__ out, size_t capacity) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  u64 run = block_offs[blockIdx.x];
+  for (size_t base = beg; base < end; base += 256) {
+    const size_t i = base + threadIdx.x;
+    const bool hit = i < end && ld_elem<W>(a, i) == value;
+    unsigned int tot;
+    const unsigned int pre = block_flag_scan(hit, &tot);
+    if (hit && run + pre < capacity) out[run + pre] = (u64)i;
+    run += tot;
+  }
+}
+
 // ------------------------------------------------------------------ sorted (label, count) pairs
 __global__ void __launch_bounds__(256) k_flip_sign(u64* keys, size_t L, u64 flip) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -404,6 +440,44 @@ int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint
     default: k_bins_emit<8><<<blocks, 256, 0, st>>>(c, bins, chunk, offs, mb, uniq_out, co, capacity); break;
   }
   return check_launch("k_bins_emit");
+}
+
+size_t frb_indices_ws_bytes(size_t n) { return (size_t)compact_blocks(n) * sizeof(u64) + 256; }
+
+int frb_indices_count(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* meta, void* ws, size_t ws_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !a || n == 0 || !meta || !ws || ws_bytes < frb_indices_ws_bytes(n)) { set_error("frb_indices_count: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  const int w = dtype_width(dtype);
+  const u64 v = trunc_width(value_bits, w);
+  switch (w) {
+    case 1: k_match_count<1><<<blocks, 256, 0, st>>>(a, n, chunk, v, (u64*)ws); break;
+    case 2: k_match_count<2><<<blocks, 256, 0, st>>>(a, n, chunk, v, (u64*)ws); break;
+    case 4: k_match_count<4><<<blocks, 256, 0, st>>>(a, n, chunk, v, (u64*)ws); break;
+    default: k_match_count<8><<<blocks, 256, 0, st>>>(a, n, chunk, v, (u64*)ws); break;
+  }
+  int rc = check_launch("k_match_count");
+  if (rc) return rc;
+  return scan_exclusive_u64((u64*)ws, (size_t)blocks, &((u64*)meta)[FRB_META_LIST_COUNT], st);
+}
+
+int frb_indices_emit(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* out, size_t capacity, const void* ws, void* stream) {
+  if (!dtype_ok(dtype) || !a || n == 0 || !ws || (capacity && !out)) { set_error("frb_indices_emit: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (capacity == 0) return FRB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  const int w = dtype_width(dtype);
+  const u64 v = trunc_width(value_bits, w);
+  const u64* offs = (const u64*)ws;
+  switch (w) {
+    case 1: k_match_emit<1><<<blocks, 256, 0, st>>>(a, n, chunk, v, offs, (u64*)out, capacity); break;
+    case 2: k_match_emit<2><<<blocks, 256, 0, st>>>(a, n, chunk, v, offs, (u64*)out, capacity); break;
+    case 4: k_match_emit<4><<<blocks, 256, 0, st>>>(a, n, chunk, v, offs, (u64*)out, capacity); break;
+    default: k_match_emit<8><<<blocks, 256, 0, st>>>(a, n, chunk, v, offs, (u64*)out, capacity); break;
+  }
+  return check_launch("k_match_emit");
 }
 
 // workspace: 2 ping-pong lists of L uint64 + radix histograms

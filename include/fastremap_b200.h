@@ -161,6 +161,14 @@ size_t frb_unique_sort_ws_bytes(size_t n, int dtype);
 int frb_unique_sort_count(const void* a, size_t n, int dtype, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
 int frb_unique_sort_emit(size_t n, int dtype, void* uniq_out, uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
 
+/* ---- indices (SURVEY 8(f) "next" row) -------------------------------------------------
+ * Replaces indices (fastremap.pyx:104-119): the ascending flat positions i with a[i] == value, in
+ * two steps because the caller sizes the output: _count leaves the number of matches in
+ * meta[FRB_META_LIST_COUNT] (and per-CTA offsets in ws), _emit writes the positions. */
+size_t frb_indices_ws_bytes(size_t n);
+int frb_indices_count(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
+int frb_indices_emit(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* out, size_t capacity, const void* ws, void* stream);
+
 /* ---- component_map -------------------------------------------------------------------
  * Replaces _component_map (fastremap.pyx:565-587): at every run start of cc the table
  * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])

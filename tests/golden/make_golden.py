@@ -247,6 +247,17 @@ if True:
   case("unique_all_single", "unique", [np.array([[777]], dtype=np.int64)], allf)
   case("unique_all_empty", "unique", [np.array([], dtype=np.uint8)], allf)
 
+# ---------------------------------------------------------------- foreground / indices ("next" rows)
+for i, dt in enumerate(DTYPES):
+  sparse = vol(dt, seed=700 + i)
+  case("foreground_%s" % dt, "foreground", [sparse])
+  case("foreground_F_%s" % dt, "foreground", [np.asfortranarray(sparse)])
+  flat = vol(dt, seed=720 + i, small_ids=20).reshape(-1)
+  case("indices_%s" % dt, "indices", [flat, int(flat[len(flat) // 2])])
+  case("indices_absent_%s" % dt, "indices", [flat, 21])
+case("indices_overflow", "indices", [np.array([1, 2, 3], dtype=np.uint8), 300])
+case("indices_empty", "indices", [np.array([], dtype=np.int32), 0])
+
 np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)
 with open(os.path.join(HERE, "golden_manifest.json"), "w") as f:
   json.dump(manifest, f, indent=1, sort_keys=True)
