@@ -8,6 +8,7 @@
 // shared-memory / home-slot filters of frb_build.cuh drop the rest.
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
+#include "frb_scan.cuh"
 
 namespace frb {
 
@@ -18,38 +19,23 @@ k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot*
   build_pass<W, FRB_OP_MAX, true, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
 }
 
-template <int WC>
-__global__ void __launch_bounds__(256)
-k_component_gather(const Slot* __restrict__ slots, u64 cap, u64* __restrict__ meta, const void* __restrict__ parent, int wp,
-                   u64 flat_offset, void* __restrict__ keys_out, void* __restrict__ parents_out, size_t capacity) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  const size_t cap_r = (cap + 31) & ~(size_t)31;
-  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap_r; s += stride) {
-    Slot cur;
-    cur.key = FRB_EMPTY;
-    cur.val = 0;
-    if (s < cap) cur = slots[s];
-    const bool occ = cur.key != FRB_EMPTY;
-    const unsigned int b = __ballot_sync(FRB_FULL_MASK, occ);
-    if (b == 0) continue;
-    u64 base = 0;
-    if (lane == 0) base = atomicAdd(&meta[FRB_META_LIST_COUNT], (u64)__popc(b));
-    base = __shfl_sync(FRB_FULL_MASK, base, 0);
-    if (occ) {
-      const u64 pos = base + __popc(b & ((1u << lane) - 1u));
-      if (pos < capacity) {
-        st_elem<WC>(keys_out, pos, cur.key);
-        st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(cur.val - 1 - flat_offset)));
-      }
-    }
+// gather: scan the table (frb_scan.cuh) and emit (label, parent[winning run start]) for every label
+struct GatherSel {
+  const void* parent;
+  void* keys_out;
+  void* parents_out;
+  u64 flat_offset;
+  int wc, wp;
+  __device__ __forceinline__ bool pick(u64 key, u64) const { return key != FRB_EMPTY; }
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64) const {
+    st_elem_rt(keys_out, wc, pos, key);
+    st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(val - 1 - flat_offset)));
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {
+};
+__global__ void k_gather_side(u64* meta, GatherSel sel, u64 capacity) {
+  if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {  // the out-of-band all-ones label
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
-    if (pos < capacity) {
-      st_elem<WC>(keys_out, pos, FRB_EMPTY);
-      st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(meta[FRB_META_SIDE_VAL] - 1 - flat_offset)));
-    }
+    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], 0);
   }
 }
 
@@ -139,17 +125,18 @@ int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc
   if (!dtype_ok(cc_dtype) || !dtype_ok(p_dtype) || !slots || !meta || !parent || (capacity && (!keys_out || !parents_out))) { set_error("frb_component_gather: bad arguments"); return FRB_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(&((u64*)meta)[FRB_META_LIST_COUNT], 0, sizeof(u64), st);
-  Grid g = grid_for((size_t)cap, 256 * 8, 8);
-  const int wc = dtype_width(cc_dtype), wp = dtype_width(p_dtype);
-  const Slot* s = (const Slot*)slots;
+  GatherSel sel;
+  sel.parent = parent;
+  sel.keys_out = keys_out;
+  sel.parents_out = parents_out;
+  sel.flat_offset = flat_offset;
+  sel.wc = dtype_width(cc_dtype);
+  sel.wp = dtype_width(p_dtype);
   u64* m = (u64*)meta;
-  switch (wc) {
-    case 1: k_component_gather<1><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
-    case 2: k_component_gather<2><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
-    case 4: k_component_gather<4><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
-    default: k_component_gather<8><<<g.blocks, g.threads, 0, st>>>(s, cap, m, parent, wp, flat_offset, keys_out, parents_out, capacity); break;
-  }
-  return check_launch("k_component_gather");
+  int rc = launch_table_scan(slots, cap, &m[FRB_META_LIST_COUNT], (u64)capacity, sel, "k_table_scan<gather>", st);
+  if (rc) return rc;
+  k_gather_side<<<1, 32, 0, st>>>(m, sel, (u64)capacity);
+  return check_launch("k_gather_side");
 }
 
 int frb_synth_volume(void* out, int dtype, uint64_t nz, uint64_t ny, uint64_t nx, uint64_t z0, uint64_t nz_total,

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "frb_common.cuh"
+#include "frb_scan.cuh"
 
 namespace frb {
 
@@ -81,48 +82,35 @@ k_table_resolve(const void* __restrict__ vals, int vw, Slot* slots, u64 cap, u64
 }
 
 // ---------------------------------------------------------------------------------- export
-// mode 0: (key bits, value); mode 1: (value, slot index) -- the (sort key, payload) list of K2
-__global__ void __launch_bounds__(256)
-k_table_export(const Slot* __restrict__ slots, u64 cap, u64* meta, u64* __restrict__ a_out, u64* __restrict__ b_out,
-               size_t capacity, int mode) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  // cap is a power of two >= 256 or the loop bound is rounded up so whole warps stay converged
-  const size_t cap_r = (cap + 31) & ~(size_t)31;
-  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap_r; s += stride) {
-    Slot cur;
-    cur.key = FRB_EMPTY;
-    cur.val = 0;
-    if (s < cap) cur = slots[s];
-    const bool occ = cur.key != FRB_EMPTY;
-    const unsigned int b = __ballot_sync(FRB_FULL_MASK, occ);
-    if (b == 0) continue;
-    u64 base = 0;
-    if (lane == 0) base = atomicAdd(&meta[FRB_META_LIST_COUNT], (u64)__popc(b));
-    base = __shfl_sync(FRB_FULL_MASK, base, 0);
-    if (occ) {
-      const u64 pos = base + __popc(b & ((1u << lane) - 1u));
-      if (pos < capacity) {
-        if (mode == 0) { a_out[pos] = cur.key; b_out[pos] = cur.val; }
-        else { a_out[pos] = cur.val; b_out[pos] = (u64)s; }
-      }
-    }
+// mode 0: (key bits, value); mode 1: (value, slot index)
+struct ExportSel {
+  u64* a_out;
+  u64* b_out;
+  int mode;
+  __device__ __forceinline__ bool pick(u64 key, u64) const { return key != FRB_EMPTY; }
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot) const {
+    if (mode == 0) { a_out[pos] = key; b_out[pos] = val; }
+    else { a_out[pos] = val; b_out[pos] = slot; }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {
+};
+__global__ void k_export_side(u64 cap, u64* meta, ExportSel sel, u64 capacity) {
+  if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {  // the out-of-band all-ones key ("slot cap")
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
-    if (pos < capacity) {
-      if (mode == 0) { a_out[pos] = FRB_EMPTY; b_out[pos] = meta[FRB_META_SIDE_VAL]; }
-      else { a_out[pos] = meta[FRB_META_SIDE_VAL]; b_out[pos] = cap; }
-    }
+    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], cap);
   }
 }
 
 int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* b_out, size_t capacity, int mode,
                         cudaStream_t st) {
   cudaMemsetAsync(&meta[FRB_META_LIST_COUNT], 0, sizeof(u64), st);
-  Grid g = grid_for((size_t)cap, 256 * 8, 8);
-  k_table_export<<<g.blocks, g.threads, 0, st>>>(slots, cap, meta, a_out, b_out, capacity, mode);
-  return check_launch("k_table_export");
+  ExportSel sel;
+  sel.a_out = a_out;
+  sel.b_out = b_out;
+  sel.mode = mode;
+  int rc = launch_table_scan(slots, cap, &meta[FRB_META_LIST_COUNT], (u64)capacity, sel, "k_table_scan<export>", st);
+  if (rc) return rc;
+  k_export_side<<<1, 32, 0, st>>>(cap, meta, sel, (u64)capacity);
+  return check_launch("k_export_side");
 }
 
 }  // namespace frb

@@ -10,6 +10,7 @@
 // per-warp shared-memory (label, count) hash, then one global atomic per live entry): see k_hist.
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
+#include "frb_coopsort.cuh"
 
 namespace frb {
 
@@ -292,18 +293,31 @@ k_match_emit(const void* __restrict__ a, size_t n, size_t chunk, u64 value, cons
 }
 
 // ------------------------------------------------------------------ sorted (label, count) pairs
-__global__ void __launch_bounds__(256) k_flip_sign(u64* keys, size_t L, u64 flip) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += stride) keys[i] ^= flip;
-}
+// One persistent kernel: flip the sign bit of signed labels (so that unsigned digit order is the
+// dtype's order), sort the pairs by label (frb_coopsort.cuh), emit typed labels + values.
+struct SortPairsArgs {
+  CoopSortBuffers sort;
+  u64 n;
+  u64 flip;
+  int key_bits;
+  void* uniq_out;
+  u64* vals_out;
+};
+
 template <int W>
-__global__ void __launch_bounds__(256)
-k_emit_pairs(const u64* __restrict__ keys, const u64* __restrict__ vals, size_t L, u64 flip, void* __restrict__ uniq_out,
-             u64* __restrict__ vals_out) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += stride) {
-    st_elem<W>(uniq_out, i, keys[i] ^ flip);
-    vals_out[i] = vals[i];
+__global__ void __launch_bounds__(CS_THREADS) k_sort_emit_pairs(SortPairsArgs A) {
+  const u64 stride = (u64)gridDim.x * CS_THREADS;
+  unsigned int generation = 0;
+  if (A.flip) {
+    for (u64 i = (u64)blockIdx.x * CS_THREADS + threadIdx.x; i < A.n; i += stride) A.sort.keys[i] ^= A.flip;
+    grid_barrier(A.sort.barrier, generation);
+  }
+  u64* kin;
+  u64* vin;
+  coop_radix_sort(A.sort, A.n, 0, A.key_bits, generation, &kin, &vin);
+  for (u64 i = (u64)blockIdx.x * CS_THREADS + threadIdx.x; i < A.n; i += stride) {
+    st_elem<W>(A.uniq_out, i, __ldcg(kin + i) ^ A.flip);
+    A.vals_out[i] = __ldcg(vin + i);
   }
 }
 
@@ -480,10 +494,10 @@ int frb_indices_emit(const void* a, size_t n, int dtype, uint64_t value_bits, ui
   return check_launch("k_match_emit");
 }
 
-// workspace: 2 ping-pong lists of L uint64 + radix histograms
+// workspace: 2 ping-pong lists of L uint64 + the cooperative sort's histograms and barrier word
 size_t frb_sort_pairs_ws_bytes(size_t L) {
   const size_t c = L < 1 ? 1 : L;
-  return 2 * align_up(c * sizeof(u64), 256) + radix_hist_bytes(c);
+  return 2 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
 }
 
 int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, void* uniq_out, uint64_t* vals_out, void* ws,
@@ -495,25 +509,34 @@ int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, vo
   if (L == 0) return FRB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int w = dtype_width(dtype);
-  const u64 flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
   const size_t lb = align_up(L * sizeof(u64), 256);
-  u64* k_alt = (u64*)ws;
-  u64* v_alt = (u64*)((char*)ws + lb);
-  void* hist = (char*)ws + 2 * lb;
-  int rc;
-  Grid g = grid_for(L, 256 * 4, 8);
-  if (flip) {
-    k_flip_sign<<<g.blocks, g.threads, 0, st>>>((u64*)keys, L, flip);
-    if ((rc = check_launch("k_flip_sign"))) return rc;
-  }
-  if ((rc = radix_sort_u64((u64*)keys, (u64*)vals, k_alt, v_alt, L, 0, 8 * w, hist, st))) return rc;
+  SortPairsArgs A;
+  A.sort.keys = (u64*)keys;
+  A.sort.pay = (u64*)vals;
+  A.sort.keys_alt = (u64*)ws;
+  A.sort.pay_alt = (u64*)((char*)ws + lb);
+  A.sort.hist = (unsigned int*)((char*)ws + 2 * lb);
+  A.sort.barrier = (unsigned int*)((char*)ws + 2 * lb + (size_t)2 * sm_count() * 256 * sizeof(unsigned int));
+  A.n = L;
+  A.flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
+  A.key_bits = 8 * w;
+  A.uniq_out = uniq_out;
+  A.vals_out = (u64*)vals_out;
+  cudaMemsetAsync(A.sort.barrier, 0, 256, st);
+  const void* kernel;
   switch (w) {
-    case 1: k_emit_pairs<1><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
-    case 2: k_emit_pairs<2><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
-    case 4: k_emit_pairs<4><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
-    default: k_emit_pairs<8><<<g.blocks, g.threads, 0, st>>>((const u64*)keys, (const u64*)vals, L, flip, uniq_out, (u64*)vals_out); break;
+    case 1: kernel = (const void*)k_sort_emit_pairs<1>; break;
+    case 2: kernel = (const void*)k_sort_emit_pairs<2>; break;
+    case 4: kernel = (const void*)k_sort_emit_pairs<4>; break;
+    default: kernel = (const void*)k_sort_emit_pairs<8>; break;
   }
-  return check_launch("k_emit_pairs");
+  void* params[] = {&A};
+  cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(sm_count()), dim3(CS_THREADS), params, 0, st);
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    return FRB_ERR_CUDA;
+  }
+  return check_launch("k_sort_emit_pairs");
 }
 
 // workspace: sorted keys (n * kw) | ping-pong (n * kw) | block counts | radix histograms;  kw = 4 (W<=4) or 8
