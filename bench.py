@@ -249,6 +249,7 @@ def run_ours(args):
     sampler.start()
   launches0 = _lib.launch_count()
   step_ms, k3_ms, k1_ms, k2_ms, merge_ms = [], [], [], [], []
+  stage_ms = {}
   barrier()
   for _ in range(args.steps):
     work.copy_(pristine)          # un-timed restore (also rewrites 8 GiB: L2 holds nothing of the input)
@@ -265,6 +266,10 @@ def run_ours(args):
       k2_ms.append(timers["k2"][0].elapsed_time(timers["k2"][1]))
       if "merge" in timers:
         merge_ms.append(timers["merge"][0].elapsed_time(timers["merge"][1]))
+      for name, (a, b) in timers.items():
+        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+      stage_ms.setdefault("start_to_k1", []).append(e0.elapsed_time(timers["k1"][0]))
+      stage_ms.setdefault("k2_to_k3", []).append(timers["k2"][1].elapsed_time(timers["k3"][0]))
     del res
   barrier()
   launches = _lib.launch_count() - launches0
@@ -283,6 +288,7 @@ def run_ours(args):
                         "k1_ms": float(np.mean(k1_ms)) if k1_ms else None, "k3_ms": float(np.mean(k3_ms)) if k3_ms else None,
                         "k2_ms": float(np.mean(k2_ms)) if k2_ms else None,
                         "merge_ms": float(np.mean(merge_ms)) if merge_ms else None,
+                        "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
                         "gpu_launches": int(launches), "labels": n_labels}))
     if world > 1:
       dist.destroy_process_group()

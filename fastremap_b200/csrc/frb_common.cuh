@@ -367,6 +367,9 @@ struct TileMap {
   __device__ __forceinline__ TileMap(size_t nvec, size_t run_) {
     tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
     run = run_ < 1 ? 1 : run_;
+    // short arrays (label tables, pipeline chunks): shorter runs, so that every CTA of the grid gets work
+    const size_t fair = tiles / (2 * (size_t)gridDim.x);
+    if (run > fair) run = fair < 1 ? 1 : fair;
     const size_t nruns = (tiles + run - 1) / run;
     const size_t b = blockIdx.x, g = gridDim.x;
     const size_t mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA

@@ -106,6 +106,16 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
       unsigned int tot = 0, part = 0;
       const unsigned int* col = hist + threadIdx.x;
       unsigned int b = 0;
+      for (; b + 32 <= active; b += 32) {  // 32 independent L2 loads in flight per thread
+        unsigned int v[32];
+#pragma unroll
+        for (int q = 0; q < 32; q++) v[q] = __ldcg(col + (size_t)(b + q) * 256);
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          part += (b + q) < blockIdx.x ? v[q] : 0u;
+          tot += v[q];
+        }
+      }
       for (; b + 8 <= active; b += 8) {
         unsigned int v[8];
 #pragma unroll

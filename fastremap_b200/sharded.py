@@ -85,7 +85,9 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   if offset is None or total is None:
     offset, total = shard_offsets(n_local, group)
 
+  api._ev(timers, "init", 0)
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), _lib.EMPTY)
+  api._ev(timers, "init", 1)
   while True:
     cap_pairs = local.entries_max()
     k64, v64 = D.alloc(cap_pairs * 8), D.alloc(cap_pairs * 8)
@@ -94,25 +96,32 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
                                     local.cap, D.ptr(local.meta), D.stream()), "frb_renumber_build")
     api._ev(timers, "k1", 1)
     api._ev(timers, "merge", 0)
+    api._ev(timers, "export", 0)
     _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), cap_pairs,
                                   D.stream()), "frb_table_export")
+    api._ev(timers, "export", 1)
     # every rank learns every rank's (count, overflow flag, exported pairs) in one small collective
+    api._ev(timers, "xchg_meta", 0)
     metas = torch.empty(world * _lib.META_WORDS, dtype=torch.int64, device=local.meta.device)
     dist.all_gather_into_tensor(metas, local.meta, group=group)
     metas_h = metas.cpu().view(world, _lib.META_WORDS).tolist()            # host round trip 1
+    api._ev(timers, "xchg_meta", 1)
     counts = [int(r[_lib.META_COUNT]) for r in metas_h]
     overfull = [bool(r[_lib.META_OVERFLOW]) or (not local.direct and 2 * cnt > local.cap) for r, cnt in zip(metas_h, counts)]
     if not any(overfull):
       break
     local.grow(max(counts))  # all ranks take the same decision: tables stay the same size everywhere
 
+  api._ev(timers, "xchg_pairs", 0)
   m = max(max(counts), 1)
   packed = torch.empty(2 * m * 8, dtype=torch.uint8, device=k64.device)
   packed[: m * 8] = k64[: m * 8]
   packed[m * 8:] = v64[: m * 8]
   gathered = torch.empty(world * 2 * m * 8, dtype=torch.uint8, device=k64.device)
   dist.all_gather_into_tensor(gathered, packed, group=group)
+  api._ev(timers, "xchg_pairs", 1)
 
+  api._ev(timers, "insert", 0)
   merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY)
   for r in range(world):
     if counts[r]:
@@ -120,6 +129,7 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
       vr = gathered[r * 2 * m * 8 + m * 8: r * 2 * m * 8 + m * 8 + counts[r] * 8]
       _lib.check(L.frb_table_insert(D.ptr(kr), 8, D.ptr(vr), 8, 0, counts[r], _lib.OP_MIN, merged.direct, D.ptr(merged.slots),
                                     merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert")
+  api._ev(timers, "insert", 1)
   api._ev(timers, "merge", 1)
   rb = api._RankBuffers(merged, dtype)
   api._ev(timers, "k2", 0)
