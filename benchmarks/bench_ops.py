@@ -102,7 +102,7 @@ def main():
     m, mn, table = timed(lambda: api.table_from_arrays(keys, vals, L, np.uint64), args.reps)
     print(json.dumps({"op": "remap table build from %d-entry key/value arrays" % L, "ms": m, "ms_min": mn}), flush=True)
     work = torch.empty_like(vol)
-    m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work), args.reps,
+    m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L)), args.reps,
                      setup=lambda: work.copy_(vol))
     report("remap u64 in place, %d-entry table, preserve_missing_labels (config 3)" % L, n, 16, m, mn, labels_in_volume=nu)
     del vol, work, table
@@ -117,7 +117,7 @@ def main():
       m, mn, table = timed(lambda: api.table_from_arrays(kb, kb, keep.numel(), np.uint64), args.reps)
       print(json.dumps({"op": "mask_except table build from %d labels" % keep.numel(), "ms": m, "ms_min": mn}), flush=True)
       work = torch.empty_like(cc)
-      m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work), args.reps,
+      m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel())), args.reps,
                        setup=lambda: work.copy_(cc))
       report("mask_except u64 in place, %d kept of %d labels (config 5)" % (keep.numel(), nu), n, 16, m, mn)
       del work, table, uniq, keep, kb

@@ -127,6 +127,13 @@ def _run_build(fn, table: LabelTable):
 # lane), not the size of the table: measured on B200, remap of 1024^3 uint64 through 10^6 labels
 # takes 6.8 ms at load 0.48, 4.2 ms at 0.24, 3.8 ms at 0.12.  So lookup tables get 8+ slots per label.
 LOOKUP_SLOTS_PER_ENTRY = 8
+# ... and once the table no longer fits L1, K3 issues the table loads of two rows of a warp-tile
+# before it consumes either (mask_except with 5 M labels: 5.0 -> 4.5 ms).
+BATCH_LOOKUP_MIN_LABELS = 1 << 14
+
+
+def _batch_rows(n_labels: int) -> int:
+  return 2 if n_labels >= BATCH_LOOKUP_MIN_LABELS else 0
 
 
 def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positions=False, resolve=True) -> LabelTable:
@@ -150,10 +157,11 @@ def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positio
 
 
 def _relabel(src_buf, n, dtype, table: LabelTable, policy, fill_bits=0, zero_fixed=False, dst_wide=None, dst_narrow=None,
-             narrow_width=0, add=0, guard_overflow=False):
+             narrow_width=0, add=0, guard_overflow=False, batch_rows=0):
   _lib.check(_L().frb_relabel(D.ptr(src_buf), D.ptr(dst_wide), D.ptr(dst_narrow), narrow_width, n, D.code(dtype),
                               D.ptr(table.slots), table.cap, table.direct, D.ptr(table.meta), policy, fill_bits,
-                              1 if zero_fixed else 0, add & _lib.EMPTY, 1 if guard_overflow else 0, D.stream()), "frb_relabel")
+                              1 if zero_fixed else 0, add & _lib.EMPTY, 1 if guard_overflow else 0, batch_rows,
+                              D.stream()), "frb_relabel")
 
 
 def _cast(src_buf, src_dtype, dst_dtype, n):
@@ -633,7 +641,7 @@ def remap(arr, table, preserve_missing_labels=False, in_place=False):
     kd, vd = D.upload_array(keys), D.upload_array(vals)
     t = table_from_arrays(kd, vd, len(keys), adtype, op=_lib.OP_SET)
     policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
-    _relabel(v.buf, v.n, adtype, t, policy, dst_wide=v.buf)
+    _relabel(v.buf, v.n, adtype, t, policy, dst_wide=v.buf, batch_rows=_batch_rows(len(keys)))
     if not preserve_missing_labels:
       _check_missing(t, v.buf, adtype, "{} was not in the remap table.")
 
@@ -672,7 +680,7 @@ def mask_except(arr, labels, in_place=False, value=0):
   if v.n:
     kd = D.upload_array(lab)
     t = table_from_arrays(kd, kd, len(lab), adtype, op=_lib.OP_SET)
-    _relabel(v.buf, v.n, adtype, t, _lib.MISS_FILL, fill_bits=fill, dst_wide=v.buf)
+    _relabel(v.buf, v.n, adtype, t, _lib.MISS_FILL, fill_bits=fill, dst_wide=v.buf, batch_rows=_batch_rows(len(lab)))
   if is_t:
     return arr if v.aliases_input else D.emit(v.buf, adtype, v.shape, v.order, True)
   if in_place_eff:
@@ -743,7 +751,7 @@ def remap_from_array_kv(arr, keys, vals, preserve_missing_labels=True, in_place=
     # positions + max => the last duplicate of a key supplies its value (fastremap.pyx:810-811)
     t = table_from_arrays(kv.buf, vv.buf, nk, dt, op=_lib.OP_MAX, positions=True) if nk else LabelTable(dt, 1, 0)
     policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
-    _relabel(v.buf, v.n, dt, t, policy, dst_wide=v.buf)
+    _relabel(v.buf, v.n, dt, t, policy, dst_wide=v.buf, batch_rows=_batch_rows(nk))
     if not preserve_missing_labels:
       _check_missing(t, v.buf, dt, "{} was not in the remap keys.")
   return _finish_1d(arr, v, in_place_eff)
@@ -923,7 +931,7 @@ def _inverse_positions(buf, n, dtype, uniq_buf, nu):
   w = dtype.itemsize
   t = table_from_arrays(uniq_buf, None, nu, dtype, op=_lib.OP_SET, positions=True, resolve=False)
   out = D.alloc(n * w)
-  _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_wide=out)
+  _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_wide=out, batch_rows=_batch_rows(nu))
   if w == 8:
     return out
   return _cast(out, np.dtype("u%d" % w), np.uint64, n)  # positions < nu <= 2^(8w): they fit the label width

@@ -219,6 +219,13 @@ __device__ __forceinline__ SlotPair ld_pair_ro(const Slot* s) {
   return r;
 }
 
+// same, but free to be scheduled early / batched by the compiler (pure load of a constant table)
+__device__ __forceinline__ SlotPair ld_pair_ro_batch(const Slot* s) {
+  SlotPair r;
+  asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a.key), "=l"(r.a.val), "=l"(r.b.key), "=l"(r.b.val) : "l"(s));
+  return r;
+}
+
 template <int OP>
 __device__ __forceinline__ bool op_settled(u64 cur, u64 v) {
   if (OP == FRB_OP_MIN) return cur <= v;

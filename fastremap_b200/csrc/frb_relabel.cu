@@ -112,6 +112,70 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
   }
 }
 
+// Batched variant for tables that do not fit L1 (remap / mask / mask_except with 10^5+ labels): the
+// home-pair loads of NB rows of the warp-tile (NB * V per lane) are issued before any of them is
+// consumed, so their L2 / HBM round trips overlap instead of queueing row after row.  In place or
+// out of place at the input width only (what the remap family needs).
+template <int W, int NB>
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int run) {
+  constexpr int V = 16 / W;
+  constexpr int R = STREAM_ROWS;
+  static_assert(W >= 4 && R % NB == 0, "hashed tables only");
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31;
+  if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
+  auto tile_end = [&](const uint4* stage, size_t vb) {
+#pragma unroll
+    for (int u0 = 0; u0 < R; u0 += NB) {
+      u64 key[NB][V], h[NB][V];
+      Probe first[NB][V];
+      bool valid[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int u = u0 + q;
+        valid[q] = vb + u * 32 + lane < nvec;
+        const uint4 cur = valid[q] ? stage[u * 32 + lane] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          key[q][j] = vec_get<W>(cur, j);
+          h[q][j] = home_slot(key[q][j], A.mask);
+          const SlotPair sp = ld_pair_ro_batch(A.slots + h[q][j]);
+          first[q][j].a = sp.a;
+          first[q][j].b = sp.b;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        if (!valid[q]) continue;
+        const size_t i0 = (vb + (u0 + q) * 32 + lane) * V;
+        u64 r[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) r[j] = relabel_one<true>(A, key[q][j], h[q][j], first[q][j], i0 + j);
+        store_results<V, W>(dst_wide, i0, r);
+      }
+    }
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, false, true>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 key = ld_elem<W>(src, i);
+      u64 h;
+      const Probe first = first_probe<true>(A, key, &h);
+      st_elem<W>(dst_wide, i, relabel_one<true>(A, key, h, first, i));
+    }
+  }
+}
+
+template <int W, int NB>
+static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, cudaStream_t st) {
+  const size_t tiles = stream_tiles(n, W);
+  k_relabel_batched<W, NB><<<stream_grid(k_relabel_batched<W, NB>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, tile_run());
+  return check_launch("k_relabel_batched");
+}
+
 template <int W, int WO, bool WIDE>
 static int launch_relabel(const void* src, void* dst_wide, void* dst_narrow, size_t n, const RelabelArgs& A, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);
@@ -238,7 +302,7 @@ extern "C" {
 
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill, int zero_fixed,
-                uint64_t add, int guard_overflow, void* stream) {
+                uint64_t add, int guard_overflow, int batch_rows, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (!dst_wide && !dst_narrow) ||
       (n && (!src || !aligned16(src) || (dst_wide && !aligned16(dst_wide)) || (dst_narrow && !aligned16(dst_narrow)))) ||
       policy < 0 || policy > 2) {
@@ -259,6 +323,10 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
   A.add = add;
   A.guard = guard_overflow ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (batch_rows > 1 && !A.direct && w >= 4 && dst_wide && !dst_narrow) {
+    if (w == 4) return batch_rows >= 4 ? launch_relabel_batched<4, 4>(src, dst_wide, n, A, st) : launch_relabel_batched<4, 2>(src, dst_wide, n, A, st);
+    return batch_rows >= 4 ? launch_relabel_batched<8, 4>(src, dst_wide, n, A, st) : launch_relabel_batched<8, 2>(src, dst_wide, n, A, st);
+  }
   switch (w) {
     case 1: return dispatch_relabel<1>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
     case 2: return dispatch_relabel<2>(src, dst_wide, dst_narrow, narrow_width, n, A, st);

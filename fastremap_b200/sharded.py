@@ -234,7 +234,7 @@ def relabel_sharded(buf, n_local, dtype, keys_dev, vals_dev, n_keys, policy, fil
   from . import device as D
   dtype = np.dtype(dtype)
   t = api.table_from_arrays(keys_dev, vals_dev, n_keys, dtype, op=_lib.OP_SET) if n_keys else api.LabelTable(dtype, 1, 0)
-  api._relabel(buf, n_local, dtype, t, policy, fill_bits=fill_bits, dst_wide=buf)
+  api._relabel(buf, n_local, dtype, t, policy, fill_bits=fill_bits, dst_wide=buf, batch_rows=api._batch_rows(n_keys))
   if policy != _lib.MISS_ERROR:
     return
   idx = int(t.read_meta()[_lib.META_MISSING_INDEX])

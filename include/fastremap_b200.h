@@ -119,11 +119,14 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
  *   zero_fixed != 0: label 0 maps to 0 without a lookup (renumber's preserve_zero).
  *   add: added to every value found in the table (renumber: table value = rank, add = start).
  *   guard_overflow != 0: do nothing if meta[FRB_META_OVERFLOW] is set (chunk pipelines launch the
- *   relabel before the host has seen whether the build of that chunk overflowed). */
+ *   relabel before the host has seen whether the build of that chunk overflowed).
+ *   batch_rows: 0 / 1 = look up row by row (a table whose live part sits in L1: renumber); 2 or 4 =
+ *   issue the table loads of that many rows of a warp-tile before consuming any (tables of 10^5+
+ *   labels that live in L2 / HBM; wide destination only). */
 enum { FRB_MISS_KEEP = 0, FRB_MISS_ERROR = 1, FRB_MISS_FILL = 2 };
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill,
-                int zero_fixed, uint64_t add, int guard_overflow, void* stream);
+                int zero_fixed, uint64_t add, int guard_overflow, int batch_rows, void* stream);
 /* single-pair compare-and-replace, the :721-729 fast path of _remap */
 int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream);
 /* remap_from_array (fastremap.pyx:771-791): dst[i] = src[i] < nvals ? vals[src[i]] : src[i] (unsigned dtypes) */

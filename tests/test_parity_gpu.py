@@ -417,3 +417,31 @@ def test_unique_torch_outputs(frb):
   assert np.array_equal(idx.cpu().view(torch.int64).numpy().astype(np.int64), idx2)
   assert np.array_equal(inv.cpu().view(torch.int64).numpy().astype(np.int64), inv2.reshape(a.shape))
   assert np.array_equal(cts.cpu().view(torch.int64).numpy().astype(np.int64), cts2)
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.uint64, np.int32, np.int64])
+def test_big_lookup_tables_batched(frb, oracle, dtype):
+  """remap / mask / mask_except / remap_from_array_kv through tables of > 2^14 labels (the batched-lookup
+  variant of K3), ragged length, half of the labels missing from the table."""
+  rng = np.random.default_rng(31)
+  info = np.iinfo(dtype)
+  pool = np.unique(rng.integers(max(int(info.min), -2 ** 62), min(int(info.max), 2 ** 62), size=60000, dtype=np.int64).astype(dtype))
+  pool = np.concatenate([pool, np.array([info.max, info.min], dtype=dtype)])
+  a = np.repeat(pool[rng.integers(0, pool.size, size=30011)], 3)[:90017].astype(dtype)
+  keys = pool[::2]
+  assert keys.size > (1 << 14)
+  table = {int(k): int(v) for k, v in zip(keys, np.roll(keys, 7))}
+  assert np.array_equal(frb.remap(np.copy(a), table, preserve_missing_labels=True), oracle.remap(np.copy(a), table, preserve_missing_labels=True))
+  with pytest.raises(KeyError) as ge:
+    frb.remap(np.copy(a), table, preserve_missing_labels=False)
+  with pytest.raises(KeyError) as ee:
+    oracle.remap(np.copy(a), table, preserve_missing_labels=False)
+  assert ge.value.args == ee.value.args
+  keep = [int(k) for k in keys]
+  assert np.array_equal(frb.mask_except(np.copy(a), keep, value=5), oracle.mask_except(np.copy(a), keep, value=5))
+  assert np.array_equal(frb.mask(np.copy(a), keep[:20000], value=9), oracle.mask(np.copy(a), keep[:20000], value=9))
+  vals = np.roll(keys, 3)
+  assert np.array_equal(frb.remap_from_array_kv(np.copy(a), keys, vals), oracle.remap_from_array_kv(np.copy(a), keys, vals))
+  u, inv = frb.unique(a, return_inverse=True)
+  eu, einv = oracle.unique(a, return_inverse=True)
+  assert np.array_equal(u, eu) and np.array_equal(inv, einv) and inv.dtype == einv.dtype
