@@ -270,12 +270,21 @@ def run_ours(args):
         stage_ms.setdefault(name, []).append(a.elapsed_time(b))
       stage_ms.setdefault("start_to_k1", []).append(e0.elapsed_time(timers["k1"][0]))
       stage_ms.setdefault("k2_to_k3", []).append(timers["k2"][1].elapsed_time(timers["k3"][0]))
+      stage_ms.setdefault("k3_to_end", []).append(timers["k3"][1].elapsed_time(e1))
+      if "merge" in timers:
+        stage_ms.setdefault("k1_to_merge", []).append(timers["k1"][1].elapsed_time(timers["merge"][0]))
+        stage_ms.setdefault("merge_to_k2", []).append(timers["merge"][1].elapsed_time(timers["k2"][0]))
     del res
   barrier()
   launches = _lib.launch_count() - launches0
   clocks = sampler.stop() if rank == 0 else None
 
   total_ms = float(sum(step_ms))
+  per_rank = None
+  if world > 1 and args.no_e2e:
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": total_ms / args.steps,
+                                      "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()}})
   if world > 1:
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,6 +298,7 @@ def run_ours(args):
                         "k2_ms": float(np.mean(k2_ms)) if k2_ms else None,
                         "merge_ms": float(np.mean(merge_ms)) if merge_ms else None,
                         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
+                        "per_rank": per_rank,
                         "gpu_launches": int(launches), "labels": n_labels}))
     if world > 1:
       dist.destroy_process_group()

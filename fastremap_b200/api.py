@@ -14,6 +14,7 @@ Keyword-only extras that do not change any default: `max_labels` (table sizing h
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import numpy as np
 import torch
@@ -93,6 +94,16 @@ class LabelTable:
 
   def read_meta(self) -> np.ndarray:
     return D.read_u64(self.meta)
+
+  def read_meta_after(self, event) -> np.ndarray:
+    """The meta block as it is once `event` (recorded on the launching stream) has happened, read
+    through a side stream: the host does not wait for kernels queued behind the event (renumber's K3
+    leaves every word the host needs untouched)."""
+    side = D.side_stream()
+    side.wait_event(event)
+    with torch.cuda.stream(side):
+      host = self.meta.to("cpu", non_blocking=False)
+    return host.numpy().view(np.uint64)
 
   def entries_max(self) -> int:
     """Most labels this table is allowed to hold before it is grown (load factor 0.5; +1 for the
@@ -320,17 +331,69 @@ def _out_dtype(dtype, start, nl):
   return np.dtype(fit_dtype(dtype, factor))
 
 
+def _narrow_limits(dtype, start, n_max):
+  if not isinstance(start, (int, np.integer)):
+    return None
+  return _narrow_limits_cached(np.dtype(dtype).str, int(start), int(n_max))
+
+
+@functools.lru_cache(maxsize=256)
+def _narrow_limits_cached(dtype, start, n_max):
+  """(lim1, lim2, lim4) for frb_relabel_auto: the refit width is w' iff n_labels < lim[w'] (and not
+  < the next smaller limit).  None when the width is not a monotone function of the label count on
+  [0, n_max] (negative start, counters that wrap in the array dtype: fastremap.pyx:225, :253-255)."""
+  dtype = np.dtype(dtype)
+  info = np.iinfo(dtype)
+  if start < 0 or start + n_max > int(info.max):
+    return None
+  lims = []
+  for wo in (1, 2, 4):
+    if _out_dtype(dtype, start, 0).itemsize > wo:
+      lims.append(0)
+      continue
+    lo, hi = 0, int(n_max)  # largest nl in [0, n_max] whose refit width is <= wo
+    while lo < hi:
+      mid = (lo + hi + 1) // 2
+      if _out_dtype(dtype, start, mid).itemsize <= wo:
+        lo = mid
+      else:
+        hi = mid - 1
+    lims.append(lo + 1)
+  return tuple(lims)
+
+
+def _relabel_auto(src_buf, n, dtype, table: LabelTable, preserve_zero, start, write_wide, limits):
+  """K3 with the refit width picked on the device (queued behind K2 without a host round trip).
+  Returns the narrow buffer (n * w/2 bytes; which part is meaningful is known once meta is read)."""
+  w = np.dtype(dtype).itemsize
+  narrow = D.alloc(n * max(w // 2, 1))
+  _lib.check(_L().frb_relabel_auto(D.ptr(src_buf), D.ptr(src_buf), D.ptr(narrow), n, D.code(dtype), D.ptr(table.slots), table.cap,
+                                   table.direct, D.ptr(table.meta), 1 if preserve_zero else 0, int(np.int64(start)) & _lib.EMPTY,
+                                   1 if write_wide else 0, limits[0], limits[1], limits[2], D.stream()), "frb_relabel_auto")
+  return narrow
+
+
+def _auto_result(src_buf, narrow, dtype, start, table, rb, meta) -> RenumberResult:
+  nl = int(meta[_lib.META_ASSIGNED])
+  res = RenumberResult()
+  res.keys, res.ids, res.n_labels, res.table = rb.keys, rb.ids, nl, table
+  res.out_dtype = _out_dtype(dtype, start, nl)
+  narrowed = res.out_dtype.itemsize < np.dtype(dtype).itemsize
+  res.out = narrow if narrowed else src_buf
+  res.wide = src_buf  # holds ids when write_wide or when nothing narrower fitted; callers use it only then
+  return res
+
+
 def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
                     flat_offset=0, total_n=None, timers=None) -> RenumberResult:
   """
   K1 -> K2 -> K3 on a flat device buffer.
     write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
     timers: optional dict; receives CUDA event pairs "k1" / "k2" / "k3" recorded on the launching stream.
-  K1 and K2 are queued back to back (the label count stays on the device); the host reads the
-  table's meta block once, to choose the refit dtype before K3.
+  The three kernels are queued back to back: the label count stays on the device (K2 reads it there,
+  K3 picks the refit width from it), and the host reads the table's meta block once, afterwards.
   """
   dtype = np.dtype(dtype)
-  w = dtype.itemsize
   c = D.code(dtype)
   L = _L()
   table = LabelTable(dtype, _default_entries(n, max_labels), _lib.EMPTY)
@@ -348,15 +411,27 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
     _ev(timers, "k2", 0)
     _rank(table, rb, dtype, start, 0, index_count)
     _ev(timers, "k2", 1)
-    meta = table.read_meta()
-    if not table.overfull(meta):
+    limits = _narrow_limits(dtype, start, min(n, rb.capacity))  # host work while K1 runs (cached across calls)
+    if limits is not None:
+      ranked = torch.cuda.Event()
+      ranked.record()
+      _ev(timers, "k3", 0)
+      narrow = _relabel_auto(src_buf, n, dtype, table, preserve_zero, start, write_wide, limits)
+      _ev(timers, "k3", 1)
+      meta = table.read_meta_after(ranked)  # K3 keeps running while the host learns the label count
+    else:
+      meta = table.read_meta()
+    if not meta[_lib.META_OVERFLOW]:
       break
-    table.grow(int(meta[_lib.META_COUNT]))  # K3 has not run: the input is intact, start over
+    table.grow(int(meta[_lib.META_COUNT]))  # K3 is guarded by the flag: the input is intact, start over
+  if limits is not None:
+    return _auto_result(src_buf, narrow, dtype, start, table, rb, meta)
   return _renumber_finish(src_buf, n, dtype, start, preserve_zero, write_wide, table, rb, meta, timers)
 
 
 def _renumber_finish(src_buf, n, dtype, start, preserve_zero, write_wide, table, rb, meta, timers=None) -> RenumberResult:
-  """K3 of renumber once the table holds ranks: pick the refit dtype, relabel (+ fused narrow store)."""
+  """K3 of renumber once the table holds ranks and the host knows their number: pick the refit dtype,
+  relabel (+ fused narrow store).  The general path (any `start`, wrapping counters)."""
   w = dtype.itemsize
   nl = int(meta[_lib.META_ASSIGNED])
   out_dtype = _out_dtype(dtype, start, nl)

@@ -112,6 +112,53 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
   }
 }
 
+// renumber's K3 when the refit width is still on the device: the number of labels (meta[ASSIGNED])
+// picks the narrow width from thresholds the host derived from fit_dtype, so that K1 -> K2 -> K3 can
+// be queued back to back without a host round trip.  wide_always: in_place semantics (ids also
+// written at the input width); otherwise the wide store happens only when nothing narrower fits.
+template <int W>
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A, u64 lim1, u64 lim2, u64 lim4,
+               int wide_always, int run) {
+  constexpr int V = 16 / W;
+  constexpr bool HASHED = W >= 4;
+  const size_t nvec = n / V;
+  if (__ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;  // the build overflowed: the host grows the table and starts over
+  const u64 nl = __ldcg(&A.meta_ro[FRB_META_ASSIGNED]);
+  int wo = nl < lim1 ? 1 : (nl < lim2 ? 2 : (nl < lim4 ? 4 : 0));
+  if (wo >= W) wo = 0;
+  const bool wide = wide_always || wo == 0;
+  auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
+    if (!valid) return;
+    u64 key[V], h[V], r[V];
+    Probe first[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      key[j] = vec_get<W>(cur, j);
+      first[j] = first_probe<HASHED>(A, key[j], &h[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
+    if (wide) store_results<V, W>(dst_wide, i0, r);
+    if (W > 1 && wo == 1) store_results<V, 1>(dst_narrow, i0, r);
+    if (W > 2 && wo == 2) store_results<V, (W > 2 ? 2 : 1)>(dst_narrow, i0, r);
+    if (W > 4 && wo == 4) store_results<V, (W > 4 ? 4 : 1)>(dst_narrow, i0, r);
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, false, true>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 key = ld_elem<W>(src, i);
+      u64 h;
+      const Probe first = first_probe<HASHED>(A, key, &h);
+      const u64 r = relabel_one<HASHED>(A, key, h, first, i);
+      if (wide) st_elem<W>(dst_wide, i, r);
+      if (wo) st_elem_rt(dst_narrow, wo, i, r);
+    }
+  }
+}
+
 // Batched variant for tables that do not fit L1 (remap / mask / mask_except with 10^5+ labels): the
 // home-pair loads of NB rows of the warp-tile (NB * V per lane) are issued before any of them is
 // consumed, so their L2 / HBM round trips overlap instead of queueing row after row.  In place or
@@ -333,6 +380,41 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
     case 4: return dispatch_relabel<4>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
     default: return dispatch_relabel<8>(src, dst_wide, dst_narrow, narrow_width, n, A, st);
   }
+}
+
+int frb_relabel_auto(const void* src, void* dst_wide, void* dst_narrow, size_t n, int dtype, const void* slots, uint64_t cap,
+                     int direct, uint64_t* meta, int zero_fixed, uint64_t add, int wide_always, uint64_t lim1, uint64_t lim2,
+                     uint64_t lim4, void* stream) {
+  if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || !dst_wide || !dst_narrow ||
+      (n && (!src || !aligned16(src) || !aligned16(dst_wide) || !aligned16(dst_narrow)))) {
+    set_error("frb_relabel_auto: bad arguments (both destinations needed, 16-byte aligned)");
+    return FRB_ERR_BAD_ARG;
+  }
+  if (n == 0) return FRB_OK;
+  const int w = dtype_width(dtype);
+  RelabelArgs A;
+  A.slots = (const Slot*)slots;
+  A.mask = cap - 1;
+  A.meta_ro = (const u64*)meta;
+  A.meta = (u64*)meta;
+  A.fill = 0;
+  A.direct = direct ? 1 : 0;
+  A.policy = FRB_MISS_ERROR;
+  A.zero_fixed = zero_fixed ? 1 : 0;
+  A.add = add;
+  A.guard = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tiles = stream_tiles(n, w);
+  const uint4* p = (const uint4*)src;
+#define FRB_AUTO(WW) k_relabel_auto<WW><<<stream_grid(k_relabel_auto<WW>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, dst_wide, dst_narrow, n, A, lim1, lim2, lim4, wide_always, tile_run())
+  switch (w) {
+    case 1: FRB_AUTO(1); break;
+    case 2: FRB_AUTO(2); break;
+    case 4: FRB_AUTO(4); break;
+    default: FRB_AUTO(8); break;
+  }
+#undef FRB_AUTO
+  return check_launch("k_relabel_auto");
 }
 
 int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream) {

@@ -67,6 +67,17 @@ def stream():
   return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_side_streams = {}
+
+
+def side_stream() -> torch.cuda.Stream:
+  """A per-device helper stream for small reads that must not wait for the main stream's tail."""
+  idx = torch.cuda.current_device()
+  if idx not in _side_streams:
+    _side_streams[idx] = torch.cuda.Stream(device=idx)
+  return _side_streams[idx]
+
+
 def ptr(t):
   if t is None:
     return None

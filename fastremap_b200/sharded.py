@@ -95,6 +95,7 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
                                     local.cap, D.ptr(local.meta), D.stream()), "frb_renumber_build")
     api._ev(timers, "k1", 1)
+    limits = api._narrow_limits(dtype, start, int(total))  # host work while K1 runs (cached across calls)
     api._ev(timers, "merge", 0)
     api._ev(timers, "export", 0)
     _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), cap_pairs,
@@ -122,7 +123,8 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   api._ev(timers, "xchg_pairs", 1)
 
   api._ev(timers, "insert", 0)
-  merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY)
+  # K3 looks every voxel up in this table: size it like a lookup table (load <= 1/8, see api.LOOKUP_SLOTS_PER_ENTRY)
+  merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
   for r in range(world):
     if counts[r]:
       kr = gathered[r * 2 * m * 8: r * 2 * m * 8 + counts[r] * 8]
@@ -135,9 +137,19 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   api._ev(timers, "k2", 0)
   api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
   api._ev(timers, "k2", 1)
-  meta = merged.read_meta()                                                # host round trip 2
+  if limits is not None:  # K3 queued behind K2: the refit width is picked on the device
+    ranked = torch.cuda.Event()
+    ranked.record()
+    api._ev(timers, "k3", 0)
+    narrow = api._relabel_auto(src_buf, n_local, dtype, merged, preserve_zero, start, write_wide, limits)
+    api._ev(timers, "k3", 1)
+    meta = merged.read_meta_after(ranked)                                  # host round trip 2 (K3 keeps running)
+  else:
+    meta = merged.read_meta()
   if meta[_lib.META_OVERFLOW]:
     raise api.FastremapB200Error("renumber_sharded: merged label table overflowed")
+  if limits is not None:
+    return api._auto_result(src_buf, narrow, dtype, start, merged, rb, meta)
   return api._renumber_finish(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, rb, meta, timers)
 
 

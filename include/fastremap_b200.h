@@ -127,6 +127,15 @@ enum { FRB_MISS_KEEP = 0, FRB_MISS_ERROR = 1, FRB_MISS_FILL = 2 };
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill,
                 int zero_fixed, uint64_t add, int guard_overflow, int batch_rows, void* stream);
+/* renumber's K3 queued straight behind K2: the refit width is chosen ON THE DEVICE from the number of
+ * labels nl = meta[FRB_META_ASSIGNED]: 1 byte if nl < lim1, else 2 if nl < lim2, else 4 if nl < lim4
+ * (widths >= the input width are ignored), else no narrow copy.  The host derives lim* from fit_dtype
+ * and reads nl afterwards to know which it was.  dst_narrow must hold n * (input width / 2) bytes.
+ * wide_always != 0: ids are also written at the input width (in_place); otherwise only when nothing
+ * narrower fits.  Does nothing if meta[FRB_META_OVERFLOW] is set.  Policy: missing label = error. */
+int frb_relabel_auto(const void* src, void* dst_wide, void* dst_narrow, size_t n, int dtype, const void* slots, uint64_t cap,
+                     int direct, uint64_t* meta, int zero_fixed, uint64_t add, int wide_always, uint64_t lim1, uint64_t lim2,
+                     uint64_t lim4, void* stream);
 /* single-pair compare-and-replace, the :721-729 fast path of _remap */
 int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t before, uint64_t after, void* stream);
 /* remap_from_array (fastremap.pyx:771-791): dst[i] = src[i] < nvals ? vals[src[i]] : src[i] (unsigned dtypes) */
