@@ -35,6 +35,8 @@ struct CoopSortBuffers {
   u64* pay;
   u64* keys_alt;  // ping-pong buffers
   u64* pay_alt;
+  u64* pay2;      // optional second payload (NULL: none) and its ping-pong buffer
+  u64* pay2_alt;
   unsigned int* hist;     // [2][gridDim.x][256] (double-buffered: a skipped pass has no second barrier)
   unsigned int* barrier;  // one word, zeroed before the launch
 };
@@ -45,7 +47,8 @@ inline size_t coop_sort_aux_bytes(int ctas) { return (size_t)2 * ctas * 256 * si
 // Sort the n pairs by bits [begin_bit, end_bit) of the key.  Must be called by every thread of every
 // CTA with identical arguments.  Shared memory: 3 * 256 + 8 * 256 + 8 words (static, declared here).
 __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n, int begin_bit, int end_bit,
-                                                unsigned int& generation, u64** sorted_keys, u64** sorted_pay) {
+                                                unsigned int& generation, u64** sorted_keys, u64** sorted_pay,
+                                                u64** sorted_pay2 = nullptr) {
   __shared__ unsigned int h[256];
   __shared__ unsigned int base[256];
   __shared__ unsigned int wc[CS_WARPS][256];
@@ -69,6 +72,9 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
   u64* vin = B.pay;
   u64* kout = B.keys_alt;
   u64* vout = B.pay_alt;
+  u64* win = B.pay2;
+  u64* wout = B.pay2_alt;
+  const bool two = B.pay2 != nullptr;
 
   int pass = 0;
   for (int shift = begin_bit; shift < end_bit && n > 1; shift += 8, pass++) {
@@ -153,7 +159,7 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
     if (skip) continue;
     // ---- stable scatter, tile by tile
     for (u64 tile = beg; tile < end; tile += CS_TILE) {
-      u64 val[CS_ITEMS];
+      u64 val[CS_ITEMS], val2[CS_ITEMS];
       unsigned int rank[CS_ITEMS];
       unsigned int dig[CS_ITEMS];
 #pragma unroll
@@ -161,6 +167,7 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
         const u64 i = tile + (u64)warp * (32 * CS_ITEMS) + k * 32 + lane;
         if (!one_tile) key[k] = i < end ? __ldcg(kin + i) : 0ull;
         val[k] = i < end ? __ldcg(vin + i) : 0ull;
+        val2[k] = (two && i < end) ? __ldcg(win + i) : 0ull;
       }
 #pragma unroll
       for (int k = 0; k < CS_ITEMS; k++) {
@@ -198,6 +205,7 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
           const u64 pos = (u64)base[dig[k]] + wc[warp][dig[k]] + rank[k];
           kout[pos] = key[k];
           vout[pos] = val[k];
+          if (two) wout[pos] = val2[k];
         }
       }
       __syncthreads();
@@ -209,9 +217,11 @@ __device__ __forceinline__ void coop_radix_sort(const CoopSortBuffers& B, u64 n,
     grid_barrier(B.barrier, generation);
     u64* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;
+    t = win; win = wout; wout = t;
   }
   *sorted_keys = kin;
   *sorted_pay = vin;
+  if (sorted_pay2) *sorted_pay2 = win;
 }
 
 }  // namespace frb

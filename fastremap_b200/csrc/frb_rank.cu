@@ -28,14 +28,16 @@ static constexpr u64 RANK_TAG = 0x8000000000000000ull;
 // restarts after a table overflow may already hold (incomplete) entries of LATER chunks
 struct PendingSel {
   u64 index_base, index_count;
-  u64* key_out;   // first index - index_base (the sort key)
-  u64* slot_out;  // slot index (the payload)
+  u64* key_out;    // first index - index_base (the sort key)
+  u64* slot_out;   // slot index (payload 1)
+  u64* label_out;  // label bits (payload 2: carried through the sort so that the assign phase has no dependent random read)
   __device__ __forceinline__ bool pick(u64 key, u64 val) const {
     return key != FRB_EMPTY && (val & RANK_TAG) && ((val & ~RANK_TAG) - index_base) < index_count;
   }
-  __device__ __forceinline__ void emit(u64 pos, u64, u64 val, u64 slot) const {
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot) const {
     key_out[pos] = (val & ~RANK_TAG) - index_base;
     slot_out[pos] = slot;
+    label_out[pos] = key;
   }
 };
 __global__ void k_pending_side(u64 cap, u64* meta, PendingSel sel, u64 capacity) {
@@ -72,20 +74,17 @@ __global__ void __launch_bounds__(CS_THREADS) k_rank_sort_assign(RankArgs A) {
   unsigned int generation = 0;
   u64* kin;
   u64* vin;
-  coop_radix_sort(A.sort, n, 0, A.index_bits, generation, &kin, &vin);
+  u64* win;
+  coop_radix_sort(A.sort, n, 0, A.index_bits, generation, &kin, &vin, &win);
 
-  // ---- rank r of the sorted list -> table value `assigned + r`; mapping arrays in id order
+  // ---- rank r of the sorted list -> table value `assigned + r`; mapping arrays in id order.
+  // Coalesced reads of (slot, label), one scattered fire-and-forget store per label.
   for (u64 r = (u64)blockIdx.x * CS_THREADS + threadIdx.x; r < n; r += (u64)gridDim.x * CS_THREADS) {
     const u64 s = __ldcg(vin + r);
+    const u64 key = __ldcg(win + r);
     const u64 rank = assigned + r;
-    u64 key;
-    if (s == A.cap) {
-      key = FRB_EMPTY;
-      A.meta[FRB_META_SIDE_VAL] = rank;
-    } else {
-      key = A.slots[s].key;
-      A.slots[s].val = rank;
-    }
+    if (s == A.cap) A.meta[FRB_META_SIDE_VAL] = rank;  // the out-of-band all-ones label
+    else A.slots[s].val = rank;
     st_elem<W>(A.keys_out, rank, key);
     st_elem<W>(A.ids_out, rank, trunc_width(A.start_bits + rank, W));  // counter arithmetic wraps in the array dtype (:225)
   }
@@ -101,10 +100,10 @@ using namespace frb;
 
 extern "C" {
 
-// workspace: 4 lists of `capacity` uint64 (sort key, payload, 2 ping-pong) + histograms + barrier word
+// workspace: 6 lists of `capacity` uint64 (sort key, 2 payloads, their ping-pong buffers) + histograms + barrier word
 size_t frb_renumber_rank_ws_bytes(size_t capacity) {
   const size_t c = capacity < 1 ? 1 : capacity;
-  return 4 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
+  return 6 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
 }
 
 int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, uint64_t index_base,
@@ -124,8 +123,10 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
   A.sort.pay = (u64*)(base + lb);
   A.sort.keys_alt = (u64*)(base + 2 * lb);
   A.sort.pay_alt = (u64*)(base + 3 * lb);
-  A.sort.hist = (unsigned int*)(base + 4 * lb);
-  A.sort.barrier = (unsigned int*)(base + 4 * lb + hb);
+  A.sort.pay2 = (u64*)(base + 4 * lb);
+  A.sort.pay2_alt = (u64*)(base + 5 * lb);
+  A.sort.hist = (unsigned int*)(base + 6 * lb);
+  A.sort.barrier = (unsigned int*)(base + 6 * lb + hb);
   A.slots = (Slot*)slots;
   A.cap = cap;
   A.meta = (u64*)meta;
@@ -145,6 +146,7 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
   sel.index_count = index_count;
   sel.key_out = A.sort.keys;
   sel.slot_out = A.sort.pay;
+  sel.label_out = A.sort.pay2;
   int rc = launch_table_scan(slots, cap, &A.meta[FRB_META_LIST_COUNT], (u64)capacity, sel, "k_table_scan<pending>", st);
   if (rc) return rc;
   k_pending_side<<<1, 32, 0, st>>>(cap, A.meta, sel, (u64)capacity);

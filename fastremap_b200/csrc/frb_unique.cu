@@ -515,6 +515,8 @@ int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, vo
   A.sort.pay = (u64*)vals;
   A.sort.keys_alt = (u64*)ws;
   A.sort.pay_alt = (u64*)((char*)ws + lb);
+  A.sort.pay2 = nullptr;
+  A.sort.pay2_alt = nullptr;
   A.sort.hist = (unsigned int*)((char*)ws + 2 * lb);
   A.sort.barrier = (unsigned int*)((char*)ws + 2 * lb + (size_t)2 * sm_count() * 256 * sizeof(unsigned int));
   A.n = L;
