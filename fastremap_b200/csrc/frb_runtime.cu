@@ -71,6 +71,24 @@ k_table_insert(const void* __restrict__ keys, int kw, const void* __restrict__ v
   block_add_to(&meta[FRB_META_COUNT], inserted);
 }
 
+// the multi-GPU merge: `world` segments of an all-gathered buffer, segment r = [m keys | m values]
+// (uint64 each) of which the first metas[r][COUNT] pairs are valid
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_table_insert_gathered(const u64* __restrict__ gathered, u64 m, int world, const u64* __restrict__ metas, int direct,
+                        Slot* slots, u64 mask, u64* meta) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t total = (size_t)m * (size_t)world;
+  unsigned int inserted = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / m, j = i - r * m;
+    if (j >= metas[r * FRB_META_WORDS + FRB_META_COUNT]) continue;
+    const u64* seg = gathered + r * 2 * m;
+    table_update<OP>(slots, mask, direct, meta, seg[j], seg[m + j], &inserted);
+  }
+  block_add_to(&meta[FRB_META_COUNT], inserted);
+}
+
 __global__ void __launch_bounds__(256)
 k_table_resolve(const void* __restrict__ vals, int vw, Slot* slots, u64 cap, u64* meta) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -158,6 +176,28 @@ int frb_table_insert(const void* keys, int key_width, const void* vals, int val_
     default: set_error("frb_table_insert: bad op"); return FRB_ERR_BAD_ARG;
   }
   return check_launch("k_table_insert");
+}
+
+int frb_table_insert_gathered(const uint64_t* gathered, uint64_t m, int world, const uint64_t* metas, int op, int direct,
+                              void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+  if (!gathered || !metas || !slots || !meta || m == 0 || world < 1 || (cap & (cap - 1)) != 0) {
+    set_error("frb_table_insert_gathered: bad arguments");
+    return FRB_ERR_BAD_ARG;
+  }
+  Grid g = grid_for((size_t)m * (size_t)world, 256 * 4, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  Slot* s = (Slot*)slots;
+  u64* mt = (u64*)meta;
+  const u64* gp = (const u64*)gathered;
+  const u64* ms = (const u64*)metas;
+  switch (op) {
+    case FRB_OP_MIN: k_table_insert_gathered<FRB_OP_MIN><<<g.blocks, g.threads, 0, st>>>(gp, m, world, ms, direct, s, cap - 1, mt); break;
+    case FRB_OP_MAX: k_table_insert_gathered<FRB_OP_MAX><<<g.blocks, g.threads, 0, st>>>(gp, m, world, ms, direct, s, cap - 1, mt); break;
+    case FRB_OP_ADD: k_table_insert_gathered<FRB_OP_ADD><<<g.blocks, g.threads, 0, st>>>(gp, m, world, ms, direct, s, cap - 1, mt); break;
+    case FRB_OP_SET: k_table_insert_gathered<FRB_OP_SET><<<g.blocks, g.threads, 0, st>>>(gp, m, world, ms, direct, s, cap - 1, mt); break;
+    default: set_error("frb_table_insert_gathered: bad op"); return FRB_ERR_BAD_ARG;
+  }
+  return check_launch("k_table_insert_gathered");
 }
 
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream) {

@@ -125,12 +125,9 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   api._ev(timers, "insert", 0)
   # K3 looks every voxel up in this table: size it like a lookup table (load <= 1/8, see api.LOOKUP_SLOTS_PER_ENTRY)
   merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
-  for r in range(world):
-    if counts[r]:
-      kr = gathered[r * 2 * m * 8: r * 2 * m * 8 + counts[r] * 8]
-      vr = gathered[r * 2 * m * 8 + m * 8: r * 2 * m * 8 + m * 8 + counts[r] * 8]
-      _lib.check(L.frb_table_insert(D.ptr(kr), 8, D.ptr(vr), 8, 0, counts[r], _lib.OP_MIN, merged.direct, D.ptr(merged.slots),
-                                    merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert")
+  # the local COUNT word is what every rank exported (export never drops pairs: cap_pairs >= count)
+  _lib.check(L.frb_table_insert_gathered(D.ptr(gathered), m, world, D.ptr(metas), _lib.OP_MIN, merged.direct, D.ptr(merged.slots),
+                                         merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_gathered")
   api._ev(timers, "insert", 1)
   api._ev(timers, "merge", 1)
   rb = api._RankBuffers(merged, dtype)

@@ -71,6 +71,11 @@ int frb_table_init(void* slots, uint64_t cap, uint64_t* meta, uint64_t init_val,
  * the pair's position (0..L-1) + val_offset as the value.  direct != 0 selects a DIRECT table. */
 int frb_table_insert(const void* keys, int key_width, const void* vals, int val_width, uint64_t val_offset,
                      size_t L, int op, int direct, void* slots, uint64_t cap, uint64_t* meta, void* stream);
+/* the multi-GPU key-table merge in one launch: `gathered` is the result of an all-gather of per-rank
+ * buffers [m uint64 keys | m uint64 values]; metas is the all-gathered meta blocks (world x
+ * FRB_META_WORDS, device memory) whose COUNT word says how many pairs of each segment are valid. */
+int frb_table_insert_gathered(const uint64_t* gathered, uint64_t m, int world, const uint64_t* metas, int op, int direct,
+                              void* slots, uint64_t cap, uint64_t* meta, void* stream);
 /* replace every stored value v (a position) by vals[v] -- "later duplicate wins" for
  * remap_from_array_kv (fastremap.pyx:810-811) after an FRB_OP_MAX insert of positions. */
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream);
