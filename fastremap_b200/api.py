@@ -939,12 +939,20 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
   if strategy == "hash":
     table = LabelTable(dtype, _default_entries(n, max_labels), 0)
     limit = max(n // HASH_MAX_FRACTION, 1 << 16)
-
-    def build(t):
-      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()), "frb_hist_hash")
-
     while True:
-      build(table)
+      # count -> export -> sort, queued back to back: the number of labels stays on the device (the sort
+      # kernel reads it there) until the one host round trip at the end
+      room = table.entries_max()
+      k64, v64 = D.alloc(room * 8), D.alloc(room * 8)
+      ws_bytes = int(L.frb_sort_pairs_ws_bytes(room))
+      ws = D.alloc(ws_bytes)
+      uniq, cts = D.alloc(room * w), D.alloc(room * 8)
+      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), D.stream()), "frb_hist_hash")
+      _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), room, D.stream()),
+                 "frb_table_export")
+      count_dev = ctypes.c_void_p(table.meta.data_ptr() + 8 * _lib.META_LIST_COUNT)
+      _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), room, count_dev, c, D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes,
+                                        D.stream()), "frb_sort_table_pairs")
       meta = table.read_meta()
       if not table.overfull(meta):
         break
@@ -952,14 +960,6 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
         return unique_counts_device(buf, n, dtype, strategy="sort")
       table.grow(int(meta[_lib.META_COUNT]))
     nu = int(meta[_lib.META_COUNT])
-    k64, v64 = D.alloc(nu * 8), D.alloc(nu * 8)
-    _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), nu, D.stream()),
-               "frb_table_export")
-    ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
-    ws = D.alloc(ws_bytes)
-    uniq, cts = D.alloc(nu * w), D.alloc(nu * 8)
-    _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, c, D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes, D.stream()),
-               "frb_sort_table_pairs")
     return uniq, cts, nu
   if strategy == "sort":
     meta = D.alloc_meta()
@@ -994,7 +994,7 @@ def _first_indices_sorted(buf, n, dtype, nu):
   ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
   ws = D.alloc(ws_bytes)
   uniq, idx = D.alloc(nu * dtype.itemsize), D.alloc(nu * 8)
-  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, D.code(dtype), D.ptr(uniq), D.ptr(idx), D.ptr(ws), ws_bytes,
+  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, None, D.code(dtype), D.ptr(uniq), D.ptr(idx), D.ptr(ws), ws_bytes,
                                     D.stream()), "frb_sort_table_pairs")
   return idx  # values still carry FRB_RANK_TAG: the caller masks it
 

@@ -374,9 +374,6 @@ struct TileMap {
   __device__ __forceinline__ TileMap(size_t nvec, size_t run_) {
     tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
     run = run_ < 1 ? 1 : run_;
-    // short arrays (label tables, pipeline chunks): shorter runs, so that every CTA of the grid gets work
-    const size_t fair = tiles / (2 * (size_t)gridDim.x);
-    if (run > fair) run = fair < 1 ? 1 : fair;
     const size_t nruns = (tiles + run - 1) / run;
     const size_t b = blockIdx.x, g = gridDim.x;
     const size_t mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA
@@ -571,16 +568,26 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 // host side: tiles in an n-element array (+1 so that the CTA owning the scalar tail exists)
 inline size_t stream_tiles(size_t n, int w) { return (n / (16 / w) + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1; }
 int tile_run();  // tuning knob (frb_runtime.cu): consecutive tiles per CTA run
+// Run length for a launch of `grid` CTAs over `tiles` tiles: short arrays (label tables, pipeline
+// chunks) get shorter runs, so that every CTA of the grid has work.  Decided on the host: the same
+// clamp inside the kernels cost k_hist 8 % (register allocation of its hot loop).
+inline int fair_run(int grid, size_t tiles) {
+  const size_t fair = tiles / (2 * (size_t)(grid < 1 ? 1 : grid));
+  const size_t run = (size_t)tile_run();
+  return (int)(run > fair ? (fair < 1 ? 1 : fair) : run);
+}
 
 // Persistent grid for a streaming kernel (STREAM_THREADS threads, STREAM_SMEM_BYTES of dynamic shared memory):
 // as many CTAs as are co-resident on the device, capped by the number of tiles.  Also opts the
 // kernel in to > 48 KiB of dynamic shared memory.
 template <typename Kernel>
 inline int stream_grid(Kernel kernel, size_t tiles) {
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, STREAM_THREADS, STREAM_SMEM_BYTES) != cudaSuccess || per_sm < 1)
-    per_sm = 2;
+  static int per_sm = 0;  // one instantiation per kernel: the occupancy query runs once
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);  // per device: always
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, STREAM_THREADS, STREAM_SMEM_BYTES) != cudaSuccess || per_sm < 1)
+      per_sm = 2;
+  }
   size_t b = (size_t)per_sm * (size_t)sm_count();
   if (tiles < 1) tiles = 1;
   return (int)(b < tiles ? b : tiles);

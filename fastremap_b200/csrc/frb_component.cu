@@ -112,10 +112,10 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   switch (w) {
-    case 1: k_component_build<1><<<stream_grid(k_component_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
-    case 2: k_component_build<2><<<stream_grid(k_component_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
-    case 4: k_component_build<4><<<stream_grid(k_component_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
-    default: k_component_build<8><<<stream_grid(k_component_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, tile_run()); break;
+    case 1: k_component_build<1><<<stream_grid(k_component_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<1>, tiles), tiles)); break;
+    case 2: k_component_build<2><<<stream_grid(k_component_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<2>, tiles), tiles)); break;
+    case 4: k_component_build<4><<<stream_grid(k_component_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<4>, tiles), tiles)); break;
+    default: k_component_build<8><<<stream_grid(k_component_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<8>, tiles), tiles)); break;
   }
   return check_launch("k_component_build");
 }

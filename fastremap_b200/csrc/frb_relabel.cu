@@ -219,14 +219,14 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 template <int W, int NB>
 static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);
-  k_relabel_batched<W, NB><<<stream_grid(k_relabel_batched<W, NB>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, tile_run());
+  k_relabel_batched<W, NB><<<stream_grid(k_relabel_batched<W, NB>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, fair_run(stream_grid(k_relabel_batched<W, NB>, tiles), tiles));
   return check_launch("k_relabel_batched");
 }
 
 template <int W, int WO, bool WIDE>
 static int launch_relabel(const void* src, void* dst_wide, void* dst_narrow, size_t n, const RelabelArgs& A, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);
-  k_relabel<W, WO, WIDE><<<stream_grid(k_relabel<W, WO, WIDE>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, dst_narrow, n, A, tile_run());
+  k_relabel<W, WO, WIDE><<<stream_grid(k_relabel<W, WO, WIDE>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, dst_narrow, n, A, fair_run(stream_grid(k_relabel<W, WO, WIDE>, tiles), tiles));
   return check_launch("k_relabel");
 }
 
@@ -406,7 +406,7 @@ int frb_relabel_auto(const void* src, void* dst_wide, void* dst_narrow, size_t n
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)src;
-#define FRB_AUTO(WW) k_relabel_auto<WW><<<stream_grid(k_relabel_auto<WW>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, dst_wide, dst_narrow, n, A, lim1, lim2, lim4, wide_always, tile_run())
+#define FRB_AUTO(WW) k_relabel_auto<WW><<<stream_grid(k_relabel_auto<WW>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, dst_wide, dst_narrow, n, A, lim1, lim2, lim4, wide_always, fair_run(stream_grid(k_relabel_auto<WW>, tiles), tiles))
   switch (w) {
     case 1: FRB_AUTO(1); break;
     case 2: FRB_AUTO(2); break;

@@ -140,8 +140,8 @@ int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* st
   const uint4* p = (const uint4*)a;
   u64* o = (u64*)out;
 #define FRB_LAUNCH(WW)                                                                                              \
-  if (sg) k_minmax_pairs<WW, true><<<stream_grid(k_minmax_pairs<WW, true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, tile_run());    \
-  else k_minmax_pairs<WW, false><<<stream_grid(k_minmax_pairs<WW, false>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, tile_run())
+  if (sg) k_minmax_pairs<WW, true><<<stream_grid(k_minmax_pairs<WW, true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, fair_run(stream_grid(k_minmax_pairs<WW, true>, tiles), tiles));    \
+  else k_minmax_pairs<WW, false><<<stream_grid(k_minmax_pairs<WW, false>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, o, fair_run(stream_grid(k_minmax_pairs<WW, false>, tiles), tiles))
   switch (w) {
     case 1: FRB_LAUNCH(1); break;
     case 2: FRB_LAUNCH(2); break;
@@ -158,10 +158,10 @@ int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_n
   const size_t tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1;
   if (mode & 4)
     k_stream_probe<true><<<stream_grid(k_stream_probe<true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, tile_run());
+        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, fair_run(stream_grid(k_stream_probe<true>, tiles), tiles));
   else
     k_stream_probe<false><<<stream_grid(k_stream_probe<false>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, tile_run());
+        (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, fair_run(stream_grid(k_stream_probe<false>, tiles), tiles));
   return check_launch("k_stream_probe");
 }
 
@@ -181,10 +181,10 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   switch (w) {
-    case 1: k_renumber_build<1><<<stream_grid(k_renumber_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
-    case 2: k_renumber_build<2><<<stream_grid(k_renumber_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
-    case 4: k_renumber_build<4><<<stream_grid(k_renumber_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
-    default: k_renumber_build<8><<<stream_grid(k_renumber_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, tile_run()); break;
+    case 1: k_renumber_build<1><<<stream_grid(k_renumber_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<1>, tiles), tiles)); break;
+    case 2: k_renumber_build<2><<<stream_grid(k_renumber_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<2>, tiles), tiles)); break;
+    case 4: k_renumber_build<4><<<stream_grid(k_renumber_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<4>, tiles), tiles)); break;
+    default: k_renumber_build<8><<<stream_grid(k_renumber_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<8>, tiles), tiles)); break;
   }
   return check_launch("k_renumber_build");
 }

@@ -297,6 +297,7 @@ k_match_emit(const void* __restrict__ a, size_t n, size_t chunk, u64 value, cons
 // dtype's order), sort the pairs by label (frb_coopsort.cuh), emit typed labels + values.
 struct SortPairsArgs {
   CoopSortBuffers sort;
+  const u64* n_dev;  // optional: the list length lives on the device (<= n)
   u64 n;
   u64 flip;
   int key_bits;
@@ -306,6 +307,10 @@ struct SortPairsArgs {
 
 template <int W>
 __global__ void __launch_bounds__(CS_THREADS) k_sort_emit_pairs(SortPairsArgs A) {
+  if (A.n_dev) {
+    const u64 nd = __ldcg(A.n_dev);
+    A.n = nd < A.n ? nd : A.n;
+  }
   const u64 stride = (u64)gridDim.x * CS_THREADS;
   unsigned int generation = 0;
   if (A.flip) {
@@ -392,10 +397,10 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   switch (w) {
-    case 1: k_hist<1, DenseSink><<<stream_grid(k_hist<1, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
-    case 2: k_hist<2, DenseSink><<<stream_grid(k_hist<2, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
-    case 4: k_hist<4, DenseSink><<<stream_grid(k_hist<4, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
-    default: k_hist<8, DenseSink><<<stream_grid(k_hist<8, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, tile_run()); break;
+    case 1: k_hist<1, DenseSink><<<stream_grid(k_hist<1, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<1, DenseSink>, tiles), tiles)); break;
+    case 2: k_hist<2, DenseSink><<<stream_grid(k_hist<2, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<2, DenseSink>, tiles), tiles)); break;
+    case 4: k_hist<4, DenseSink><<<stream_grid(k_hist<4, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<4, DenseSink>, tiles), tiles)); break;
+    default: k_hist<8, DenseSink><<<stream_grid(k_hist<8, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<8, DenseSink>, tiles), tiles)); break;
   }
   return check_launch("k_hist<dense>");
 }
@@ -415,10 +420,10 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   const uint4* p = (const uint4*)a;
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
   switch (w) {
-    case 1: k_hist<1, HashSink><<<stream_grid(k_hist<1, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
-    case 2: k_hist<2, HashSink><<<stream_grid(k_hist<2, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
-    case 4: k_hist<4, HashSink><<<stream_grid(k_hist<4, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
-    default: k_hist<8, HashSink><<<stream_grid(k_hist<8, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, tile_run()); break;
+    case 1: k_hist<1, HashSink><<<stream_grid(k_hist<1, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<1, HashSink>, tiles), tiles)); break;
+    case 2: k_hist<2, HashSink><<<stream_grid(k_hist<2, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<2, HashSink>, tiles), tiles)); break;
+    case 4: k_hist<4, HashSink><<<stream_grid(k_hist<4, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<4, HashSink>, tiles), tiles)); break;
+    default: k_hist<8, HashSink><<<stream_grid(k_hist<8, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<8, HashSink>, tiles), tiles)); break;
   }
   return check_launch("k_hist<hash>");
 }
@@ -500,8 +505,8 @@ size_t frb_sort_pairs_ws_bytes(size_t L) {
   return 2 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
 }
 
-int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, void* uniq_out, uint64_t* vals_out, void* ws,
-                         size_t ws_bytes, void* stream) {
+int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_t* count_dev, int dtype, void* uniq_out,
+                         uint64_t* vals_out, void* ws, size_t ws_bytes, void* stream) {
   if (!dtype_ok(dtype) || !ws || ws_bytes < frb_sort_pairs_ws_bytes(L) || (L && (!keys || !vals || !uniq_out || !vals_out))) {
     set_error("frb_sort_table_pairs: bad arguments");
     return FRB_ERR_BAD_ARG;
@@ -520,6 +525,7 @@ int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, vo
   A.sort.hist = (unsigned int*)((char*)ws + 2 * lb);
   A.sort.barrier = (unsigned int*)((char*)ws + 2 * lb + (size_t)2 * sm_count() * 256 * sizeof(unsigned int));
   A.n = L;
+  A.n_dev = (const u64*)count_dev;
   A.flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
   A.key_bits = 8 * w;
   A.uniq_out = uniq_out;

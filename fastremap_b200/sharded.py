@@ -200,7 +200,7 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
   ws_bytes = int(L.frb_sort_pairs_ws_bytes(nu))
   ws = D.alloc(ws_bytes)
   uniq, cts = D.alloc(nu * dtype.itemsize), D.alloc(nu * 8)
-  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, D.code(dtype), D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes,
+  _lib.check(L.frb_sort_table_pairs(D.ptr(k64), D.ptr(v64), nu, None, D.code(dtype), D.ptr(uniq), D.ptr(cts), D.ptr(ws), ws_bytes,
                                     D.stream()), "frb_sort_table_pairs")
   return uniq, cts, nu
 

@@ -168,10 +168,12 @@ int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint
                           uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
 int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream);
 size_t frb_sort_pairs_ws_bytes(size_t L);
-/* sort L exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are
- * clobbered) and emit typed keys + values */
-int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, int dtype, void* uniq_out, uint64_t* vals_out,
-                         void* ws, size_t ws_bytes, void* stream);
+/* sort exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are
+ * clobbered) and emit typed keys + values.  L = number of pairs, or -- count_dev != NULL -- the
+ * capacity of the lists whose actual length min(*count_dev, L) is still on the device (e.g.
+ * &meta[FRB_META_LIST_COUNT] right after frb_table_export: no host round trip in between). */
+int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_t* count_dev, int dtype, void* uniq_out,
+                         uint64_t* vals_out, void* ws, size_t ws_bytes, void* stream);
 /* sort strategy, two steps: _count copies + radix sorts the voxels inside ws and leaves the number
  * of distinct labels in meta[FRB_META_LIST_COUNT]; _emit run-length encodes the sorted copy. */
 size_t frb_unique_sort_ws_bytes(size_t n, int dtype);
