@@ -14,7 +14,7 @@ value   : Gvox/s with the input resident in HBM, CUDA-event time per step summed
           (the un-timed restore of the input between steps rewrites 8 GiB, which also flushes L2)
 e2e     : Gvox/s through the public API fastremap_b200.renumber(numpy array, in_place=True) with
           pinned host buffers: H2D of the volume, kernels, D2H of both result arrays, dict build
-roofline: the dominant kernel (K3 k_relabel: 8 B read + 8 B wide write + 4 B narrow write per
+roofline: the dominant kernel (K3 k_relabel_auto: 8 B read + 8 B wide write + 4 B narrow write per
           voxel = 20 algorithmic bytes/voxel), timed with CUDA events on the launching stream
 cpu_baseline: oracle/_ref (the compiled reference) renumber(in_place=True) on a bounded sample.
 """
@@ -346,7 +346,7 @@ def run_ours(args):
   if k3_ms:
     k3 = float(np.mean(k3_ms))
     achieved = ALG_BYTES_PER_VOXEL * n / (k3 / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_relabel<8,4,wide> (K3)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_relabel_auto<8> (K3: lookup + wide store + fused narrow store)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL * n,
                 "k1_build_ms": float(np.mean(k1_ms)), "k2_rank_ms": float(np.mean(k2_ms)),
