@@ -706,6 +706,15 @@ def remap(arr, table, preserve_missing_labels=False, in_place=False):
     in_place_eff = v.aliases_input
   else:
     in_place_eff = (bool(in_place) and writeable and contiguous) or widened
+    if arr.nbytes >= STREAM_MIN_BYTES and not (preserve_missing_labels and len(table) == 1):
+      if not contiguous:
+        arr = np.copy(arr, order="C")
+      D.dev()
+      kd, vd = D.upload_array(keys), D.upload_array(vals)
+      t = table_from_arrays(kd, vd, len(keys), adtype, op=_lib.OP_SET)
+      policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
+      return _relabel_host_streamed(arr, in_place_eff and arr.flags.writeable, t, policy, 0, len(keys),
+                                    "{} was not in the remap table.")
     v = D.ingest(arr)
 
   if preserve_missing_labels and len(table) == 1:
@@ -726,6 +735,77 @@ def remap(arr, table, preserve_missing_labels=False, in_place=False):
     D.download_into(v.buf, v.nbytes, D.flat_view(v.host))
     return v.host
   return D.emit(v.buf, adtype, v.shape, v.order, False)
+
+
+def _relabel_host_streamed(arr: np.ndarray, in_place_eff: bool, table: LabelTable, policy, fill_bits, n_labels, message):
+  """
+  Lookup pass (remap / mask / mask_except / remap_from_array_kv) over a large HOST array as a chunk
+  pipeline: voxels are independent, so chunk c is relabelled while chunk c+1 is on its way to the
+  device and chunk c-1 on its way back (three streams; PCIe busy in both directions).
+  With the error policy nothing is written back until the whole array has been checked, so a
+  KeyError leaves the caller's array untouched.
+  Returns the result array (arr itself when in_place_eff).
+  """
+  dtype = arr.dtype
+  w = dtype.itemsize
+  n = arr.size
+  nbytes = n * w
+  order = "F" if arr.flags["F_CONTIGUOUS"] else "C"
+  src_u8 = D.as_torch_bytes(D.flat_view(arr))
+  out = arr if in_place_eff else D.host_empty(arr.shape, dtype, order)
+  out_u8 = D.as_torch_bytes(D.flat_view(out))
+  chunk = max(STREAM_CHUNK_BYTES // 16 * 16, 16)
+  bounds = [(a, min(a + chunk, nbytes)) for a in range(0, nbytes, chunk)]
+  cur = torch.cuda.current_stream()
+  s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+  dev_buf = D.alloc(nbytes)
+  s_in.wait_stream(cur)
+  s_out.wait_stream(cur)
+  overlap_d2h = policy != _lib.MISS_ERROR
+  ev_in = []
+  with torch.cuda.stream(s_in):
+    for a, b in bounds:
+      dev_buf[a:b].copy_(src_u8[a:b], non_blocking=True)
+      e = torch.cuda.Event()
+      e.record(s_in)
+      ev_in.append(e)
+  batch = _batch_rows(n_labels)
+  for i, (a, b) in enumerate(bounds):
+    cur.wait_event(ev_in[i])
+    view = dev_buf[a:b]
+    # the first missing index is relative to the chunk: chunks are visited in memory order and
+    # atomicMin keeps the smallest, so a later chunk may only lower it if no earlier chunk set it
+    if policy == _lib.MISS_ERROR:
+      _relabel_chunk_error(view, (b - a) // w, dtype, table, a // w, batch)
+    else:
+      _relabel(view, (b - a) // w, dtype, table, policy, fill_bits=fill_bits, dst_wide=view, batch_rows=batch)
+    if overlap_d2h:
+      e = torch.cuda.Event()
+      e.record(cur)
+      s_out.wait_event(e)
+      with torch.cuda.stream(s_out):
+        out_u8[a:b].copy_(view, non_blocking=True)
+  if not overlap_d2h:
+    cur.synchronize()
+    _check_missing(table, dev_buf, dtype, message)
+    s_out.wait_stream(cur)
+    with torch.cuda.stream(s_out):
+      out_u8.copy_(dev_buf[:nbytes], non_blocking=True)
+  s_out.synchronize()
+  cur.synchronize()
+  return out
+
+
+def _relabel_chunk_error(view, ne, dtype, table: LabelTable, elem_offset, batch):
+  """Error-policy lookup of one chunk: the table's MISSING_INDEX word must end up as the GLOBAL first
+  missing index, so the chunk-relative index the kernel records is rebased between launches."""
+  before = table.meta[_lib.META_MISSING_INDEX].clone()
+  table.meta[_lib.META_MISSING_INDEX] = -1  # all-ones: none
+  _relabel(view, ne, dtype, table, _lib.MISS_ERROR, dst_wide=view, batch_rows=batch)
+  local = table.meta[_lib.META_MISSING_INDEX]
+  # earlier chunks win (smaller global index); all-ones (-1 as int64) means none
+  rebased = torch.where(local == -1, local, local + elem_offset)
+  table.meta[_lib.META_MISSING_INDEX] = torch.where(before == -1, rebased, before)
 
 
 def mask(arr, labels, in_place=False, value=0):
@@ -751,6 +831,13 @@ def mask_except(arr, labels, in_place=False, value=0):
   else:
     contiguous = arr.flags.f_contiguous or arr.flags.c_contiguous
     in_place_eff = bool(in_place) and arr.flags.writeable and contiguous
+    if arr.nbytes >= STREAM_MIN_BYTES:
+      if not contiguous:
+        arr = np.copy(arr, order="C")
+      D.dev()
+      kd = D.upload_array(lab)
+      t = table_from_arrays(kd, kd, len(lab), adtype, op=_lib.OP_SET)
+      return _relabel_host_streamed(arr, in_place_eff, t, _lib.MISS_FILL, fill, len(lab), "")
     v = D.ingest(arr)
   if v.n:
     kd = D.upload_array(lab)
@@ -820,6 +907,13 @@ def remap_from_array_kv(arr, keys, vals, preserve_missing_labels=True, in_place=
     in_place_eff = v.aliases_input
   else:
     in_place_eff = bool(in_place) and arr.flags.writeable and arr.flags.c_contiguous
+    if arr.nbytes >= STREAM_MIN_BYTES:
+      if not arr.flags.c_contiguous:
+        arr = np.ascontiguousarray(arr)
+      kv, vv = D.ingest(keys, alias_ok=True), D.ingest(vals, alias_ok=True)
+      t = table_from_arrays(kv.buf, vv.buf, nk, dt, op=_lib.OP_MAX, positions=True) if nk else LabelTable(dt, 1, 0)
+      policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
+      return _relabel_host_streamed(arr, in_place_eff, t, policy, 0, nk, "{} was not in the remap keys.")
     v = D.ingest(arr)
   if v.n:
     kv, vv = D.ingest(keys, alias_ok=True), D.ingest(vals, alias_ok=True)

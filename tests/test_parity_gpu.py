@@ -445,3 +445,49 @@ def test_big_lookup_tables_batched(frb, oracle, dtype):
   u, inv = frb.unique(a, return_inverse=True)
   eu, einv = oracle.unique(a, return_inverse=True)
   assert np.array_equal(u, eu) and np.array_equal(inv, einv) and inv.dtype == einv.dtype
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int16, np.int64])
+def test_lookup_family_streamed_vs_oracle(frb, oracle, small_chunks, dtype):
+  """remap / mask / mask_except / remap_from_array_kv of host arrays through the chunk pipeline
+  (4 KiB chunks): C and F order, in place or not, KeyError naming the first missing label in memory
+  order and leaving the caller's array untouched."""
+  a = synth((18, 40, 56), (5, 9, 11), dtype, seed=int(np.dtype(dtype).num) + 70, zero_frac=0.15, noise=0.1)
+  labels = np.unique(a)
+  table = {int(k): int(labels[(i * 7) % labels.size]) for i, k in enumerate(labels[::2])}
+  keep = [int(x) for x in labels[1::3]]
+  for arr in (a, np.asfortranarray(a)):
+    for in_place in (False, True):
+      e_in, g_in = np.copy(arr, order="K"), np.copy(arr, order="K")
+      e = oracle.remap(e_in, table, preserve_missing_labels=True, in_place=in_place)
+      g = frb.remap(g_in, table, preserve_missing_labels=True, in_place=in_place)
+      assert g.dtype == e.dtype and np.array_equal(g, e) and np.array_equal(g_in, e_in)
+      assert g.flags.f_contiguous == e.flags.f_contiguous and np.shares_memory(g, g_in) == np.shares_memory(e, e_in)
+      e_in, g_in = np.copy(arr, order="K"), np.copy(arr, order="K")
+      e = oracle.mask_except(e_in, keep, in_place=in_place, value=3)
+      g = frb.mask_except(g_in, keep, in_place=in_place, value=3)
+      assert np.array_equal(g, e) and np.array_equal(g_in, e_in) and np.shares_memory(g, g_in) == np.shares_memory(e, e_in)
+      e = oracle.mask(np.copy(arr, order="K"), keep, in_place=in_place, value=1)
+      g = frb.mask(np.copy(arr, order="K"), keep, in_place=in_place, value=1)
+      assert np.array_equal(g, e)
+    g_in = np.copy(arr, order="K")
+    with pytest.raises(KeyError) as ge:
+      frb.remap(g_in, table, preserve_missing_labels=False, in_place=True)
+    with pytest.raises(KeyError) as ee:
+      oracle.remap(np.copy(arr, order="K"), table, preserve_missing_labels=False, in_place=True)
+    assert ge.value.args == ee.value.args and np.array_equal(g_in, arr)
+  full = {int(k): int(k) ^ 1 if (int(k) ^ 1) in set(labels.tolist()) else int(k) for k in labels}
+  assert np.array_equal(frb.remap(np.copy(a), full), oracle.remap(np.copy(a), full))
+  flat = a.reshape(-1)
+  keys = labels[::2]
+  vals = np.roll(keys, 1)
+  for in_place in (False, True):
+    e_in, g_in = np.copy(flat), np.copy(flat)
+    e = oracle.remap_from_array_kv(e_in, keys, vals, in_place=in_place)
+    g = frb.remap_from_array_kv(g_in, keys, vals, in_place=in_place)
+    assert np.array_equal(g, e) and np.array_equal(g_in, e_in)
+  with pytest.raises(KeyError) as ge:
+    frb.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
+  with pytest.raises(KeyError) as ee:
+    oracle.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
+  assert ge.value.args == ee.value.args
