@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
   component_map,
   foreground,
   indices,
+  inverse_component_map,
   mask,
   mask_except,
   minmax,
@@ -37,7 +38,6 @@ def _out_of_scope(name):
 
 ascontiguousarray = _out_of_scope("ascontiguousarray")
 asfortranarray = _out_of_scope("asfortranarray")
-inverse_component_map = _out_of_scope("inverse_component_map")
 point_cloud = _out_of_scope("point_cloud")
 tobytes = _out_of_scope("tobytes")
 transpose = _out_of_scope("transpose")

@@ -47,6 +47,7 @@ SIGNATURES = {
   "frb_replace_one": (_i, [_vp, _vp, _sz, _i, _u64, _u64, _vp]),
   "frb_remap_from_array": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
   "frb_swap_halves": (_i, [_vp, _vp, _sz, _i, _vp]),
+  "frb_pack_pairs": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp]),
   "frb_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
   "frb_hist_dense": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp]),
   "frb_compact_bins_ws_bytes": (_sz, [_u64]),

@@ -991,6 +991,78 @@ def component_map(component_labels, parent_labels):
   return dict(zip(keys.tolist(), pars.tolist()))
 
 
+def inverse_component_map(parent_labels, component_labels):
+  """
+  { parent label: [component labels ...] } for every (parent, component) pair that occurs at the
+  same voxel (reference: fastremap.pyx:589-652, which collects the pairs into Python sets; the lists
+  here are sorted ascending, the reference's are in set order).
+  The pair of a voxel is packed into one 64-bit label and the distinct pairs are a `unique` of the
+  packed volume; labels wider than 4 bytes are renumbered to dense 32-bit ids first.
+  """
+  is_t = isinstance(component_labels, torch.Tensor)
+  if not is_t:
+    if not isinstance(component_labels, np.ndarray):
+      component_labels = np.array(component_labels)
+    if not isinstance(parent_labels, np.ndarray):
+      parent_labels = np.array(parent_labels)
+    size = component_labels.size
+  else:
+    size = component_labels.numel()
+  if size == 0:
+    return {}
+  if tuple(component_labels.shape) != tuple(parent_labels.shape):
+    raise ValueError("The size of the inputs must match: {} vs {}".format(
+      tuple(component_labels.shape), tuple(parent_labels.shape)))
+  if is_t:
+    vc = D.ingest(component_labels)
+    vp = D.ingest(parent_labels)
+    if vc.order != vp.order:
+      vp = D.ingest(parent_labels.contiguous() if vc.order == "C" else parent_labels)
+      if vc.order != vp.order:
+        raise FastremapB200Error("inverse_component_map: tensors must share one memory order")
+  else:
+    if component_labels.flags.c_contiguous:  # both arrays take the memory order of the first (fastremap.pyx:95-102)
+      component_labels, parent_labels = np.ascontiguousarray(component_labels), np.ascontiguousarray(parent_labels)
+    else:
+      component_labels, parent_labels = np.asfortranarray(component_labels), np.asfortranarray(parent_labels)
+    vc, vp = D.ingest(component_labels), D.ingest(parent_labels)
+  _require_int(vc.dtype, "inverse_component_map")
+  _require_int(vp.dtype, "inverse_component_map")
+  n = vc.n
+
+  def dense32(v):
+    """(buffer of <= 4-byte raw labels, width, decode) with decode: raw value -> original Python int"""
+    if v.dtype.itemsize <= 4:
+      return v.buf, v.dtype.itemsize, None
+    # 8-byte labels: dense ids 0 .. L-1 in encounter order (fewer than 2^32 of them in any array this size)
+    res = renumber_device(v.buf, n, v.dtype, start=0, preserve_zero=False, write_wide=False)
+    if res.out_dtype.itemsize > 4:
+      raise FastremapB200Error("inverse_component_map: more than 2^32 distinct labels")
+    keys = D.download(res.keys, res.n_labels, v.dtype)
+    return res.out, res.out_dtype.itemsize, keys
+
+  pbuf, wp, pkeys = dense32(vp)
+  cbuf, wc, ckeys = dense32(vc)
+  packed = D.alloc(n * 8)
+  _lib.check(_L().frb_pack_pairs(D.ptr(pbuf), wp, D.ptr(cbuf), wc, D.ptr(packed), n, D.stream()), "frb_pack_pairs")
+  uniq, _, nu = unique_counts_device(packed, n, np.uint64) if n > 1 else (packed, None, 1)
+  pairs = D.download(uniq, nu, np.uint64)
+  par = pairs >> np.uint64(8 * wc)
+  com = pairs & np.uint64((1 << (8 * wc)) - 1)
+
+  def decode(raw, keys, dtype):
+    if keys is not None:
+      return keys[raw.astype(np.int64)]
+    return raw.astype("u%d" % dtype.itemsize).view(dtype) if dtype.itemsize < 8 else raw.view(dtype)
+
+  par, com = decode(par, pkeys, vp.dtype), decode(com, ckeys, vc.dtype)
+  order = np.lexsort((com, par))
+  par, com = par[order], com[order]
+  heads = np.flatnonzero(np.concatenate(([True], par[1:] != par[:-1])))
+  ends = np.append(heads[1:], par.size)
+  return {int(par[a]): com[a:b].tolist() for a, b in zip(heads, ends)}
+
+
 # ------------------------------------------------------------------------------------- unique
 
 # strategy thresholds (they change speed only, never results -- SURVEY App. A-11)

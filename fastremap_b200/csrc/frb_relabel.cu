@@ -312,6 +312,17 @@ __global__ void __launch_bounds__(256) k_swap_halves(const void* __restrict__ sr
   }
 }
 
+// ---------------------------------------------------------------------- pack pairs (inverse_component_map)
+// out[i] = (hi[i] << lo_bits) | lo[i], raw bits, as uint64: the (parent, component) pair of a voxel
+// as ONE label, so that the distinct pairs are a `unique` of the packed volume
+// (_inverse_component_map, fastremap.pyx:623-652, collects the same pairs into Python sets).
+__global__ void __launch_bounds__(256)
+k_pack_pairs(const void* __restrict__ hi, int whi, const void* __restrict__ lo, int wlo, u64* __restrict__ out, size_t n, int lo_bits) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (ld_elem_rt(hi, whi, i) << lo_bits) | ld_elem_rt(lo, wlo, i);
+}
+
 // ---------------------------------------------------------------------- cast (refit astype)
 template <int WI, int WO, bool SIGNED_IN>
 __global__ void __launch_bounds__(256) k_cast(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
@@ -462,6 +473,15 @@ int frb_swap_halves(const void* src, void* dst, size_t n, int width, void* strea
     default: k_swap_halves<8><<<g.blocks, g.threads, 0, st>>>(src, dst, n); break;
   }
   return check_launch("k_swap_halves");
+}
+
+int frb_pack_pairs(const void* hi, int hi_width, const void* lo, int lo_width, uint64_t* out, size_t n, void* stream) {
+  const bool wok = (hi_width == 1 || hi_width == 2 || hi_width == 4) && (lo_width == 1 || lo_width == 2 || lo_width == 4);
+  if (!wok || (n && (!hi || !lo || !out))) { set_error("frb_pack_pairs: bad arguments (widths 1, 2 or 4)"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  Grid g = grid_for(n, 256 * 4, 16);
+  k_pack_pairs<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>(hi, hi_width, lo, lo_width, (u64*)out, n, 8 * lo_width);
+  return check_launch("k_pack_pairs");
 }
 
 int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {

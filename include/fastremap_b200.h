@@ -148,6 +148,10 @@ int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals,
 /* exchange the low and high halves of n elements of `width` bytes (2, 4, 8): the (N,2) edge-list
  * packing of _two_axis_unique (fastremap.pyx:967-982), src may equal dst */
 int frb_swap_halves(const void* src, void* dst, size_t n, int width, void* stream);
+/* out[i] = (hi[i] << 8*lo_width) | lo[i] (raw bits, widths 1 / 2 / 4 bytes) as uint64: a voxel's
+ * (parent, component) pair as one label -- inverse_component_map (fastremap.pyx:589-652) is then the
+ * `unique` of the packed volume. */
+int frb_pack_pairs(const void* hi, int hi_width, const void* lo, int lo_width, uint64_t* out, size_t n, void* stream);
 /* refit's astype (fastremap.pyx:301): integer width change, truncating or sign/zero extending */
 int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

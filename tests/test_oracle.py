@@ -204,3 +204,18 @@ def test_live_vs_reference(oracle, reference, dtype):
   assert np.array_equal(reference.mask_except(a, labels[::2]), oracle.mask_except(a, labels[::2]))
   par = (a.astype(np.int64) % 50).astype(np.int16)
   assert reference.component_map(a, par) == oracle.component_map(a, par)
+
+
+def test_inverse_component_map(oracle):  # automated_test.py:580-594
+  assert oracle.inverse_component_map([1, 2, 1, 3], [4, 4, 5, 6]) == {1: [4, 5], 2: [4], 3: [6]}
+  assert oracle.inverse_component_map([1, 1, 1, 3], [4, 4, 5, 6]) == {1: [4, 5], 3: [6]}
+  assert oracle.inverse_component_map([1, 1, 1, 1], [4, 2, 5, 6]) == {1: [2, 4, 5, 6]}
+  assert oracle.inverse_component_map([], []) == {}
+
+
+def test_inverse_component_map_vs_reference(oracle, reference):
+  from fastremap_b200.synth import synth_numpy
+  cc = synth_numpy((12, 20, 24), (4, 5, 6), np.uint32, seed=9, zero_frac=0.1, noise=0.1)
+  par = synth_numpy((12, 20, 24), (4, 5, 6), np.int16, seed=9, zero_frac=0.1, noise=0.0, cell_div=3)
+  ref = reference.inverse_component_map(par, cc)
+  assert {k: sorted(v) for k, v in ref.items()} == oracle.inverse_component_map(par, cc)

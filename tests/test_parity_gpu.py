@@ -491,3 +491,31 @@ def test_lookup_family_streamed_vs_oracle(frb, oracle, small_chunks, dtype):
   with pytest.raises(KeyError) as ee:
     oracle.remap_from_array_kv(np.copy(flat), keys, vals, preserve_missing_labels=False)
   assert ge.value.args == ee.value.args
+
+
+# ------------------------------------------------------------------ inverse_component_map
+
+
+def test_inverse_component_map_goldens(frb):
+  """automated_test.py:580-594 for all 64 dtype combinations."""
+  for dc in DTYPES:
+    for dp in DTYPES:
+      p = lambda x: np.array(x, dtype=dp)
+      c = lambda x: np.array(x, dtype=dc)
+      assert frb.inverse_component_map(p([1, 2, 1, 3]), c([4, 4, 5, 6])) == {1: [4, 5], 2: [4], 3: [6]}
+      assert frb.inverse_component_map(p([1, 1, 1, 3]), c([4, 4, 5, 6])) == {1: [4, 5], 3: [6]}
+      assert frb.inverse_component_map(p([1, 1, 1, 1]), c([4, 2, 5, 6])) == {1: [2, 4, 5, 6]}
+  assert frb.inverse_component_map([], []) == {}
+  with pytest.raises(ValueError):
+    frb.inverse_component_map(np.zeros((2, 3), np.uint8), np.zeros((3, 2), np.uint8))
+
+
+@pytest.mark.parametrize("dtypes", [(np.uint32, np.uint16), (np.uint64, np.uint64), (np.int64, np.uint8), (np.int16, np.int64), (np.uint8, np.int32)])
+def test_inverse_component_map_vs_oracle(frb, oracle, dtypes):
+  dc, dp = dtypes
+  cc = synth((14, 24, 40), (4, 6, 7), dc, seed=21, zero_frac=0.1, noise=0.15)           # components split across parents (noise)
+  par = synth((14, 24, 40), (4, 6, 7), dp, seed=21, zero_frac=0.1, noise=0.0, cell_div=3)
+  for a, b in ((par, cc), (np.asfortranarray(par), np.asfortranarray(cc)), (np.asfortranarray(par), cc)):
+    got = frb.inverse_component_map(a, b)
+    assert got == oracle.inverse_component_map(a, b)
+    assert all(isinstance(k, int) for k in got) and all(isinstance(x, int) for v in got.values() for x in v)
