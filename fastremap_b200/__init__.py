@@ -4,8 +4,8 @@ fastremap_b200 -- B200-native (sm_100a CUDA) implementation of fastremap's relab
 Drop-in for the hot-path names of the reference's module surface
 (seung-lab/fastremap, fastremap/__init__.py:1-24): `import fastremap_b200 as fastremap`.
 The names the reference exports that are OUTSIDE this build's scope (in-place
-transposition, tobytes, point_cloud, ...) are present but raise NotImplementedError: by design
-there is no CPU fallback anywhere in this package.
+transposition, tobytes) are present but raise NotImplementedError: by design there is no CPU
+fallback anywhere in this package.
 """
 from .api import (  # noqa: F401
   component_map,
@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
   mask_except,
   minmax,
   pixel_pairs,
+  point_cloud,
   refit,
   remap,
   remap_from_array,
@@ -38,7 +39,6 @@ def _out_of_scope(name):
 
 ascontiguousarray = _out_of_scope("ascontiguousarray")
 asfortranarray = _out_of_scope("asfortranarray")
-point_cloud = _out_of_scope("point_cloud")
 tobytes = _out_of_scope("tobytes")
 transpose = _out_of_scope("transpose")
 

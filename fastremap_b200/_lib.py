@@ -62,6 +62,12 @@ SIGNATURES = {
   "frb_indices_ws_bytes": (_sz, [_sz]),
   "frb_indices_count": (_i, [_vp, _sz, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_indices_emit": (_i, [_vp, _sz, _i, _u64, _vp, _sz, _vp, _vp]),
+  "frb_nonzero_ws_bytes": (_sz, [_sz]),
+  "frb_nonzero_count": (_i, [_vp, _sz, _i, _vp, _vp, _sz, _vp]),
+  "frb_nonzero_emit": (_i, [_vp, _sz, _i, _vp, _vp, _sz, _vp, _vp]),
+  "frb_sort_pairs_u64_ws_bytes": (_sz, [_sz]),
+  "frb_sort_pairs_u64": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
+  "frb_unravel_u16": (_i, [_vp, _sz, _i, _u64, _u64, _vp, _vp]),
   "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),

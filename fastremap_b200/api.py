@@ -991,6 +991,67 @@ def component_map(component_labels, parent_labels):
   return dict(zip(keys.tolist(), pars.tolist()))
 
 
+def point_cloud(arr):
+  """
+  { label: (N, 2 or 3) uint16 array of the positions of its voxels } for the non-zero labels of a 2-D
+  or 3-D integer image (reference: fastremap.pyx:1423-1540).  Voxels are visited in C order whatever
+  the memory layout (the reference indexes arr[i, j, k]); inside a label the rows are in scan order
+  (the reference's argsort is not stable, so its order inside a label is unspecified).
+  The values are views into one array, like the reference's.
+  """
+  is_t = isinstance(arr, torch.Tensor)
+  if not is_t:
+    arr = np.asarray(arr)
+  adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
+  if adtype == np.dtype("bool"):
+    arr = arr.view(torch.uint8) if is_t else arr.view(np.uint8)
+    adtype = np.dtype("u1")
+  if not D.is_int_dtype(adtype):
+    raise TypeError("No matching signature found")
+  ndim = arr.dim() if is_t else arr.ndim
+  if ndim not in (2, 3):
+    raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % ndim)
+  shape = tuple(int(x) for x in arr.shape)
+  n = int(np.prod(shape, dtype=np.int64))
+  if n == 0:
+    return {}
+  if any(d > 65536 for d in shape):
+    raise ValueError("point_cloud: coordinates are uint16; no axis may be longer than 65536")
+  arr = arr.contiguous() if is_t else np.ascontiguousarray(arr)  # the scan is in C order
+  v = D.ingest(arr, alias_ok=True)
+  L = _L()
+  c = D.code(adtype)
+  meta = D.alloc_meta()
+  ws_bytes = int(L.frb_nonzero_ws_bytes(n))
+  ws = D.alloc(ws_bytes)
+  _lib.check(L.frb_nonzero_count(D.ptr(v.buf), n, c, D.ptr(meta), D.ptr(ws), ws_bytes, D.stream()), "frb_nonzero_count")
+  nfg = int(D.read_u64(meta)[_lib.META_LIST_COUNT])
+  if nfg == 0:
+    return {}
+  labels, index = D.alloc(nfg * 8), D.alloc(nfg * 8)
+  _lib.check(L.frb_nonzero_emit(D.ptr(v.buf), n, c, D.ptr(labels), D.ptr(index), nfg, D.ptr(ws), D.stream()), "frb_nonzero_emit")
+  sws_bytes = int(L.frb_sort_pairs_u64_ws_bytes(nfg))
+  sws = D.alloc(sws_bytes)
+  _lib.check(L.frb_sort_pairs_u64(D.ptr(labels), D.ptr(index), nfg, 8 * adtype.itemsize, D.ptr(sws), sws_bytes, D.stream()),
+             "frb_sort_pairs_u64")
+  coords = D.alloc(nfg * ndim * 2)
+  d1, d2 = (shape[1], 1) if ndim == 2 else (shape[1], shape[2])
+  _lib.check(L.frb_unravel_u16(D.ptr(index), nfg, ndim, d1, d2, D.ptr(coords), D.stream()), "frb_unravel_u16")
+  # label boundaries: the sorted labels and their counts (ascending in the dtype's order, like the sort above)
+  uniq, cts, nu = unique_counts_device(v.buf, n, adtype)
+  u_np = D.download(uniq, nu, adtype)
+  c_np = D.download(cts, nu, np.uint64)
+  keep = u_np != 0
+  u_np, c_np = u_np[keep], c_np[keep]
+  ends = np.cumsum(c_np.astype(np.int64))
+  starts = ends - c_np.astype(np.int64)
+  if is_t:
+    cloud = coords[: nfg * ndim * 2].view(torch.uint16).reshape(nfg, ndim)
+  else:
+    cloud = D.download(coords, nfg * ndim, np.uint16).reshape(nfg, ndim)
+  return {int(lbl): cloud[a:b] for lbl, a, b in zip(u_np.tolist(), starts.tolist(), ends.tolist())}
+
+
 def inverse_component_map(parent_labels, component_labels):
   """
   { parent label: [component labels ...] } for every (parent, component) pair that occurs at the

@@ -292,6 +292,65 @@ k_match_emit(const void* __restrict__ a, size_t n, size_t chunk, u64 value, cons
   }
 }
 
+// ------------------------------------------------------------------ point_cloud: foreground voxels as (label, index) pairs
+// ordered compaction of the non-zero voxels: label bits (sign bit flipped for signed dtypes, so that
+// unsigned radix order is numeric order) and flat index, both uint64
+template <int W>
+__global__ void __launch_bounds__(256)
+k_nonzero_count(const void* __restrict__ a, size_t n, size_t chunk, u64* __restrict__ block_counts) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  unsigned int c = 0;
+  for (size_t i = beg + threadIdx.x; i < end; i += 256) c += ld_elem<W>(a, i) != 0 ? 1 : 0;
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  c = __reduce_add_sync(FRB_FULL_MASK, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_nonzero_emit(const void* __restrict__ a, size_t n, size_t chunk, const u64* __restrict__ block_offs, u64 flip,
+               u64* __restrict__ labels_out, u64* __restrict__ index_out, size_t capacity) {
+  const size_t beg = (size_t)blockIdx.x * chunk;
+  size_t end = beg + chunk;
+  if (end > n) end = n;
+  u64 run = block_offs[blockIdx.x];
+  for (size_t base = beg; base < end; base += 256) {
+    const size_t i = base + threadIdx.x;
+    const u64 v = i < end ? ld_elem<W>(a, i) : 0;
+    unsigned int tot;
+    const unsigned int pre = block_flag_scan(v != 0, &tot);
+    if (v != 0 && run + pre < capacity) {
+      labels_out[run + pre] = v ^ flip;
+      index_out[run + pre] = (u64)i;
+    }
+    run += tot;
+  }
+}
+
+// flat C-order index -> (i, j[, k]) as uint16 rows
+__global__ void __launch_bounds__(256)
+k_unravel_u16(const u64* __restrict__ index, size_t n, int ndim, u64 d1, u64 d2, uint16_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const u64 f = index[p];
+    if (ndim == 2) {
+      out[2 * p] = (uint16_t)(f / d1);
+      out[2 * p + 1] = (uint16_t)(f % d1);
+    } else {
+      const u64 ij = f / d2;
+      out[3 * p] = (uint16_t)(ij / d1);
+      out[3 * p + 1] = (uint16_t)(ij % d1);
+      out[3 * p + 2] = (uint16_t)(f % d2);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ sorted (label, count) pairs
 // One persistent kernel: flip the sign bit of signed labels (so that unsigned digit order is the
 // dtype's order), sort the pairs by label (frb_coopsort.cuh), emit typed labels + values.
@@ -497,6 +556,64 @@ int frb_indices_emit(const void* a, size_t n, int dtype, uint64_t value_bits, ui
     default: k_match_emit<8><<<blocks, 256, 0, st>>>(a, n, chunk, v, offs, (u64*)out, capacity); break;
   }
   return check_launch("k_match_emit");
+}
+
+size_t frb_nonzero_ws_bytes(size_t n) { return (size_t)compact_blocks(n) * sizeof(u64) + 256; }
+
+int frb_nonzero_count(const void* a, size_t n, int dtype, uint64_t* meta, void* ws, size_t ws_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !a || n == 0 || !meta || !ws || ws_bytes < frb_nonzero_ws_bytes(n)) { set_error("frb_nonzero_count: bad arguments"); return FRB_ERR_BAD_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  switch (dtype_width(dtype)) {
+    case 1: k_nonzero_count<1><<<blocks, 256, 0, st>>>(a, n, chunk, (u64*)ws); break;
+    case 2: k_nonzero_count<2><<<blocks, 256, 0, st>>>(a, n, chunk, (u64*)ws); break;
+    case 4: k_nonzero_count<4><<<blocks, 256, 0, st>>>(a, n, chunk, (u64*)ws); break;
+    default: k_nonzero_count<8><<<blocks, 256, 0, st>>>(a, n, chunk, (u64*)ws); break;
+  }
+  int rc = check_launch("k_nonzero_count");
+  if (rc) return rc;
+  return scan_exclusive_u64((u64*)ws, (size_t)blocks, &((u64*)meta)[FRB_META_LIST_COUNT], st);
+}
+
+int frb_nonzero_emit(const void* a, size_t n, int dtype, uint64_t* labels_out, uint64_t* index_out, size_t capacity,
+                     const void* ws, void* stream) {
+  if (!dtype_ok(dtype) || !a || n == 0 || !ws || (capacity && (!labels_out || !index_out))) { set_error("frb_nonzero_emit: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (capacity == 0) return FRB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = compact_blocks(n);
+  const size_t chunk = compact_chunk(n, blocks);
+  const int w = dtype_width(dtype);
+  const u64 flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
+  const u64* offs = (const u64*)ws;
+  switch (w) {
+    case 1: k_nonzero_emit<1><<<blocks, 256, 0, st>>>(a, n, chunk, offs, flip, (u64*)labels_out, (u64*)index_out, capacity); break;
+    case 2: k_nonzero_emit<2><<<blocks, 256, 0, st>>>(a, n, chunk, offs, flip, (u64*)labels_out, (u64*)index_out, capacity); break;
+    case 4: k_nonzero_emit<4><<<blocks, 256, 0, st>>>(a, n, chunk, offs, flip, (u64*)labels_out, (u64*)index_out, capacity); break;
+    default: k_nonzero_emit<8><<<blocks, 256, 0, st>>>(a, n, chunk, offs, flip, (u64*)labels_out, (u64*)index_out, capacity); break;
+  }
+  return check_launch("k_nonzero_emit");
+}
+
+// stable sort of n (key, value) uint64 pairs by the low key_bits bits of the key (many-launch LSD
+// radix sort: lists as long as the volume).  workspace: 2 ping-pong lists + histograms
+size_t frb_sort_pairs_u64_ws_bytes(size_t n) {
+  const size_t c = n < 1 ? 1 : n;
+  return 2 * align_up(c * sizeof(u64), 256) + radix_hist_bytes(c);
+}
+int frb_sort_pairs_u64(uint64_t* keys, uint64_t* vals, size_t n, int key_bits, void* ws, size_t ws_bytes, void* stream) {
+  if ((n && (!keys || !vals)) || !ws || ws_bytes < frb_sort_pairs_u64_ws_bytes(n) || key_bits < 1 || key_bits > 64) { set_error("frb_sort_pairs_u64: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n <= 1) return FRB_OK;
+  const size_t lb = align_up(n * sizeof(u64), 256);
+  return radix_sort_u64((u64*)keys, (u64*)vals, (u64*)ws, (u64*)((char*)ws + lb), n, 0, key_bits, (char*)ws + 2 * lb, (cudaStream_t)stream);
+}
+
+int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint64_t d2, uint16_t* out, void* stream) {
+  if ((n && (!index || !out)) || (ndim != 2 && ndim != 3) || d1 == 0 || (ndim == 3 && d2 == 0)) { set_error("frb_unravel_u16: bad arguments"); return FRB_ERR_BAD_ARG; }
+  if (n == 0) return FRB_OK;
+  Grid g = grid_for(n, 256 * 4, 16);
+  k_unravel_u16<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((const u64*)index, n, ndim, d1, d2, out);
+  return check_launch("k_unravel_u16");
 }
 
 // workspace: 2 ping-pong lists of L uint64 + the cooperative sort's histograms and barrier word

@@ -192,6 +192,19 @@ size_t frb_indices_ws_bytes(size_t n);
 int frb_indices_count(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
 int frb_indices_emit(const void* a, size_t n, int dtype, uint64_t value_bits, uint64_t* out, size_t capacity, const void* ws, void* stream);
 
+/* ---- point_cloud (SURVEY 8(f) "next" row) ------------------------------------------------
+ * Replaces _point_cloud_2d / _3d (fastremap.pyx:1444-1540): the non-zero voxels of a C-order image
+ * as (label, flat index) uint64 pairs in scan order (labels with the sign bit flipped for signed
+ * dtypes), a stable sort by label, and the indices unravelled to uint16 coordinate rows. */
+size_t frb_nonzero_ws_bytes(size_t n);
+int frb_nonzero_count(const void* a, size_t n, int dtype, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
+int frb_nonzero_emit(const void* a, size_t n, int dtype, uint64_t* labels_out, uint64_t* index_out, size_t capacity,
+                     const void* ws, void* stream);
+size_t frb_sort_pairs_u64_ws_bytes(size_t n);
+int frb_sort_pairs_u64(uint64_t* keys, uint64_t* vals, size_t n, int key_bits, void* ws, size_t ws_bytes, void* stream);
+/* out[p] = unravel(index[p]) for a C-order shape (d0, d1) or (d0, d1, d2): rows of ndim uint16 */
+int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint64_t d2, uint16_t* out, void* stream);
+
 /* ---- component_map -------------------------------------------------------------------
  * Replaces _component_map (fastremap.pyx:565-587): at every run start of cc the table
  * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])

@@ -219,3 +219,28 @@ def test_inverse_component_map_vs_reference(oracle, reference):
   par = synth_numpy((12, 20, 24), (4, 5, 6), np.int16, seed=9, zero_frac=0.1, noise=0.0, cell_div=3)
   ref = reference.inverse_component_map(par, cc)
   assert {k: sorted(v) for k, v in ref.items()} == oracle.inverse_component_map(par, cc)
+
+
+def _cloud_sets(pc):
+  return {k: sorted(map(tuple, np.asarray(v).tolist())) for k, v in pc.items()}
+
+
+def test_point_cloud(oracle):  # automated_test.py:596-628
+  x = np.ones((2, 2, 2), dtype=np.uint8)
+  gt = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]])
+  ptc = oracle.point_cloud(x)
+  assert len(ptc) == 1 and np.all(ptc[1] == gt)
+  x[0, 0, 0] = 2
+  x[1, 1, 1] = 3
+  ptc = oracle.point_cloud(x)
+  assert len(ptc) == 3 and np.all(ptc[1] == gt[1:7]) and np.all(ptc[2] == gt[:1]) and np.all(ptc[3] == gt[7:])
+  assert oracle.point_cloud(np.ones((0, 0, 0), dtype=np.uint8)) == {}
+
+
+def test_point_cloud_vs_reference(oracle, reference):
+  from fastremap_b200.synth import synth_numpy
+  for shape, grid in (((9, 14, 20), (3, 4, 5)), ((1, 30, 26), (1, 5, 4))):
+    a = synth_numpy(shape, grid, np.int32, seed=4, zero_frac=0.3, noise=0.1)
+    a[a % 3 == 0] *= -1
+    for arr in (a, np.asfortranarray(a), a[0]):
+      assert _cloud_sets(reference.point_cloud(arr)) == _cloud_sets(oracle.point_cloud(arr))

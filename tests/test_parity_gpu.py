@@ -519,3 +519,31 @@ def test_inverse_component_map_vs_oracle(frb, oracle, dtypes):
     got = frb.inverse_component_map(a, b)
     assert got == oracle.inverse_component_map(a, b)
     assert all(isinstance(k, int) for k in got) and all(isinstance(x, int) for v in got.values() for x in v)
+
+
+# ------------------------------------------------------------------ point_cloud
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_point_cloud_vs_oracle(frb, oracle, dtype):
+  x = np.ones((2, 2, 2), dtype=dtype)  # automated_test.py:596-628
+  gt = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]])
+  ptc = frb.point_cloud(x)
+  assert len(ptc) == 1 and np.all(ptc[1] == gt) and ptc[1].dtype == np.uint16
+  x[0, 0, 0] = 2
+  x[1, 1, 1] = 3
+  ptc = frb.point_cloud(x)
+  assert len(ptc) == 3 and np.all(ptc[1] == gt[1:7]) and np.all(ptc[2] == gt[:1]) and np.all(ptc[3] == gt[7:])
+  assert frb.point_cloud(np.ones((0, 0, 0), dtype=dtype)) == {}
+  assert frb.point_cloud(np.zeros((3, 4, 5), dtype=dtype)) == {}
+  a = synth((11, 18, 27), (3, 4, 5), dtype, seed=6, zero_frac=0.3, noise=0.1)
+  if np.issubdtype(dtype, np.signedinteger):
+    a[a % 3 == 0] *= -1
+  for arr in (a, np.asfortranarray(a), a[3], np.asfortranarray(a[3])):
+    got, exp = frb.point_cloud(arr), oracle.point_cloud(arr)
+    assert list(got.keys()) == list(exp.keys())          # ascending labels, like the reference's argsort
+    for k in exp:
+      assert got[k].dtype == np.uint16 and np.array_equal(got[k], exp[k])   # scan order inside a label
+  b = (a != 0)
+  got, exp = frb.point_cloud(b), oracle.point_cloud(b)
+  assert list(got) == [1] and np.array_equal(got[1], exp[1])
