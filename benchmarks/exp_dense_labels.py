@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""renumber of 1024^3 uint64 at growing label counts: K1 / K2 / K3 times and the table's load factor."""
+import json, os, sys
+import numpy as np, torch
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from fastremap_b200 import api
+from fastremap_b200 import device as D
+from fastremap_b200.synth import synth_device
+S = 1024
+n = S ** 3
+D.dev()
+for g in (46, 108, 130, 165, 215):
+  vol = synth_device((S, S, S), (g, g, g), np.uint64, seed=3, zero_frac=0.1).reshape(-1).view(torch.uint8)
+  work = torch.empty_like(vol)
+  best = None
+  for _ in range(3):
+    work.copy_(vol)
+    timers = {}
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = api.renumber_device(work, n, np.uint64, write_wide=True, timers=timers)
+    e1.record()
+    torch.cuda.synchronize()
+    row = {"grid": g, "labels": res.n_labels, "cap": res.table.cap, "load": round(res.n_labels / res.table.cap, 3),
+           "total_ms": round(e0.elapsed_time(e1), 3)}
+    row.update({k: round(a.elapsed_time(b), 3) for k, (a, b) in timers.items()})
+    best = row if best is None or row["total_ms"] < best["total_ms"] else best
+  print(json.dumps(best), flush=True)
+  del vol, work, res

@@ -39,7 +39,12 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   __shared__ u64 s_seen[8][BUILD_CACHE];
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned int inserted = 0;
+  unsigned int inserted = 0;  // labels this lane has inserted ...
+  unsigned int reported = 0;  // ... of which this many have been added to meta[COUNT] already
+  unsigned int tiles_since_report = 0;
+  // a hashed table that is more than half full is too small: stop early (the host grows it and starts
+  // over) instead of running into the probe limit at ~100 % load, where every offer walks 512 slots
+  const u64 count_limit = direct ? ~0ull : (mask + 1) / 2 + 1;
   if (warp < STREAM_WARPS)
     for (int i = lane; i < BUILD_CACHE; i += 32) s_seen[warp][i] = FRB_EMPTY;
   __syncwarp();
@@ -144,12 +149,28 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
       }
     }
     __syncwarp();
+    // every 16th tile the warp adds what it has inserted to the global count (one atomic per warp) and
+    // learns from the returned value whether the table has passed half full
+    if (++tiles_since_report == 16) {
+      tiles_since_report = 0;
+      const unsigned int delta = __reduce_add_sync(FRB_FULL_MASK, inserted - reported);
+      reported = inserted;
+      if (delta) {
+        u64 before = 0;
+        if (lane == 0) before = atomicAdd(&meta[FRB_META_COUNT], (u64)delta);
+        before = __shfl_sync(FRB_FULL_MASK, before, 0);
+        if (before + delta > count_limit) {
+          if (lane == 0) atomicExch(&meta[FRB_META_OVERFLOW], 1ull);
+          aborted = true;
+        }
+      }
+    }
   };
 
   const TileMap map(nvec, (size_t)run);
   stream_rows<W, REVERSE, true, false>(a, nvec, map, row_fn, tile_end);
   resolve_pending();
-  block_add_to(&meta[FRB_META_COUNT], inserted);
+  block_add_to(&meta[FRB_META_COUNT], inserted - reported);
 }
 
 }  // namespace frb

@@ -68,6 +68,10 @@ k_table_scan(const uint4* __restrict__ slots, u64 cap, u64* counter, u64 capacit
 
 template <typename Sel>
 inline int launch_table_scan(const void* slots, u64 cap, u64* counter, u64 capacity, const Sel& sel, const char* what, cudaStream_t st) {
+  if (cap > (1ull << 32)) {
+    set_error("label tables hold at most 2^32 slots (64 GiB)");
+    return FRB_ERR_BAD_ARG;
+  }
   const size_t tiles = ((size_t)cap + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
   k_table_scan<Sel><<<stream_grid(k_table_scan<Sel>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
       (const uint4*)slots, cap, counter, capacity, sel, fair_run(stream_grid(k_table_scan<Sel>, tiles), tiles));
