@@ -41,6 +41,11 @@ struct CoopSortBuffers {
   unsigned int* barrier;  // one word, zeroed before the launch
 };
 
+#ifndef FRB_COOP_CTAS_PER_SM
+#define FRB_COOP_CTAS_PER_SM 1
+#endif
+// host side: CTAs of a cooperative sort launch (co-resident by construction)
+inline int coop_sort_grid() { return FRB_COOP_CTAS_PER_SM * sm_count(); }
 // host side: bytes of the hist + barrier area for a grid of `ctas` CTAs
 inline size_t coop_sort_aux_bytes(int ctas) { return (size_t)2 * ctas * 256 * sizeof(unsigned int) + 256; }
 

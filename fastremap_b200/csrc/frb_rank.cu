@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_rank_sort_assign(RankArgs A) {
   if (blockIdx.x == 0 && threadIdx.x == 0) A.meta[FRB_META_ASSIGNED] = assigned + n;
 }
 
-static int rank_grid() { return sm_count(); }  // one CTA per SM: the barrier cost grows with the grid, the work is tiny
+static int rank_grid() { return coop_sort_grid(); }
 
 }  // namespace frb
 
@@ -103,7 +103,7 @@ extern "C" {
 // workspace: 6 lists of `capacity` uint64 (sort key, 2 payloads, their ping-pong buffers) + histograms + barrier word
 size_t frb_renumber_rank_ws_bytes(size_t capacity) {
   const size_t c = capacity < 1 ? 1 : capacity;
-  return 6 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
+  return 6 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(coop_sort_grid()), 256);
 }
 
 int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int64_t start, uint64_t index_base,
@@ -116,7 +116,7 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t lb = align_up(capacity * sizeof(u64), 256);
-  const size_t hb = (size_t)2 * sm_count() * 256 * sizeof(unsigned int);
+  const size_t hb = (size_t)2 * coop_sort_grid() * 256 * sizeof(unsigned int);
   char* base = (char*)ws;
   RankArgs A;
   A.sort.keys = (u64*)(base);

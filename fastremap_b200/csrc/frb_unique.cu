@@ -619,7 +619,7 @@ int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint
 // workspace: 2 ping-pong lists of L uint64 + the cooperative sort's histograms and barrier word
 size_t frb_sort_pairs_ws_bytes(size_t L) {
   const size_t c = L < 1 ? 1 : L;
-  return 2 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(sm_count()), 256);
+  return 2 * align_up(c * sizeof(u64), 256) + align_up(coop_sort_aux_bytes(coop_sort_grid()), 256);
 }
 
 int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_t* count_dev, int dtype, void* uniq_out,
@@ -640,7 +640,7 @@ int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_
   A.sort.pay2 = nullptr;
   A.sort.pay2_alt = nullptr;
   A.sort.hist = (unsigned int*)((char*)ws + 2 * lb);
-  A.sort.barrier = (unsigned int*)((char*)ws + 2 * lb + (size_t)2 * sm_count() * 256 * sizeof(unsigned int));
+  A.sort.barrier = (unsigned int*)((char*)ws + 2 * lb + (size_t)2 * coop_sort_grid() * 256 * sizeof(unsigned int));
   A.n = L;
   A.n_dev = (const u64*)count_dev;
   A.flip = dtype_signed(dtype) ? (1ull << (8 * w - 1)) : 0ull;
@@ -656,7 +656,7 @@ int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_
     default: kernel = (const void*)k_sort_emit_pairs<8>; break;
   }
   void* params[] = {&A};
-  cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(sm_count()), dim3(CS_THREADS), params, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(coop_sort_grid()), dim3(CS_THREADS), params, 0, st);
   if (e != cudaSuccess) {
     set_error(cudaGetErrorString(e));
     return FRB_ERR_CUDA;

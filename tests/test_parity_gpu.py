@@ -547,3 +547,51 @@ def test_point_cloud_vs_oracle(frb, oracle, dtype):
   b = (a != 0)
   got, exp = frb.point_cloud(b), oracle.point_cloud(b)
   assert list(got) == [1] and np.array_equal(got[1], exp[1])
+
+
+# ------------------------------------------------------------------ BASELINE.json's full size: size-independent properties
+
+
+def test_full_size_properties_1024(frb):
+  """1024^3 uint64 (8 GiB, the workload bench.py times), device-resident: properties that must hold
+  whatever the size -- round trip through the inverse mapping, dense ids in encounter order,
+  idempotence, counts that add up, complementary masks."""
+  from fastremap_b200.synth import synth_device
+  S = 1024
+  n = S ** 3
+  vol = synth_device((S, S, S), (46, 46, 46), np.uint64, seed=0, zero_frac=0.1)
+  as_i64 = lambda t: t.reshape(-1).view(torch.uint8).view(torch.int64)
+  out, mapping = frb.renumber(vol)                                   # not in place: vol stays intact
+  assert out.dtype == torch.uint32 and tuple(out.shape) == (S, S, S)
+  L = len(mapping) - 1                                               # label 0 is preserved
+  assert mapping[0] == 0 and sorted(mapping.values()) == list(range(L + 1))
+  # ids are handed out in order of first appearance: the first voxels of the volume
+  head = vol.reshape(-1)[:4096].cpu().view(torch.int64).numpy().view(np.uint64)
+  seen, expect = {0: 0}, []
+  for x in head.tolist():
+    if x not in seen:
+      seen[x] = len(seen)
+    expect.append(seen[x])
+  assert out.reshape(-1)[:4096].cpu().view(torch.int32).numpy().tolist() == expect
+  # unique of the result: ids 0..L, counts add up to n and equal the counts of the labels they replace
+  u, c = frb.unique(out, return_counts=True)
+  assert u.cpu().view(torch.int32).numpy().tolist() == list(range(L + 1))
+  assert int(c.view(torch.int64).sum().item()) == n
+  u0, c0 = frb.unique(vol, return_counts=True)
+  by_label = dict(zip(u0.cpu().view(torch.int64).numpy().view(np.uint64).tolist(), c0.cpu().view(torch.int64).numpy().tolist()))
+  c_ids = c.cpu().view(torch.int64).numpy()
+  assert all(by_label[k] == int(c_ids[v]) for k, v in list(mapping.items())[:: max(L // 2000, 1)])
+  # round trip: remapping the ids through the inverse mapping gives the volume back (widened to uint64 by remap)
+  inverse = {v: k for k, v in mapping.items()}
+  back = frb.remap(out, inverse)
+  assert back.dtype == torch.uint64 and torch.equal(as_i64(back), as_i64(vol))
+  del back
+  # idempotence: the ids are already in encounter order
+  out2, mapping2 = frb.renumber(out)
+  assert all(k == v for k, v in mapping2.items()) and torch.equal(out2.reshape(-1).view(torch.int32), out.reshape(-1).view(torch.int32))
+  del out2
+  # complementary masks partition the foreground
+  keep = list(range(1, L + 1, 2))
+  fg = frb.foreground(out)
+  assert frb.foreground(frb.mask_except(out, keep)) + frb.foreground(frb.mask(out, keep)) == fg
+  assert frb.minmax(out) == (0, L) and frb.pixel_pairs(out) == frb.pixel_pairs(vol)
