@@ -228,8 +228,8 @@ def run_ours(args):
 
   def step_device():
     if world > 1:
-      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True, offset=rank * n, total=world * n, timers=timers)
-    return api.renumber_device(work, n, DTYPE, write_wide=True, timers=timers)
+      return sharded.renumber_sharded(work, n, DTYPE, write_wide=True, offset=rank * n, total=world * n, timers=timers, row_bytes=SIDE * 8)
+    return api.renumber_device(work, n, DTYPE, write_wide=True, timers=timers, row_bytes=SIDE * 8)
 
   def barrier():
     if world > 1:
@@ -318,7 +318,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     if world > 1:
       v = D.ingest(work_np)
-      r = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True, offset=rank * n, total=world * n)
+      r = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True, offset=rank * n, total=world * n, row_bytes=v.row_bytes)
       mapping = api._mapping_to_dict(r, v.dtype, True)
       D.download_into(r.wide, v.nbytes, D.flat_view(work_np))
       out = D.emit(r.out, r.out_dtype, v.shape, v.order, False)

@@ -78,15 +78,15 @@ def main():
       report("minmax+pixel_pairs u64 (K6)", n, 8, m, mn)
     del vol
     if "unique_dense" in ops:
-      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32), args.reps)
+      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, incl. minmax pre-pass (config 2a)", n, 4, m, mn, n_unique=out[2])
-      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, strategy="hash"), args.reps)
+      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, strategy="hash", row_bytes=S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, forced hash strategy", n, 4, m, mn, n_unique=out[2])
     del dense
 
   if "unique_sparse" in ops:
     vol = flat_u8(synth_device((S, S, S), (max(int(100 * sc), 1),) * 3, np.uint32, seed=1, zero_frac=0.1))
-    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32), args.reps)
+    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4), args.reps)
     report("unique(return_counts) u32 sparse ids, incl. minmax pre-pass (config 2b)", n, 4, m, mn, n_unique=out[2])
     if S <= 512:
       m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, strategy="sort"), max(args.reps // 2, 1))
@@ -123,7 +123,7 @@ def main():
       del work, table, uniq, keep, kb
     if "component_map" in ops:
       par = flat_u8(synth_device((S, S, S), (g, g, g), np.uint64, seed=5, zero_frac=0.0, cell_div=4))
-      m, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3), args.reps)
+      m, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8), args.reps)
       report("component_map (u64, u64) device arrays (config 5)", n, 16, m, mn, n_components=out[2])
       del par
     del cc

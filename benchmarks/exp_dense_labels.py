@@ -20,7 +20,7 @@ for g in (46, 108, 130, 165, 215):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = api.renumber_device(work, n, np.uint64, write_wide=True, timers=timers)
+    res = api.renumber_device(work, n, np.uint64, write_wide=True, timers=timers, row_bytes=S * 8)
     e1.record()
     torch.cuda.synchronize()
     row = {"grid": g, "labels": res.n_labels, "cap": res.table.cap, "load": round(res.n_labels / res.table.cap, 3),

@@ -29,7 +29,7 @@ def run_chunks(chunk_bytes, use_probe_only=False):
     src = ctypes.c_void_p(work.data_ptr() + a)
     nar = ctypes.c_void_p(narrow.data_ptr() + a // 2)
     if not use_probe_only:
-      _lib.check(L.frb_renumber_build(src, ne, c, a // 8, 1, D.ptr(table.slots), table.cap, D.ptr(table.meta), st))
+      _lib.check(L.frb_renumber_build(src, ne, c, a // 8, 1, D.ptr(table.slots), table.cap, D.ptr(table.meta), S * 8, st))
     else:
       _lib.check(L.frb_stream_probe(src, b - a, None, None, 0, D.ptr(out), st))
     _lib.check(L.frb_stream_probe(src, b - a, src, nar, 2, D.ptr(out), st))

@@ -39,7 +39,7 @@ SIGNATURES = {
   "frb_table_resolve": (_i, [_vp, _i, _vp, _u64, _vp, _vp]),
   "frb_table_export": (_i, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
   "frb_minmax_pairs": (_i, [_vp, _sz, _i, _vp, _vp]),
-  "frb_renumber_build": (_i, [_vp, _sz, _i, _u64, _i, _vp, _u64, _vp, _vp]),
+  "frb_renumber_build": (_i, [_vp, _sz, _i, _u64, _i, _vp, _u64, _vp, _u64, _vp]),
   "frb_renumber_rank_ws_bytes": (_sz, [_sz]),
   "frb_renumber_rank": (_i, [_vp, _u64, _vp, _i, _i64, _u64, _u64, _vp, _vp, _sz, _vp, _sz, _vp]),
   "frb_relabel": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _u64, _i, _i, _vp]),
@@ -49,11 +49,11 @@ SIGNATURES = {
   "frb_swap_halves": (_i, [_vp, _vp, _sz, _i, _vp]),
   "frb_pack_pairs": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp]),
   "frb_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
-  "frb_hist_dense": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp]),
+  "frb_hist_dense": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _u64, _vp]),
   "frb_compact_bins_ws_bytes": (_sz, [_u64]),
   "frb_compact_bins_count": (_i, [_vp, _u64, _vp, _vp, _sz, _vp]),
   "frb_compact_bins_emit": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _sz, _vp, _vp]),
-  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _vp]),
+  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _u64, _vp]),
   "frb_sort_pairs_ws_bytes": (_sz, [_sz]),
   "frb_sort_table_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
   "frb_unique_sort_ws_bytes": (_sz, [_sz, _i]),
@@ -68,7 +68,7 @@ SIGNATURES = {
   "frb_sort_pairs_u64_ws_bytes": (_sz, [_sz]),
   "frb_sort_pairs_u64": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
   "frb_unravel_u16": (_i, [_vp, _sz, _i, _u64, _u64, _vp, _vp]),
-  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _vp]),
+  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
   "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),

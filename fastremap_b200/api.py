@@ -385,11 +385,13 @@ def _auto_result(src_buf, narrow, dtype, start, table, rb, meta) -> RenumberResu
 
 
 def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                    flat_offset=0, total_n=None, timers=None) -> RenumberResult:
+                    flat_offset=0, total_n=None, timers=None, row_bytes=0) -> RenumberResult:
   """
   K1 -> K2 -> K3 on a flat device buffer.
     write_wide: also overwrite src_buf with the new ids at the input width (in_place=True).
     timers: optional dict; receives CUDA event pairs "k1" / "k2" / "k3" recorded on the launching stream.
+    row_bytes: length of the volume's fastest axis in bytes (0 = unknown): a hint that aims K1's
+    "same as the voxels directly above" filter.
   The three kernels are queued back to back: the label count stays on the device (K2 reads it there,
   K3 picks the refit width from it), and the host reads the table's meta block once, afterwards.
   """
@@ -402,7 +404,7 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
   def build(t):
     _ev(timers, "k1", 0)
     _lib.check(L.frb_renumber_build(D.ptr(src_buf), n, c, flat_offset, 1 if preserve_zero else 0, D.ptr(t.slots), t.cap,
-                                    D.ptr(t.meta), D.stream()), "frb_renumber_build")
+                                    D.ptr(t.meta), row_bytes, D.stream()), "frb_renumber_build")
     _ev(timers, "k1", 1)
 
   while True:
@@ -498,6 +500,7 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
   nbytes = n * w
   order = "F" if arr.flags["F_CONTIGUOUS"] else "C"
   host_u8 = D.as_torch_bytes(D.flat_view(arr))
+  hint = D.row_bytes(arr.shape, order, dtype)
   chunk = max(STREAM_CHUNK_BYTES // 16 * 16, 16)
   bounds = [(a, min(a + chunk, nbytes)) for a in range(0, nbytes, chunk)]
   C = len(bounds)
@@ -526,7 +529,7 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
     cur.wait_event(ev_in[i])
     view = dev_buf[a:b]
     _lib.check(L.frb_renumber_build(D.ptr(view), ne, c, a // w, 1 if preserve_zero else 0, D.ptr(table.slots), table.cap,
-                                    D.ptr(table.meta), D.stream()), "frb_renumber_build")
+                                    D.ptr(table.meta), hint, D.stream()), "frb_renumber_build")
     _rank(table, rb, dtype, start, a // w, ne)
     flags[i].copy_(table.meta, non_blocking=True)
     ev_meta[i] = torch.cuda.Event()
@@ -619,7 +622,7 @@ def renumber(arr, start=1, preserve_zero=True, in_place=False, *, max_labels=Non
       return _renumber_streamed(arr, start, preserve_zero, in_place_eff, max_labels)
     v = D.ingest(arr)
   res = renumber_device(v.buf, v.n, v.dtype, start=start, preserve_zero=preserve_zero, write_wide=in_place_eff,
-                        max_labels=max_labels)
+                        max_labels=max_labels, row_bytes=v.row_bytes)
   mapping = _mapping_to_dict(res, v.dtype, preserve_zero)
 
   if is_t:
@@ -948,11 +951,11 @@ def component_map_arrays(component_labels, parent_labels, max_labels=None):
     vc, vp = D.ingest(component_labels), D.ingest(parent_labels)
   _require_int(vc.dtype, "component_map")
   _require_int(vp.dtype, "component_map")
-  keys, pars, nl = component_map_device(vc.buf, vc.n, vc.dtype, vp.buf, vp.dtype, max_labels=max_labels)
+  keys, pars, nl = component_map_device(vc.buf, vc.n, vc.dtype, vp.buf, vp.dtype, max_labels=max_labels, row_bytes=vc.row_bytes)
   return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
 
 
-def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None):
+def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None, row_bytes=0):
   """K7 on flat device buffers: returns (keys_buf, parents_buf, n_labels), unordered."""
   cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
   L = _L()
@@ -960,7 +963,7 @@ def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labe
 
   def build(t):
     _lib.check(L.frb_component_build(D.ptr(cc_buf), n, D.code(cc_dtype), 0, D.ptr(t.slots), t.cap, D.ptr(t.meta),
-                                     D.stream()), "frb_component_build")
+                                     row_bytes, D.stream()), "frb_component_build")
 
   meta = _run_build(build, table)
   nl = int(meta[_lib.META_COUNT])
@@ -1131,7 +1134,7 @@ DENSE_MAX_BINS = 1 << 27        # 1 GiB of uint64 bins
 HASH_MAX_FRACTION = 8           # hash strategy while distinct labels <= n / 8, else sort + RLE
 
 
-def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
+def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_bytes=0):
   """
   Sorted distinct labels and their counts of a flat device buffer.
   Returns (uniq_buf, counts_buf, n_unique); buffers are flat uint8 CUDA tensors (labels in `dtype`,
@@ -1152,7 +1155,7 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
       raise ValueError("unique: dense strategy needs max - min < %d" % DENSE_MAX_BINS)
     min_bits = _to_bits(mn, dtype)
     counts = torch.zeros(bins, dtype=torch.int64, device=D.dev())
-    _lib.check(L.frb_hist_dense(D.ptr(buf), n, c, min_bits, D.ptr(counts), bins, D.stream()), "frb_hist_dense")
+    _lib.check(L.frb_hist_dense(D.ptr(buf), n, c, min_bits, D.ptr(counts), bins, row_bytes, D.stream()), "frb_hist_dense")
     meta = D.alloc_meta()
     ws_bytes = int(L.frb_compact_bins_ws_bytes(bins))
     ws = D.alloc(ws_bytes)
@@ -1174,7 +1177,7 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None):
       ws_bytes = int(L.frb_sort_pairs_ws_bytes(room))
       ws = D.alloc(ws_bytes)
       uniq, cts = D.alloc(room * w), D.alloc(room * 8)
-      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), D.stream()), "frb_hist_hash")
+      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), row_bytes, D.stream()), "frb_hist_hash")
       _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), room, D.stream()),
                  "frb_table_export")
       count_dev = ctypes.c_void_p(table.meta.data_ptr() + 8 * _lib.META_LIST_COUNT)
@@ -1208,7 +1211,7 @@ def _first_indices_sorted(buf, n, dtype, nu):
   table = LabelTable(dtype, nu, _lib.EMPTY)
 
   def build(t):
-    _lib.check(L.frb_renumber_build(D.ptr(buf), n, D.code(dtype), 0, 0, D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()),
+    _lib.check(L.frb_renumber_build(D.ptr(buf), n, D.code(dtype), 0, 0, D.ptr(t.slots), t.cap, D.ptr(t.meta), 0, D.stream()),
                "frb_renumber_build")
 
   meta = _run_build(build, table)
@@ -1333,7 +1336,7 @@ def unique(labels, return_index=False, return_inverse=False, return_counts=False
       if v.order == "F" and len(shape) > 1:
         v = D.ingest(labels.contiguous() if is_t else np.ascontiguousarray(labels), alias_ok=True)
 
-  uniq, cts, nu = unique_counts_device(v.buf, v.n, v.dtype, strategy=strategy)
+  uniq, cts, nu = unique_counts_device(v.buf, v.n, v.dtype, strategy=strategy, row_bytes=v.row_bytes)
   intp = branch == "numpy"
   results = []
   if is_t:

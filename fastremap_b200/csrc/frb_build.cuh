@@ -5,10 +5,10 @@
 // with MIN / MAX -- so the work is in offering as few as possible: segmentation volumes repeat the
 // same label for tens of voxels in every direction.  Three filters sit between a voxel and the
 // table, each exact:
-//   1. registers: a lane remembers the 16-byte vector it saw at the same position of its warp's
-//      previous tile (with the run-interleaved tile order that is the voxels one or two rows up in
-//      y; tiles are walked backwards for MAX, so "previous" always means "already offered something
-//      at least as good").  K1: an element equal to the remembered one, or to its predecessor in
+//   1. registers: a lane remembers the 16-byte vectors of its last four rows; a warp's rows are
+//      4 KiB apart (stream_vec), so for the usual row lengths one of them is the voxels DIRECTLY above
+//      (rows_up / pick_slot; below, when tiles are walked backwards for MAX -- "remembered" always
+//      means "already offered something at least as good").  K1: an element equal to the remembered one, or to its predecessor in
 //      memory, is dominated.  K7 (HEADS): if the vector AND the element in front of it are the same
 //      as remembered, every run start in it has a twin one tile later.  Testing a whole vector costs
 //      7 integer instructions for all V elements.
@@ -31,7 +31,9 @@ __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct
 }
 
 // value offered for element i is bias + i.  HEADS: only run starts (a[i] != a[i-1]) are offered.
-template <int W, int OP, bool REVERSE, bool HEADS>
+// DU: which of the lane's row slots holds the row directly above / below (rows_up; compile-time, the
+// selection must not cost instructions: this loop is issue-bound)
+template <int W, int OP, bool REVERSE, bool HEADS, int DU>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run) {
   constexpr int V = 16 / W;
@@ -57,9 +59,10 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     }
   }
 
-  uint4 last[STREAM_ROWS];
-  u64 last_prev[HEADS ? STREAM_ROWS : 1];
-  bool have_last = false;      // false until the warp has processed its first tile
+  static_assert(STREAM_ROWS == 4, "pick_slot assumes 4 row slots per lane");
+  uint4 last[4];
+  u64 last_prev[4];  // HEADS only
+  unsigned int have = 0;       // bit u: row slot u of this lane holds a vector it has really seen
   u64 cand = 0;                // bit (u * V + j): element j of row u needs a closer look
   // A full table makes the rest of the pass pointless (the host grows the table and retries): a lane
   // stops offering once one of its own offers failed, or if the table had already overflowed when
@@ -77,11 +80,13 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
 
   auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
     if (!valid) return;
-    const uint4 l = last[u];
+    const uint4 l = last[ref_slot_ct<REVERSE, DU>(u)];  // the row above (below) this one, if the row length is known
+    const bool have_last = (have >> ref_slot_ct<REVERSE, DU>(u)) & 1u;
     last[u] = cur;
+    have |= 1u << u;
     const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
     if (HEADS) {
-      const u64 lp = last_prev[u];
+      const u64 lp = last_prev[ref_slot_ct<REVERSE, DU>(u)];
       last_prev[u] = prev;
       if (d != 0 || !have_last || !has_prev || prev != lp) {
         // not a copy of the remembered row: every run start in it is a candidate
@@ -117,7 +122,6 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   };
 
   auto tile_end = [&](const uint4* stage, size_t vb) {
-    have_last = true;
     resolve_pending();
     if (aborted) cand = 0;
     // phase 1: which candidates has this warp not offered before?
@@ -125,7 +129,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     for (u64 m = cand; m; m &= m - 1) {
       const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
       const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec(u, warp, lane))[j];
       const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
       if (!hit) todo |= 1ull << b;
     }
@@ -135,9 +139,9 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     for (u64 m = todo; m; m &= m - 1) {
       const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
       const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + u * 32 + lane)[j];
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec(u, warp, lane))[j];
       const u64 h = hash_key(key);
-      const u64 val = bias + (u64)((vb + u * 32 + lane) * V + j);
+      const u64 val = bias + (u64)((vb + stream_vec(u, warp, lane)) * V + j);
       s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
       if (!pend && key != FRB_EMPTY) {
         pend = true;
@@ -168,7 +172,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   };
 
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, REVERSE, true, false>(a, nvec, map, row_fn, tile_end);
+  stream_rows<W, REVERSE, true, true>(a, nvec, map, row_fn, tile_end);
   resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);
 }

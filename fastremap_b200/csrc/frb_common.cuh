@@ -347,8 +347,8 @@ __device__ __forceinline__ void block_add_to(u64* target, unsigned int v) {
 //              lanes, rows, tiles and CTAs: it comes out of the same staged bytes), valid iff has_prev
 //   after_tile(k) (optional) is called by every consumer warp after it has released tile number k
 //     of the CTA -- also by warps whose part of the last tile lies past the end of the array.
-//   tile_end(wstage, vb) is called once per warp-tile after its rows; `wstage` still holds the
-//     warp-tile (vector u*32+lane of it is what row_fn(u) saw), vb is its first vector index.
+//   tile_end(stage, vb) is called once per warp and tile after its rows; `stage` still holds the CTA
+//     tile (vector stream_vec(u, warp, lane) of it is what row_fn(u) saw), vb is its first vector index.
 //
 // REVERSE walks tiles and rows from the back (component_map keeps the LAST run start).
 // Kernels are launched with STREAM_THREADS threads; every lane of a consumer warp calls row_fn
@@ -367,6 +367,31 @@ static constexpr int STREAM_STAGES = FRB_STREAM_STAGES;
 static constexpr int STREAM_STAGE_VECS = STREAM_TILE_VECS + 8;             // 128 B in front: predecessor vector + pad
 static constexpr int STREAM_SMEM_BYTES = STREAM_STAGES * STREAM_STAGE_VECS * 16 + 2 * STREAM_STAGES * 8;
 
+// Vector (inside the 16 KiB CTA tile) that lane `lane` of consumer warp `warp` handles in its row u.
+// Rows of one warp are INTERLEAVED with those of the other warps (512-byte chunk number u * 8 + warp),
+// so a warp's rows are 4 KiB apart: for volumes whose fastest axis is a multiple of 4 KiB long, a
+// lane meets the voxels directly above / below its previous row one or two rows later -- what the
+// "same as the row above" filters of the build and counting kernels feed on.
+template <bool INTERLEAVE = true>
+__device__ __forceinline__ int stream_vec(int u, int warp, int lane) {
+  return INTERLEAVE ? (u * STREAM_WARPS + warp) * 32 + lane : (warp * STREAM_ROWS + u) * 32 + lane;
+}
+
+// A lane remembers the last vector it saw in each of its 4 row slots.  For a volume whose fastest
+// axis is q * 4 KiB long (q = 1..4) the voxels directly above row u (below, when tiles are walked
+// backwards) are what the lane saw q rows earlier: slot (u -/+ q) mod 4, of this tile or the previous
+// one.  DU = q, or 4 when the row length is unknown / no such slot exists ("same position, previous
+// tile": a row or two further up for typical volumes -- still a good predictor, just a weaker one).
+// DU is a template parameter of the kernels: selecting the slot at run time cost K1 30 %.
+inline int rows_up(size_t row_bytes) {
+  if (row_bytes == 0 || (row_bytes % 4096) != 0) return 4;
+  const size_t q = row_bytes / 4096;
+  return q >= 1 && q <= 4 ? (int)q : 4;
+}
+template <bool REVERSE, int DU>
+__device__ __forceinline__ constexpr int ref_slot_ct(int u) {
+  return DU == 1 ? (REVERSE ? ((u + 1) & 3) : ((u + 3) & 3)) : DU == 2 ? ((u + 2) & 3) : DU == 3 ? (REVERSE ? ((u + 3) & 3) : ((u + 1) & 3)) : (u & 3);
+}
 struct TileMap {
   size_t tiles;   // tiles in the whole array
   size_t run;     // consecutive tiles per run
@@ -458,7 +483,10 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn, typename AfterTileFn>
+// INTERLEAVE: see stream_vec.  Kernels that write the volume back (K3) keep a warp's rows contiguous:
+// measured, interleaving costs them 8 % (stores of one warp 4 KiB apart), while the kernels that only
+// read gain from the vertical alignment of a lane's rows.
+template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
@@ -511,45 +539,45 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   for (size_t k = 0; k < ntiles; k++) {
     const size_t t = it.tile();
     it.template step<REVERSE>();
-    const size_t vb = t * STREAM_TILE_VECS + (size_t)warp * (R * 32);
+    const size_t vb = t * STREAM_TILE_VECS;  // first vector of the CTA tile
     mbar_wait(&full[s], round & 1u);
-    const uint4* wstage = ring + (size_t)s * STREAM_STAGE_VECS + 8 + (size_t)warp * (R * 32);
-    if (vb + R * 32 <= nvec) {
-      // whole warp-tile inside the array (all but the last tile): no per-lane bounds checks
+    const uint4* stage = ring + (size_t)s * STREAM_STAGE_VECS + 8;
+    if (vb + STREAM_TILE_VECS <= nvec) {
+      // whole tile inside the array (all but the last tile): no per-lane bounds checks
 #pragma unroll
       for (int uu = 0; uu < R; uu++) {
         const int u = REVERSE ? R - 1 - uu : uu;
-        const int off = u * 32 + lane;
-        const uint4 cur = wstage[off];
+        const int off = stream_vec<INTERLEAVE>(u, warp, lane);
+        const uint4 cur = stage[off];
         u64 prev = 0;
         bool has_prev = false;
         if (NEED_PREV) {
           has_prev = (vb + off) != 0;
-          if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);
+          if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(stage + off) - 1);
         }
         row_fn(u, cur, true, (vb + off) * V, prev, has_prev);
       }
-      tile_end(wstage, vb);
-    } else if (vb < nvec) {
+      tile_end(stage, vb);
+    } else if (vb + (size_t)stream_vec<INTERLEAVE>(0, warp, 0) < nvec) {  // the warp's first row starts inside the array
 #pragma unroll
       for (int uu = 0; uu < R; uu++) {
         const int u = REVERSE ? R - 1 - uu : uu;
-        const int off = u * 32 + lane;
+        const int off = stream_vec<INTERLEAVE>(u, warp, lane);
         const size_t vi = vb + off;
         const bool valid = vi < nvec;
         uint4 cur = make_uint4(0, 0, 0, 0);
         u64 prev = 0;
         bool has_prev = false;
         if (valid) {
-          cur = wstage[off];
+          cur = stage[off];
           if (NEED_PREV && vi > 0) {
-            prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);  // element in front
+            prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(stage + off) - 1);  // element in front
             has_prev = true;
           }
         }
         row_fn(u, cur, valid, vi * V, prev, has_prev);
       }
-      tile_end(wstage, vb);
+      tile_end(stage, vb);
     }
     __syncwarp();  // every lane of this warp is done with the stage
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -557,10 +585,10 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
-template <int W, bool REVERSE, bool NEED_PREV, bool RW, typename RowFn, typename TileEndFn>
+template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end) {
-  stream_rows<W, REVERSE, NEED_PREV, RW>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }
 // barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }

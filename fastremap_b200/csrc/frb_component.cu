@@ -12,11 +12,11 @@
 
 namespace frb {
 
-template <int W>
+template <int W, int DU>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
                   u64* __restrict__ meta, int run) {
-  build_pass<W, FRB_OP_MAX, true, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
+  build_pass<W, FRB_OP_MAX, true, true, DU>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run);
 }
 
 // gather: scan the table (frb_scan.cuh) and emit (label, parent[winning run start]) for every label
@@ -100,7 +100,7 @@ using namespace frb;
 extern "C" {
 
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, void* stream) {
+                        uint64_t* meta, uint64_t row_bytes, void* stream) {
   if (!dtype_ok(cc_dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!cc || !aligned16(cc)))) { set_error("frb_component_build: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(cc_dtype);
@@ -111,12 +111,18 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   const uint4* p = (const uint4*)cc;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
+  const int du = rows_up((size_t)row_bytes);
+#define FRB_K7(WW, DD) k_component_build<WW, DD><<<stream_grid(k_component_build<WW, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, DD>, tiles), tiles))
+#define FRB_K7_DU(WW) switch (du) { case 1: FRB_K7(WW, 1); break; case 2: FRB_K7(WW, 2); break; case 3: FRB_K7(WW, 3); break; default: FRB_K7(WW, 4); break; }
   switch (w) {
-    case 1: k_component_build<1><<<stream_grid(k_component_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<1>, tiles), tiles)); break;
-    case 2: k_component_build<2><<<stream_grid(k_component_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<2>, tiles), tiles)); break;
-    case 4: k_component_build<4><<<stream_grid(k_component_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<4>, tiles), tiles)); break;
-    default: k_component_build<8><<<stream_grid(k_component_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<8>, tiles), tiles)); break;
+    case 1: FRB_K7_DU(1) break;
+    case 2: FRB_K7_DU(2) break;
+    case 4: FRB_K7_DU(4) break;
+    default: FRB_K7_DU(8) break;
   }
+#undef FRB_K7_DU
+#undef FRB_K7
   return check_launch("k_component_build");
 }
 

@@ -98,7 +98,7 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
     if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, true>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<W, false, false, false>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
@@ -145,7 +145,7 @@ k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, Rel
     if (W > 4 && wo == 4) store_results<V, (W > 4 ? 4 : 1)>(dst_narrow, i0, r);
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, true>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<W, false, false, false>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
@@ -170,7 +170,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
   constexpr int R = STREAM_ROWS;
   static_assert(W >= 4 && R % NB == 0, "hashed tables only");
   const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
   auto tile_end = [&](const uint4* stage, size_t vb) {
 #pragma unroll
@@ -181,8 +181,8 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 #pragma unroll
       for (int q = 0; q < NB; q++) {
         const int u = u0 + q;
-        valid[q] = vb + u * 32 + lane < nvec;
-        const uint4 cur = valid[q] ? stage[u * 32 + lane] : make_uint4(0, 0, 0, 0);
+        valid[q] = vb + stream_vec<false>(u, warp, lane) < nvec;
+        const uint4 cur = valid[q] ? stage[stream_vec<false>(u, warp, lane)] : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < V; j++) {
           key[q][j] = vec_get<W>(cur, j);
@@ -195,7 +195,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 #pragma unroll
       for (int q = 0; q < NB; q++) {
         if (!valid[q]) continue;
-        const size_t i0 = (vb + (u0 + q) * 32 + lane) * V;
+        const size_t i0 = (vb + stream_vec<false>(u0 + q, warp, lane)) * V;
         u64 r[V];
 #pragma unroll
         for (int j = 0; j < V; j++) r[j] = relabel_one<true>(A, key[q][j], h[q][j], first[q][j], i0 + j);
@@ -204,7 +204,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
     }
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, true>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
+  stream_rows<W, false, false, false>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {

@@ -96,11 +96,11 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 // ------------------------------------------------------------------------------------------ K1
 // First-index pass: the table receives, for every label, the minimum flat index at which it occurs
 // (tagged: see FRB_RANK_TAG).  The filtered build pass is shared with K7: frb_build.cuh.
-template <int W>
+template <int W, int DU>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
                  u64 mask, int direct, u64* __restrict__ meta, int run) {
-  build_pass<W, FRB_OP_MIN, false, false>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run);
+  build_pass<W, FRB_OP_MIN, false, false, DU>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run);
 }
 
 // ------------------------------------------------------------------------------------------ probes
@@ -117,7 +117,7 @@ k_stream_probe(const uint4* __restrict__ a, size_t nvec, void* wide, void* narro
     if (mode >= 2) st_stream8((char*)narrow + i0 * 4, make_uint2(cur.x, cur.z));
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<8, false, PREV, true>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<8, false, PREV, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
   acc = __reduce_xor_sync(FRB_FULL_MASK, acc);
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
 }
@@ -166,7 +166,7 @@ int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_n
 }
 
 int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset, int skip_zero, void* slots,
-                       uint64_t cap, uint64_t* meta, void* stream) {
+                       uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a)))) {
     set_error("frb_renumber_build: bad arguments");
     return FRB_ERR_BAD_ARG;
@@ -180,12 +180,18 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   const uint4* p = (const uint4*)a;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
+  const int du = rows_up((size_t)row_bytes);
+#define FRB_K1(WW, DD) k_renumber_build<WW, DD><<<stream_grid(k_renumber_build<WW, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, DD>, tiles), tiles))
+#define FRB_K1_DU(WW) switch (du) { case 1: FRB_K1(WW, 1); break; case 2: FRB_K1(WW, 2); break; case 3: FRB_K1(WW, 3); break; default: FRB_K1(WW, 4); break; }
   switch (w) {
-    case 1: k_renumber_build<1><<<stream_grid(k_renumber_build<1>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<1>, tiles), tiles)); break;
-    case 2: k_renumber_build<2><<<stream_grid(k_renumber_build<2>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<2>, tiles), tiles)); break;
-    case 4: k_renumber_build<4><<<stream_grid(k_renumber_build<4>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<4>, tiles), tiles)); break;
-    default: k_renumber_build<8><<<stream_grid(k_renumber_build<8>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<8>, tiles), tiles)); break;
+    case 1: FRB_K1_DU(1) break;
+    case 2: FRB_K1_DU(2) break;
+    case 4: FRB_K1_DU(4) break;
+    default: FRB_K1_DU(8) break;
   }
+#undef FRB_K1_DU
+#undef FRB_K1
   return check_launch("k_renumber_build");
 }
 

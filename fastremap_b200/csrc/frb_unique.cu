@@ -51,8 +51,9 @@ static constexpr int HIST_FLUSH_SYNCS = 8;     // ... and flush the table to mem
 static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its entries are taken
 
 // Counting pass.  Three levels of aggregation sit between a voxel and a global atomic:
-//   lane   remembers the 16-byte vector it saw at the same position of its warp's previous tile
-//          (one row up in the volume) and a repeat count; an identical vector just bumps the count
+//   lane   remembers the 16-byte vector it saw directly above (rows of a warp are 4 KiB apart, rows
+//          that lie above one another share a pattern slot: hist_slot) and a repeat count; an
+//          identical vector just bumps the count
 //          (7 integer instructions for V voxels).  A different vector flushes the old one: equal
 //          neighbours inside the vector are merged and (label, multiplicity * repeats) is added to
 //   CTA    a shared-memory hash of (label, partial count) shared by the 8 consumer warps (they walk
@@ -63,7 +64,11 @@ static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its
 //          named barrier and, on a schedule or when the table is filling up, drain it with one
 //   global atomic per live entry (dense bins or the label table, see the sinks above); the home-slot
 //          reads of a thread's entries are issued together so their L2 round trips overlap.
-template <int W, typename Sink>
+// pattern slot of row u: rows that lie directly above one another (q * 4 KiB apart, q = DU) share a slot
+template <int DU>
+__device__ __forceinline__ constexpr int hist_slot(int u) { return DU == 1 ? 0 : DU == 2 ? (u & 1) : DU == 3 ? (u == 3 ? 0 : u) : u; }
+
+template <int W, typename Sink, int DU>
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
   constexpr int V = 16 / W;
   __shared__ u64 s_key[HIST_CACHE];
@@ -122,14 +127,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
 
   auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
     if (!valid) return;
-    const uint4 l = pat[u];
+    const int sl = hist_slot<DU>(u);  // a constant once the row loop is unrolled
+    const uint4 l = pat[sl];
     const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
-    if (d == 0 && rep[u] != 0) {
-      rep[u]++;
+    if (d == 0 && rep[sl] != 0) {
+      rep[sl]++;
     } else {
-      if (rep[u] != 0) flush_vec(l, rep[u]);
-      pat[u] = cur;
-      rep[u] = 1;
+      if (rep[sl] != 0) flush_vec(l, rep[sl]);
+      pat[sl] = cur;
+      rep[sl] = 1;
     }
   };
   // all consumer threads, between two consumer barriers: nobody is inside add()
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
   };
 
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  stream_rows<W, false, false, true>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
   if (consumer) {
 #pragma unroll
     for (int u = 0; u < STREAM_ROWS; u++)
@@ -444,7 +450,7 @@ using namespace frb;
 
 extern "C" {
 
-int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, void* stream) {
+int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, uint64_t row_bytes, void* stream) {
   if (!dtype_ok(dtype) || !counts || bins == 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_dense: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(dtype);
@@ -455,16 +461,22 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
+  const int du = rows_up((size_t)row_bytes);
+#define FRB_KH(WW, DD) k_hist<WW, DenseSink, DD><<<stream_grid(k_hist<WW, DenseSink, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, DD>, tiles), tiles))
+#define FRB_KH_DU(WW) switch (du) { case 1: FRB_KH(WW, 1); break; case 2: FRB_KH(WW, 2); break; case 3: FRB_KH(WW, 3); break; default: FRB_KH(WW, 4); break; }
   switch (w) {
-    case 1: k_hist<1, DenseSink><<<stream_grid(k_hist<1, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<1, DenseSink>, tiles), tiles)); break;
-    case 2: k_hist<2, DenseSink><<<stream_grid(k_hist<2, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<2, DenseSink>, tiles), tiles)); break;
-    case 4: k_hist<4, DenseSink><<<stream_grid(k_hist<4, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<4, DenseSink>, tiles), tiles)); break;
-    default: k_hist<8, DenseSink><<<stream_grid(k_hist<8, DenseSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, nullptr, fair_run(stream_grid(k_hist<8, DenseSink>, tiles), tiles)); break;
+    case 1: FRB_KH_DU(1) break;
+    case 2: FRB_KH_DU(2) break;
+    case 4: FRB_KH_DU(4) break;
+    default: FRB_KH_DU(8) break;
   }
+#undef FRB_KH_DU
+#undef FRB_KH
   return check_launch("k_hist<dense>");
 }
 
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_hash: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(dtype);
@@ -478,12 +490,18 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
+  const int du = rows_up((size_t)row_bytes);
+#define FRB_KH(WW, DD) k_hist<WW, HashSink, DD><<<stream_grid(k_hist<WW, HashSink, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, DD>, tiles), tiles))
+#define FRB_KH_DU(WW) switch (du) { case 1: FRB_KH(WW, 1); break; case 2: FRB_KH(WW, 2); break; case 3: FRB_KH(WW, 3); break; default: FRB_KH(WW, 4); break; }
   switch (w) {
-    case 1: k_hist<1, HashSink><<<stream_grid(k_hist<1, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<1, HashSink>, tiles), tiles)); break;
-    case 2: k_hist<2, HashSink><<<stream_grid(k_hist<2, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<2, HashSink>, tiles), tiles)); break;
-    case 4: k_hist<4, HashSink><<<stream_grid(k_hist<4, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<4, HashSink>, tiles), tiles)); break;
-    default: k_hist<8, HashSink><<<stream_grid(k_hist<8, HashSink>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, ct, fair_run(stream_grid(k_hist<8, HashSink>, tiles), tiles)); break;
+    case 1: FRB_KH_DU(1) break;
+    case 2: FRB_KH_DU(2) break;
+    case 4: FRB_KH_DU(4) break;
+    default: FRB_KH_DU(8) break;
   }
+#undef FRB_KH_DU
+#undef FRB_KH
   return check_launch("k_hist<hash>");
 }
 

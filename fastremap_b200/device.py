@@ -158,6 +158,17 @@ class Vol:
   def nbytes(self):
     return self.n * self.dtype.itemsize
 
+  @property
+  def row_bytes(self):
+    """Length in bytes of the fastest-varying axis (a hint for the kernels' row filters)."""
+    return row_bytes(self.shape, self.order, self.dtype)
+
+
+def row_bytes(shape, order, dtype) -> int:
+  if len(shape) == 0:
+    return 0
+  return int(shape[0] if order == "F" else shape[-1]) * np.dtype(dtype).itemsize
+
 
 def ingest(arr, alias_ok: bool = False) -> Vol:
   """

@@ -67,7 +67,7 @@ def allgather_pairs(keys: torch.Tensor, vals: torch.Tensor, group=None):
 
 
 def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write_wide=False, max_labels=None,
-                     group=None, offset=None, total=None, timers=None):
+                     group=None, offset=None, total=None, timers=None, row_bytes=0):
   """Renumber this rank's slab consistently with the whole sharded volume.  Returns RenumberResult
   (keys / ids hold the GLOBAL mapping, identical on every rank).  offset / total (flat offset of the
   slab, total voxels) are exchanged once here unless the caller already knows them.
@@ -93,7 +93,7 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     k64, v64 = D.alloc(cap_pairs * 8), D.alloc(cap_pairs * 8)
     api._ev(timers, "k1", 0)
     _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
-                                    local.cap, D.ptr(local.meta), D.stream()), "frb_renumber_build")
+                                    local.cap, D.ptr(local.meta), row_bytes, D.stream()), "frb_renumber_build")
     api._ev(timers, "k1", 1)
     limits = api._narrow_limits(dtype, start, int(total))  # host work while K1 runs (cached across calls)
     api._ev(timers, "merge", 0)
@@ -181,7 +181,7 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), 0)
 
   def build_local(t):
-    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), D.stream()),
+    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), 0, D.stream()),
                "frb_hist_hash")
 
   api._run_build(build_local, local)

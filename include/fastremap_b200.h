@@ -93,9 +93,11 @@ int frb_minmax_pairs(const void* a, size_t n, int dtype, uint64_t* out, void* st
 /* ---- renumber ------------------------------------------------------------------------
  * K1 replaces the find/insert half of _renumber's loop (fastremap.pyx:236-251): for every
  * run head a[i] != a[i-1] the table receives key a[i] with value min(i + flat_offset).
- * skip_zero != 0 (preserve_zero) leaves label 0 out of the table. */
+ * skip_zero != 0 (preserve_zero) leaves label 0 out of the table.
+ * row_bytes: length in bytes of the volume's fastest axis, or 0 if unknown -- a performance hint only
+ * (the "same as the voxels directly above" filter can be aimed exactly when it is 4, 8, 12 or 16 KiB). */
 int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset, int skip_zero,
-                       void* slots, uint64_t cap, uint64_t* meta, void* stream);
+                       void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream);
 /* K2 replaces the implicit `remap_id += 1` ordering (fastremap.pyx:244-246).  Every label whose
  * table value is still a tagged first index is ranked by that index; the label with the r-th
  * smallest index gets rank meta[FRB_META_ASSIGNED] + r as its table value, and ASSIGNED advances.
@@ -161,8 +163,10 @@ int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n,
  * dense:  counts[a[i]-min] += 1 over `bins` uint64 bins (caller-zeroed), then an ordered
  *         compaction of the non-empty bins;
  * hash:   (key,count) table + sort of the distinct keys;
- * sort:   radix sort of all voxels + run-length encode. */
-int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, void* stream);
+ * sort:   radix sort of all voxels + run-length encode.
+ * row_bytes: fastest-axis length in bytes or 0 (performance hint, see frb_renumber_build). */
+int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, uint64_t row_bytes,
+                   void* stream);
 /* ordered compaction of the non-empty bins, in two steps because the caller sizes the outputs:
  * _count leaves the number of non-empty bins in meta[FRB_META_LIST_COUNT] (and per-CTA offsets in
  * ws); _emit writes label = min + bin (array dtype) and its count for every non-empty bin. */
@@ -170,7 +174,7 @@ size_t frb_compact_bins_ws_bytes(uint64_t bins);
 int frb_compact_bins_count(const uint64_t* counts, uint64_t bins, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
 int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint64_t min_bits, void* uniq_out,
                           uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream);
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream);
 size_t frb_sort_pairs_ws_bytes(size_t L);
 /* sort exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are
  * clobbered) and emit typed keys + values.  L = number of pairs, or -- count_dev != NULL -- the
@@ -210,7 +214,7 @@ int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint
  * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])
  * for the winning run start of every label.  count in meta[FRB_META_LIST_COUNT]. */
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, void* stream);
+                        uint64_t* meta, uint64_t row_bytes, void* stream);
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
                          uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream);
 
