@@ -347,8 +347,10 @@ __device__ __forceinline__ void block_add_to(u64* target, unsigned int v) {
 //              lanes, rows, tiles and CTAs: it comes out of the same staged bytes), valid iff has_prev
 //   after_tile(k) (optional) is called by every consumer warp after it has released tile number k
 //     of the CTA -- also by warps whose part of the last tile lies past the end of the array.
-//   tile_end(stage, vb) is called once per warp and tile after its rows; `stage` still holds the CTA
-//     tile (vector stream_vec(u, warp, lane) of it is what row_fn(u) saw), vb is its first vector index.
+//   tile_end(stage, vb) is called once per warp and tile after its rows.  INTERLEAVE: `stage` holds the
+//     CTA tile (vector stream_vec(u, warp, lane) of it is what row_fn(u) saw), vb is the tile's first
+//     vector index.  Contiguous rows: `stage` is the warp's own 2 KiB of the tile (vector u*32+lane),
+//     vb the index of the warp's first vector.
 //
 // REVERSE walks tiles and rows from the back (component_map keeps the LAST run start).
 // Kernels are launched with STREAM_THREADS threads; every lane of a consumer warp calls row_fn
@@ -532,6 +534,8 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   }
 
   // ---------------- consumers
+  constexpr int ROW_STRIDE = INTERLEAVE ? STREAM_WARPS * 32 : 32;  // vectors between two rows of one warp
+  const int first = stream_vec<INTERLEAVE>(0, warp, lane);
   TileIter it;
   it.template init<REVERSE>(map);
   int s = 0;
@@ -539,45 +543,90 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   for (size_t k = 0; k < ntiles; k++) {
     const size_t t = it.tile();
     it.template step<REVERSE>();
-    const size_t vb = t * STREAM_TILE_VECS;  // first vector of the CTA tile
-    mbar_wait(&full[s], round & 1u);
-    const uint4* stage = ring + (size_t)s * STREAM_STAGE_VECS + 8;
-    if (vb + STREAM_TILE_VECS <= nvec) {
-      // whole tile inside the array (all but the last tile): no per-lane bounds checks
+    if constexpr (INTERLEAVE) {
+      const size_t vb = t * STREAM_TILE_VECS;  // first vector of the CTA tile
+      mbar_wait(&full[s], round & 1u);
+      const uint4* stage = ring + (size_t)s * STREAM_STAGE_VECS + 8;
+      const uint4* mine = stage + first;       // this lane's vector of row 0; row u is u * ROW_STRIDE further
+      const size_t vfirst = vb + first;
+      if (vb + STREAM_TILE_VECS <= nvec) {
+        // whole tile inside the array (all but the last tile): no per-lane bounds checks
 #pragma unroll
-      for (int uu = 0; uu < R; uu++) {
-        const int u = REVERSE ? R - 1 - uu : uu;
-        const int off = stream_vec<INTERLEAVE>(u, warp, lane);
-        const uint4 cur = stage[off];
-        u64 prev = 0;
-        bool has_prev = false;
-        if (NEED_PREV) {
-          has_prev = (vb + off) != 0;
-          if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(stage + off) - 1);
-        }
-        row_fn(u, cur, true, (vb + off) * V, prev, has_prev);
-      }
-      tile_end(stage, vb);
-    } else if (vb + (size_t)stream_vec<INTERLEAVE>(0, warp, 0) < nvec) {  // the warp's first row starts inside the array
-#pragma unroll
-      for (int uu = 0; uu < R; uu++) {
-        const int u = REVERSE ? R - 1 - uu : uu;
-        const int off = stream_vec<INTERLEAVE>(u, warp, lane);
-        const size_t vi = vb + off;
-        const bool valid = vi < nvec;
-        uint4 cur = make_uint4(0, 0, 0, 0);
-        u64 prev = 0;
-        bool has_prev = false;
-        if (valid) {
-          cur = stage[off];
-          if (NEED_PREV && vi > 0) {
-            prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(stage + off) - 1);  // element in front
-            has_prev = true;
+        for (int uu = 0; uu < R; uu++) {
+          const int u = REVERSE ? R - 1 - uu : uu;
+          const uint4 cur = mine[u * ROW_STRIDE];
+          u64 prev = 0;
+          bool has_prev = false;
+          if (NEED_PREV) {
+            has_prev = (vfirst + u * ROW_STRIDE) != 0;
+            if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(mine + u * ROW_STRIDE) - 1);
           }
+          row_fn(u, cur, true, (vfirst + u * ROW_STRIDE) * V, prev, has_prev);
         }
-        row_fn(u, cur, valid, vi * V, prev, has_prev);
+        tile_end(stage, vb);
+      } else if (vb + (size_t)stream_vec<INTERLEAVE>(0, warp, 0) < nvec) {  // the warp's first row starts inside the array
+#pragma unroll
+        for (int uu = 0; uu < R; uu++) {
+          const int u = REVERSE ? R - 1 - uu : uu;
+          const size_t vi = vfirst + u * ROW_STRIDE;
+          const bool valid = vi < nvec;
+          uint4 cur = make_uint4(0, 0, 0, 0);
+          u64 prev = 0;
+          bool has_prev = false;
+          if (valid) {
+            cur = mine[u * ROW_STRIDE];
+            if (NEED_PREV && vi > 0) {
+              prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(mine + u * ROW_STRIDE) - 1);  // element in front
+              has_prev = true;
+            }
+          }
+          row_fn(u, cur, valid, vi * V, prev, has_prev);
+        }
+        tile_end(stage, vb);
       }
-      tile_end(stage, vb);
+    } else {
+      // contiguous rows: tile_end gets the WARP's part of the stage and its first vector index
+      // (kept as it was before the interleaved mode existed: K3 is 5 % slower through the other body)
+      const size_t vb = t * STREAM_TILE_VECS + (size_t)warp * (R * 32);
+      mbar_wait(&full[s], round & 1u);
+      const uint4* wstage = ring + (size_t)s * STREAM_STAGE_VECS + 8 + (size_t)warp * (R * 32);
+      if (vb + R * 32 <= nvec) {
+        // whole warp-tile inside the array (all but the last tile): no per-lane bounds checks
+#pragma unroll
+        for (int uu = 0; uu < R; uu++) {
+          const int u = REVERSE ? R - 1 - uu : uu;
+          const int off = u * 32 + lane;
+          const uint4 cur = wstage[off];
+          u64 prev = 0;
+          bool has_prev = false;
+          if (NEED_PREV) {
+            has_prev = (vb + off) != 0;
+            if (has_prev) prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);
+          }
+          row_fn(u, cur, true, (vb + off) * V, prev, has_prev);
+        }
+        tile_end(wstage, vb);
+      } else if (vb < nvec) {
+#pragma unroll
+        for (int uu = 0; uu < R; uu++) {
+          const int u = REVERSE ? R - 1 - uu : uu;
+          const int off = u * 32 + lane;
+          const size_t vi = vb + off;
+          const bool valid = vi < nvec;
+          uint4 cur = make_uint4(0, 0, 0, 0);
+          u64 prev = 0;
+          bool has_prev = false;
+          if (valid) {
+            cur = wstage[off];
+            if (NEED_PREV && vi > 0) {
+              prev = (u64)*(reinterpret_cast<const typename UIntOf<W>::type*>(wstage + off) - 1);  // element in front
+              has_prev = true;
+            }
+          }
+          row_fn(u, cur, valid, vi * V, prev, has_prev);
+        }
+        tile_end(wstage, vb);
+      }
     }
     __syncwarp();  // every lane of this warp is done with the stage
     if (lane == 0) mbar_arrive(&empty[s]);

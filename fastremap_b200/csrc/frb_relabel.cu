@@ -170,7 +170,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
   constexpr int R = STREAM_ROWS;
   static_assert(W >= 4 && R % NB == 0, "hashed tables only");
   const size_t nvec = n / V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
   auto tile_end = [&](const uint4* stage, size_t vb) {
 #pragma unroll
@@ -181,8 +181,8 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 #pragma unroll
       for (int q = 0; q < NB; q++) {
         const int u = u0 + q;
-        valid[q] = vb + stream_vec<false>(u, warp, lane) < nvec;
-        const uint4 cur = valid[q] ? stage[stream_vec<false>(u, warp, lane)] : make_uint4(0, 0, 0, 0);
+        valid[q] = vb + (u * 32 + lane) < nvec;
+        const uint4 cur = valid[q] ? stage[(u * 32 + lane)] : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < V; j++) {
           key[q][j] = vec_get<W>(cur, j);
@@ -195,7 +195,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 #pragma unroll
       for (int q = 0; q < NB; q++) {
         if (!valid[q]) continue;
-        const size_t i0 = (vb + stream_vec<false>(u0 + q, warp, lane)) * V;
+        const size_t i0 = (vb + ((u0 + q) * 32 + lane)) * V;
         u64 r[V];
 #pragma unroll
         for (int j = 0; j < V; j++) r[j] = relabel_one<true>(A, key[q][j], h[q][j], first[q][j], i0 + j);
