@@ -170,7 +170,7 @@ def _export_pairs(table):
   return k64[: nl * 8].view(torch.int64), v64[: nl * 8].view(torch.int64)
 
 
-def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
+def unique_sharded(buf, n_local, dtype, max_labels=None, group=None, row_bytes=0):
   """unique(return_counts=True) of the whole sharded volume, replicated on every rank.
   Returns (uniq_buf, counts_buf, n_unique) like api.unique_counts_device."""
   from . import _lib
@@ -181,7 +181,7 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), 0)
 
   def build_local(t):
-    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), 0, D.stream()),
+    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), row_bytes, D.stream()),
                "frb_hist_hash")
 
   api._run_build(build_local, local)
@@ -205,7 +205,7 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None):
   return uniq, cts, nu
 
 
-def component_map_sharded(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=None, group=None):
+def component_map_sharded(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=None, group=None, row_bytes=0):
   """component_map of the whole sharded pair of volumes, replicated on every rank.
   Returns (keys_buf, parents_buf, n_labels), unordered, like api.component_map_device."""
   from . import _lib
@@ -213,7 +213,8 @@ def component_map_sharded(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, m
   from . import device as D
   L = _lib.load()
   cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
-  keys_l, pars_l, nl = api.component_map_device(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=max_labels)
+  keys_l, pars_l, nl = api.component_map_device(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=max_labels,
+                                                row_bytes=row_bytes)
   # widen the raw bit patterns to 64 bits for the exchange
   ucc, upar = np.dtype("u%d" % cc_dtype.itemsize), np.dtype("u%d" % parent_dtype.itemsize)
   k64 = api._cast(keys_l, ucc, np.uint64, nl)[: nl * 8].view(torch.int64)
