@@ -33,9 +33,10 @@ __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct
 // value offered for element i is bias + i.  HEADS: only run starts (a[i] != a[i-1]) are offered.
 // DU: which of the lane's row slots holds the row directly above / below (rows_up; compile-time, the
 // selection must not cost instructions: this loop is issue-bound)
-template <int W, int OP, bool REVERSE, bool HEADS, int DU>
+template <int W, int OP, bool REVERSE, bool HEADS, int DU, bool VAR_TILE>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
-                                           Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run) {
+                                           Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run,
+                                           int tile_vecs) {
   constexpr int V = 16 / W;
   typedef typename UIntOf<W>::type T;
   __shared__ u64 s_seen[8][BUILD_CACHE];
@@ -171,8 +172,8 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     }
   };
 
-  const TileMap map(nvec, (size_t)run);
-  stream_rows<W, REVERSE, true, true>(a, nvec, map, row_fn, tile_end);
+  const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+  stream_rows<W, REVERSE, true, true, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
   resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);
 }

@@ -398,8 +398,10 @@ struct TileMap {
   size_t tiles;   // tiles in the whole array
   size_t run;     // consecutive tiles per run
   size_t count;   // tiles owned by this CTA
-  __device__ __forceinline__ TileMap(size_t nvec, size_t run_) {
-    tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
+  size_t tv;      // vectors per tile: STREAM_TILE_VECS, or less when a tile is a whole number of volume rows
+  __device__ __forceinline__ TileMap(size_t nvec, size_t run_, size_t tile_vecs = STREAM_TILE_VECS) {
+    tv = tile_vecs < 32 || tile_vecs > (size_t)STREAM_TILE_VECS ? (size_t)STREAM_TILE_VECS : tile_vecs;
+    tiles = (nvec + tv - 1) / tv;
     run = run_ < 1 ? 1 : run_;
     const size_t nruns = (tiles + run - 1) / run;
     const size_t b = blockIdx.x, g = gridDim.x;
@@ -488,7 +490,9 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // INTERLEAVE: see stream_vec.  Kernels that write the volume back (K3) keep a warp's rows contiguous:
 // measured, interleaving costs them 8 % (stores of one warp 4 KiB apart), while the kernels that only
 // read gain from the vertical alignment of a lane's rows.
-template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn, typename AfterTileFn>
+// VAR_TILE: the tile length is map.tv (a whole number of volume rows) instead of the constant 16 KiB; a
+// template flag because the constant folds into shifts in loops that are issue-bound (K1 + 18 % otherwise).
+template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, bool VAR_TILE, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
@@ -500,6 +504,7 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   u64* full = reinterpret_cast<u64*>(frb_dyn_smem + (size_t)S * STREAM_STAGE_VECS * 16);
   u64* empty = full + S;
   const size_t ntiles = map.count;
+  const size_t TV = VAR_TILE ? map.tv : (size_t)STREAM_TILE_VECS;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -518,9 +523,9 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
       uint32_t round = 0;
       for (size_t k = 0; k < ntiles; k++) {
         if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);  // all 8 warps released the previous fill
-        const size_t vb = it.tile() * STREAM_TILE_VECS;
+        const size_t vb = it.tile() * TV;
         it.template step<REVERSE>();
-        size_t nv = nvec - vb < (size_t)STREAM_TILE_VECS ? nvec - vb : (size_t)STREAM_TILE_VECS;
+        size_t nv = nvec - vb < TV ? nvec - vb : TV;
         uint4* dst = ring + (size_t)s * STREAM_STAGE_VECS + 8;
         const uint4* src = a + vb;
         if (NEED_PREV && vb > 0) { dst -= 1; src -= 1; nv += 1; }
@@ -544,12 +549,12 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     const size_t t = it.tile();
     it.template step<REVERSE>();
     if constexpr (INTERLEAVE) {
-      const size_t vb = t * STREAM_TILE_VECS;  // first vector of the CTA tile
+      const size_t vb = t * TV;                // first vector of the CTA tile
       mbar_wait(&full[s], round & 1u);
       const uint4* stage = ring + (size_t)s * STREAM_STAGE_VECS + 8;
       const uint4* mine = stage + first;       // this lane's vector of row 0; row u is u * ROW_STRIDE further
       const size_t vfirst = vb + first;
-      if (vb + STREAM_TILE_VECS <= nvec) {
+      if (!VAR_TILE && vb + STREAM_TILE_VECS <= nvec) {
         // whole tile inside the array (all but the last tile): no per-lane bounds checks
 #pragma unroll
         for (int uu = 0; uu < R; uu++) {
@@ -564,12 +569,12 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
           row_fn(u, cur, true, (vfirst + u * ROW_STRIDE) * V, prev, has_prev);
         }
         tile_end(stage, vb);
-      } else if (vb + (size_t)stream_vec<INTERLEAVE>(0, warp, 0) < nvec) {  // the warp's first row starts inside the array
+      } else if ((size_t)(warp * 32) < TV && vb + (size_t)(warp * 32) < nvec) {  // the warp's first row starts inside the tile and the array
 #pragma unroll
         for (int uu = 0; uu < R; uu++) {
           const int u = REVERSE ? R - 1 - uu : uu;
           const size_t vi = vfirst + u * ROW_STRIDE;
-          const bool valid = vi < nvec;
+          const bool valid = (size_t)(first + u * ROW_STRIDE) < TV && vi < nvec;
           uint4 cur = make_uint4(0, 0, 0, 0);
           u64 prev = 0;
           bool has_prev = false;
@@ -634,15 +639,30 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
+template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn, typename AfterTileFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+                                            TileEndFn tile_end, AfterTileFn after_tile) {
+  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE, false>(a, nvec, map, row_fn, tile_end, after_tile);
+}
 template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end) {
-  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }
 // barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }
 
 // host side: tiles in an n-element array (+1 so that the CTA owning the scalar tail exists)
+// Vectors per tile for the kernels with interleaved rows.  A fastest axis that is not a multiple of
+// 4 KiB cannot be aligned with the row slots (rows_up), but if a tile is a whole number of rows, "same
+// position, previous tile" is again a fixed number of rows up -- 16 000-byte tiles for 1000-wide
+// uint64 volumes instead of 16 384 (a few idle lanes per tile) bring K1 back from 3.8 to ~1.5 ms.
+inline int stream_tile_vecs(size_t row_bytes) {
+  if (row_bytes == 0 || (row_bytes % 16) != 0 || (row_bytes % 4096) == 0) return STREAM_TILE_VECS;
+  const size_t rv = row_bytes / 16;
+  if (rv > (size_t)STREAM_TILE_VECS) return STREAM_TILE_VECS;
+  return (int)((STREAM_TILE_VECS / rv) * rv);
+}
 inline size_t stream_tiles(size_t n, int w) { return (n / (16 / w) + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1; }
 int tile_run();  // tuning knob (frb_runtime.cu): consecutive tiles per CTA run
 // Run length for a launch of `grid` CTAs over `tiles` tiles: short arrays (label tables, pipeline

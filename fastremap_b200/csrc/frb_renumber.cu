@@ -96,11 +96,11 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 // ------------------------------------------------------------------------------------------ K1
 // First-index pass: the table receives, for every label, the minimum flat index at which it occurs
 // (tagged: see FRB_RANK_TAG).  The filtered build pass is shared with K7: frb_build.cuh.
-template <int W, int DU>
+template <int W, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
-                 u64 mask, int direct, u64* __restrict__ meta, int run) {
-  build_pass<W, FRB_OP_MIN, false, false, DU>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run);
+                 u64 mask, int direct, u64* __restrict__ meta, int run, int tile_vecs) {
+  build_pass<W, FRB_OP_MIN, false, false, DU, VAR_TILE>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run, tile_vecs);
 }
 
 // ------------------------------------------------------------------------------------------ probes
@@ -181,9 +181,12 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
   const int du = rows_up((size_t)row_bytes);
-#define FRB_K1(WW, DD) k_renumber_build<WW, DD><<<stream_grid(k_renumber_build<WW, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, DD>, tiles), tiles))
-#define FRB_K1_DU(WW) switch (du) { case 1: FRB_K1(WW, 1); break; case 2: FRB_K1(WW, 2); break; case 3: FRB_K1(WW, 3); break; default: FRB_K1(WW, 4); break; }
+  const int tv = stream_tile_vecs((size_t)row_bytes);
+#define FRB_K1(WW, DD, VV) k_renumber_build<WW, DD, VV><<<stream_grid(k_renumber_build<WW, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, DD, VV>, tiles), tiles), tv)
+#define FRB_K1_DU(WW)                                                                                             \
+  if (tv != STREAM_TILE_VECS) { FRB_K1(WW, 4, true); }                                                            \
+  else switch (du) { case 1: FRB_K1(WW, 1, false); break; case 2: FRB_K1(WW, 2, false); break; case 3: FRB_K1(WW, 3, false); break; default: FRB_K1(WW, 4, false); break; }
   switch (w) {
     case 1: FRB_K1_DU(1) break;
     case 2: FRB_K1_DU(2) break;

@@ -68,8 +68,9 @@ static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its
 template <int DU>
 __device__ __forceinline__ constexpr int hist_slot(int u) { return DU == 1 ? 0 : DU == 2 ? (u & 1) : DU == 3 ? (u == 3 ? 0 : u) : u; }
 
-template <int W, typename Sink, int DU>
-__global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run) {
+template <int W, typename Sink, int DU, bool VAR_TILE>
+__global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run,
+                                                            int tile_vecs) {
   constexpr int V = 16 / W;
   __shared__ u64 s_key[HIST_CACHE];
   __shared__ unsigned int s_cnt[HIST_CACHE];
@@ -177,8 +178,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
     }
   };
 
-  const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, true>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+  stream_rows<W, false, false, true, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
   if (consumer) {
 #pragma unroll
     for (int u = 0; u < STREAM_ROWS; u++)
@@ -462,9 +463,12 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   const int du = rows_up((size_t)row_bytes);
-#define FRB_KH(WW, DD) k_hist<WW, DenseSink, DD><<<stream_grid(k_hist<WW, DenseSink, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, DD>, tiles), tiles))
-#define FRB_KH_DU(WW) switch (du) { case 1: FRB_KH(WW, 1); break; case 2: FRB_KH(WW, 2); break; case 3: FRB_KH(WW, 3); break; default: FRB_KH(WW, 4); break; }
+  const int tv = stream_tile_vecs((size_t)row_bytes);
+#define FRB_KH(WW, DD, VV) k_hist<WW, DenseSink, DD, VV><<<stream_grid(k_hist<WW, DenseSink, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, DD, VV>, tiles), tiles), tv)
+#define FRB_KH_DU(WW)                                                                                             \
+  if (tv != STREAM_TILE_VECS) { FRB_KH(WW, 4, true); }                                                            \
+  else switch (du) { case 1: FRB_KH(WW, 1, false); break; case 2: FRB_KH(WW, 2, false); break; case 3: FRB_KH(WW, 3, false); break; default: FRB_KH(WW, 4, false); break; }
   switch (w) {
     case 1: FRB_KH_DU(1) break;
     case 2: FRB_KH_DU(2) break;
@@ -491,9 +495,12 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   const uint4* p = (const uint4*)a;
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
   const int du = rows_up((size_t)row_bytes);
-#define FRB_KH(WW, DD) k_hist<WW, HashSink, DD><<<stream_grid(k_hist<WW, HashSink, DD>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, DD>, tiles), tiles))
-#define FRB_KH_DU(WW) switch (du) { case 1: FRB_KH(WW, 1); break; case 2: FRB_KH(WW, 2); break; case 3: FRB_KH(WW, 3); break; default: FRB_KH(WW, 4); break; }
+  const int tv = stream_tile_vecs((size_t)row_bytes);
+#define FRB_KH(WW, DD, VV) k_hist<WW, HashSink, DD, VV><<<stream_grid(k_hist<WW, HashSink, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, DD, VV>, tiles), tiles), tv)
+#define FRB_KH_DU(WW)                                                                                             \
+  if (tv != STREAM_TILE_VECS) { FRB_KH(WW, 4, true); }                                                            \
+  else switch (du) { case 1: FRB_KH(WW, 1, false); break; case 2: FRB_KH(WW, 2, false); break; case 3: FRB_KH(WW, 3, false); break; default: FRB_KH(WW, 4, false); break; }
   switch (w) {
     case 1: FRB_KH_DU(1) break;
     case 2: FRB_KH_DU(2) break;
