@@ -31,9 +31,10 @@ __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct
 }
 
 // value offered for element i is bias + i.  HEADS: only run starts (a[i] != a[i-1]) are offered.
-// DU: which of the lane's row slots holds the row directly above / below (rows_up; compile-time, the
-// selection must not cost instructions: this loop is issue-bound)
-template <int W, int OP, bool REVERSE, bool HEADS, int DU, bool VAR_TILE>
+// IL / DU: how a warp's rows are laid out in the tile and which of the lane's row slots holds the row
+// directly above / below (row_geom; compile-time: the selection must not cost instructions, this loop
+// is issue-bound)
+template <int W, int OP, bool REVERSE, bool HEADS, int IL, int DU, bool VAR_TILE>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run,
                                            int tile_vecs) {
@@ -130,7 +131,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     for (u64 m = cand; m; m &= m - 1) {
       const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
       const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec(u, warp, lane))[j];
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec<IL>(u, warp, lane))[j];
       const bool hit = key != FRB_EMPTY && s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] == key;
       if (!hit) todo |= 1ull << b;
     }
@@ -140,9 +141,9 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     for (u64 m = todo; m; m &= m - 1) {
       const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
       const unsigned int u = b / V, j = b % V;
-      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec(u, warp, lane))[j];
+      const u64 key = (u64)reinterpret_cast<const T*>(stage + stream_vec<IL>(u, warp, lane))[j];
       const u64 h = hash_key(key);
-      const u64 val = bias + (u64)((vb + stream_vec(u, warp, lane)) * V + j);
+      const u64 val = bias + (u64)((vb + stream_vec<IL>(u, warp, lane)) * V + j);
       s_seen[warp][(h >> 48) & (BUILD_CACHE - 1)] = key;
       if (!pend && key != FRB_EMPTY) {
         pend = true;
@@ -173,7 +174,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   };
 
   const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
-  stream_rows<W, REVERSE, true, true, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
   resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);
 }

@@ -374,9 +374,14 @@ static constexpr int STREAM_SMEM_BYTES = STREAM_STAGES * STREAM_STAGE_VECS * 16 
 // so a warp's rows are 4 KiB apart: for volumes whose fastest axis is a multiple of 4 KiB long, a
 // lane meets the voxels directly above / below its previous row one or two rows later -- what the
 // "same as the row above" filters of the build and counting kernels feed on.
-template <bool INTERLEAVE = true>
+// IL = how many 512-byte chunks apart the rows of one warp are: 8 (all warps interleaved, rows 4 KiB
+// apart), 4 / 2 / 1 (groups of IL warps interleaved: rows 2 KiB / 1 KiB / 512 B apart, for volumes with
+// rows that short), 0 = contiguous rows with the legacy consumer body (kernels that write the volume).
+template <int IL>
 __device__ __forceinline__ int stream_vec(int u, int warp, int lane) {
-  return INTERLEAVE ? (u * STREAM_WARPS + warp) * 32 + lane : (warp * STREAM_ROWS + u) * 32 + lane;
+  if (IL == 0) return (warp * STREAM_ROWS + u) * 32 + lane;
+  if (IL == STREAM_WARPS) return (u * STREAM_WARPS + warp) * 32 + lane;  // one group: spelled out, the general form costs K1 14 %
+  return ((warp / IL) * (STREAM_ROWS * IL) + (warp % IL) + u * IL) * 32 + lane;
 }
 
 // A lane remembers the last vector it saw in each of its 4 row slots.  For a volume whose fastest
@@ -385,10 +390,22 @@ __device__ __forceinline__ int stream_vec(int u, int warp, int lane) {
 // one.  DU = q, or 4 when the row length is unknown / no such slot exists ("same position, previous
 // tile": a row or two further up for typical volumes -- still a good predictor, just a weaker one).
 // DU is a template parameter of the kernels: selecting the slot at run time cost K1 30 %.
-inline int rows_up(size_t row_bytes) {
-  if (row_bytes == 0 || (row_bytes % 4096) != 0) return 4;
-  const size_t q = row_bytes / 4096;
-  return q >= 1 && q <= 4 ? (int)q : 4;
+struct RowGeom {
+  int il;  // chunk distance between the rows of a warp (stream_vec)
+  int du;  // row slot distance to the voxels directly above (ref_slot_ct)
+  int tv;  // vectors per tile
+};
+inline RowGeom row_geom(size_t row_bytes) {
+  RowGeom g = {8, 4, 1024};
+  if (row_bytes == 0 || (row_bytes % 16) != 0) return g;  // unknown: "same position, previous tile"
+  if ((row_bytes % 512) == 0) {
+    const size_t rc = row_bytes / 512;  // 512-byte chunks per row
+    if (rc == 1 || rc == 2 || rc == 4) { g.il = (int)rc; g.du = 1; return g; }      // short rows: a warp's rows ARE consecutive volume rows
+    if (rc == 8 || rc == 16 || rc == 24 || rc == 32) { g.du = (int)(rc / 8); return g; }  // 4 .. 16 KiB
+  }
+  const size_t rv = row_bytes / 16;
+  if (rv <= 1024) g.tv = (int)((1024 / rv) * rv);  // a whole number of rows per tile
+  return g;
 }
 template <bool REVERSE, int DU>
 __device__ __forceinline__ constexpr int ref_slot_ct(int u) {
@@ -492,7 +509,7 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // read gain from the vertical alignment of a lane's rows.
 // VAR_TILE: the tile length is map.tv (a whole number of volume rows) instead of the constant 16 KiB; a
 // template flag because the constant folds into shifts in loops that are issue-bound (K1 + 18 % otherwise).
-template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, bool VAR_TILE, typename RowFn, typename TileEndFn, typename AfterTileFn>
+template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
@@ -539,8 +556,8 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   }
 
   // ---------------- consumers
-  constexpr int ROW_STRIDE = INTERLEAVE ? STREAM_WARPS * 32 : 32;  // vectors between two rows of one warp
-  const int first = stream_vec<INTERLEAVE>(0, warp, lane);
+  constexpr int ROW_STRIDE = IL ? IL * 32 : 32;  // vectors between two rows of one warp
+  const int first = stream_vec<IL>(0, warp, lane);
   TileIter it;
   it.template init<REVERSE>(map);
   int s = 0;
@@ -548,7 +565,7 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   for (size_t k = 0; k < ntiles; k++) {
     const size_t t = it.tile();
     it.template step<REVERSE>();
-    if constexpr (INTERLEAVE) {
+    if constexpr (IL != 0) {
       const size_t vb = t * TV;                // first vector of the CTA tile
       mbar_wait(&full[s], round & 1u);
       const uint4* stage = ring + (size_t)s * STREAM_STAGE_VECS + 8;
@@ -569,7 +586,7 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
           row_fn(u, cur, true, (vfirst + u * ROW_STRIDE) * V, prev, has_prev);
         }
         tile_end(stage, vb);
-      } else if ((size_t)(warp * 32) < TV && vb + (size_t)(warp * 32) < nvec) {  // the warp's first row starts inside the tile and the array
+      } else if ((size_t)stream_vec<IL>(0, warp, 0) < TV && vb + (size_t)stream_vec<IL>(0, warp, 0) < nvec) {  // the warp's first row starts inside the tile and the array
 #pragma unroll
         for (int uu = 0; uu < R; uu++) {
           const int u = REVERSE ? R - 1 - uu : uu;
@@ -639,30 +656,20 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
-template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn, typename AfterTileFn>
+template <int W, bool REVERSE, bool NEED_PREV, int IL, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
-  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE, false>(a, nvec, map, row_fn, tile_end, after_tile);
+  stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, after_tile);
 }
-template <int W, bool REVERSE, bool NEED_PREV, bool INTERLEAVE, typename RowFn, typename TileEndFn>
+template <int W, bool REVERSE, bool NEED_PREV, int IL, typename RowFn, typename TileEndFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
                                             TileEndFn tile_end) {
-  stream_rows<W, REVERSE, NEED_PREV, INTERLEAVE, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }
 // barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }
 
 // host side: tiles in an n-element array (+1 so that the CTA owning the scalar tail exists)
-// Vectors per tile for the kernels with interleaved rows.  A fastest axis that is not a multiple of
-// 4 KiB cannot be aligned with the row slots (rows_up), but if a tile is a whole number of rows, "same
-// position, previous tile" is again a fixed number of rows up -- 16 000-byte tiles for 1000-wide
-// uint64 volumes instead of 16 384 (a few idle lanes per tile) bring K1 back from 3.8 to ~1.5 ms.
-inline int stream_tile_vecs(size_t row_bytes) {
-  if (row_bytes == 0 || (row_bytes % 16) != 0 || (row_bytes % 4096) == 0) return STREAM_TILE_VECS;
-  const size_t rv = row_bytes / 16;
-  if (rv > (size_t)STREAM_TILE_VECS) return STREAM_TILE_VECS;
-  return (int)((STREAM_TILE_VECS / rv) * rv);
-}
 inline size_t stream_tiles(size_t n, int w) { return (n / (16 / w) + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1; }
 int tile_run();  // tuning knob (frb_runtime.cu): consecutive tiles per CTA run
 // Run length for a launch of `grid` CTAs over `tiles` tiles: short arrays (label tables, pipeline

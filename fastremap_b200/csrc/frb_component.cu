@@ -12,11 +12,11 @@
 
 namespace frb {
 
-template <int W, int DU, bool VAR_TILE>
+template <int W, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
                   u64* __restrict__ meta, int run, int tile_vecs) {
-  build_pass<W, FRB_OP_MAX, true, true, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs);
+  build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs);
 }
 
 // gather: scan the table (frb_scan.cuh) and emit (label, parent[winning run start]) for every label
@@ -111,20 +111,26 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   const uint4* p = (const uint4*)cc;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
-  const int du = rows_up((size_t)row_bytes);
-  const int tv = stream_tile_vecs((size_t)row_bytes);
-#define FRB_K7(WW, DD, VV) k_component_build<WW, DD, VV><<<stream_grid(k_component_build<WW, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, DD, VV>, tiles), tiles), tv)
-#define FRB_K7_DU(WW)                                                                                             \
-  if (tv != STREAM_TILE_VECS) { FRB_K7(WW, 4, true); }                                                            \
-  else switch (du) { case 1: FRB_K7(WW, 1, false); break; case 2: FRB_K7(WW, 2, false); break; case 3: FRB_K7(WW, 3, false); break; default: FRB_K7(WW, 4, false); break; }
+  const RowGeom geo = row_geom((size_t)row_bytes);
+  const int tv = geo.tv;
+#define FRB_K7(WW, II, DD, VV) k_component_build<WW, II, DD, VV><<<stream_grid(k_component_build<WW, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, II, DD, VV>, tiles), tiles), tv)
+#define FRB_K7_GEO(WW)                                                        \
+  if (geo.tv != STREAM_TILE_VECS) { FRB_K7(WW, 8, 4, true); }                 \
+  else if (geo.il == 4) { FRB_K7(WW, 4, 1, false); }                          \
+  else if (geo.il == 2) { FRB_K7(WW, 2, 1, false); }                          \
+  else if (geo.il == 1) { FRB_K7(WW, 1, 1, false); }                          \
+  else if (geo.du == 1) { FRB_K7(WW, 8, 1, false); }                          \
+  else if (geo.du == 2) { FRB_K7(WW, 8, 2, false); }                          \
+  else if (geo.du == 3) { FRB_K7(WW, 8, 3, false); }                          \
+  else { FRB_K7(WW, 8, 4, false); }
   switch (w) {
-    case 1: FRB_K7_DU(1) break;
-    case 2: FRB_K7_DU(2) break;
-    case 4: FRB_K7_DU(4) break;
-    default: FRB_K7_DU(8) break;
+    case 1: FRB_K7_GEO(1) break;
+    case 2: FRB_K7_GEO(2) break;
+    case 4: FRB_K7_GEO(4) break;
+    default: FRB_K7_GEO(8) break;
   }
-#undef FRB_K7_DU
+#undef FRB_K7_GEO
 #undef FRB_K7
   return check_launch("k_component_build");
 }

@@ -98,7 +98,7 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
     if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, false>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<W, false, false, 0>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
@@ -145,7 +145,7 @@ k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, Rel
     if (W > 4 && wo == 4) store_results<V, (W > 4 ? 4 : 1)>(dst_narrow, i0, r);
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, false>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<W, false, false, 0>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
@@ -204,7 +204,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
     }
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, false, false>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
+  stream_rows<W, false, false, 0>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {

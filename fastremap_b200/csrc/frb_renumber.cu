@@ -48,7 +48,7 @@ k_minmax_pairs(const uint4* __restrict__ a, size_t n, u64* __restrict__ out, int
     }
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<W, false, true, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<W, false, true, 0>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
     for (size_t i = nvec * V; i < n; i++) {
@@ -96,11 +96,11 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 // ------------------------------------------------------------------------------------------ K1
 // First-index pass: the table receives, for every label, the minimum flat index at which it occurs
 // (tagged: see FRB_RANK_TAG).  The filtered build pass is shared with K7: frb_build.cuh.
-template <int W, int DU, bool VAR_TILE>
+template <int W, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
                  u64 mask, int direct, u64* __restrict__ meta, int run, int tile_vecs) {
-  build_pass<W, FRB_OP_MIN, false, false, DU, VAR_TILE>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run, tile_vecs);
+  build_pass<W, FRB_OP_MIN, false, false, IL, DU, VAR_TILE>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run, tile_vecs);
 }
 
 // ------------------------------------------------------------------------------------------ probes
@@ -117,7 +117,7 @@ k_stream_probe(const uint4* __restrict__ a, size_t nvec, void* wide, void* narro
     if (mode >= 2) st_stream8((char*)narrow + i0 * 4, make_uint2(cur.x, cur.z));
   };
   const TileMap map(nvec, (size_t)run);
-  stream_rows<8, false, PREV, false>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
+  stream_rows<8, false, PREV, 0>(a, nvec, map, row_fn, [](const uint4*, size_t) {});
   acc = __reduce_xor_sync(FRB_FULL_MASK, acc);
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
 }
@@ -180,20 +180,26 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   const uint4* p = (const uint4*)a;
   Slot* s = (Slot*)slots;
   u64* m = (u64*)meta;
-  const int du = rows_up((size_t)row_bytes);
-  const int tv = stream_tile_vecs((size_t)row_bytes);
-#define FRB_K1(WW, DD, VV) k_renumber_build<WW, DD, VV><<<stream_grid(k_renumber_build<WW, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, DD, VV>, tiles), tiles), tv)
-#define FRB_K1_DU(WW)                                                                                             \
-  if (tv != STREAM_TILE_VECS) { FRB_K1(WW, 4, true); }                                                            \
-  else switch (du) { case 1: FRB_K1(WW, 1, false); break; case 2: FRB_K1(WW, 2, false); break; case 3: FRB_K1(WW, 3, false); break; default: FRB_K1(WW, 4, false); break; }
+  const RowGeom geo = row_geom((size_t)row_bytes);
+  const int tv = geo.tv;
+#define FRB_K1(WW, II, DD, VV) k_renumber_build<WW, II, DD, VV><<<stream_grid(k_renumber_build<WW, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, II, DD, VV>, tiles), tiles), tv)
+#define FRB_K1_GEO(WW)                                                        \
+  if (geo.tv != STREAM_TILE_VECS) { FRB_K1(WW, 8, 4, true); }                 \
+  else if (geo.il == 4) { FRB_K1(WW, 4, 1, false); }                          \
+  else if (geo.il == 2) { FRB_K1(WW, 2, 1, false); }                          \
+  else if (geo.il == 1) { FRB_K1(WW, 1, 1, false); }                          \
+  else if (geo.du == 1) { FRB_K1(WW, 8, 1, false); }                          \
+  else if (geo.du == 2) { FRB_K1(WW, 8, 2, false); }                          \
+  else if (geo.du == 3) { FRB_K1(WW, 8, 3, false); }                          \
+  else { FRB_K1(WW, 8, 4, false); }
   switch (w) {
-    case 1: FRB_K1_DU(1) break;
-    case 2: FRB_K1_DU(2) break;
-    case 4: FRB_K1_DU(4) break;
-    default: FRB_K1_DU(8) break;
+    case 1: FRB_K1_GEO(1) break;
+    case 2: FRB_K1_GEO(2) break;
+    case 4: FRB_K1_GEO(4) break;
+    default: FRB_K1_GEO(8) break;
   }
-#undef FRB_K1_DU
+#undef FRB_K1_GEO
 #undef FRB_K1
   return check_launch("k_renumber_build");
 }

@@ -59,7 +59,7 @@ k_table_scan(const uint4* __restrict__ slots, u64 cap, u64* counter, u64 capacit
     else consumer_bar();                                 // nobody may stage the next tile before everyone has read s_count
   };
   const TileMap map((size_t)cap, (size_t)run);
-  stream_rows<8, false, false, false>(slots, (size_t)cap, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  stream_rows<8, false, false, 0>(slots, (size_t)cap, map, row_fn, [](const uint4*, size_t) {}, after_tile);
   if (warp < STREAM_WARPS) {
     consumer_bar();
     flush();

@@ -68,7 +68,7 @@ static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its
 template <int DU>
 __device__ __forceinline__ constexpr int hist_slot(int u) { return DU == 1 ? 0 : DU == 2 ? (u & 1) : DU == 3 ? (u == 3 ? 0 : u) : u; }
 
-template <int W, typename Sink, int DU, bool VAR_TILE>
+template <int W, typename Sink, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run,
                                                             int tile_vecs) {
   constexpr int V = 16 / W;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
   };
 
   const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
-  stream_rows<W, false, false, true, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
   if (consumer) {
 #pragma unroll
     for (int u = 0; u < STREAM_ROWS; u++)
@@ -462,21 +462,20 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
-  const int du = rows_up((size_t)row_bytes);
-  const int tv = stream_tile_vecs((size_t)row_bytes);
-#define FRB_KH(WW, DD, VV) k_hist<WW, DenseSink, DD, VV><<<stream_grid(k_hist<WW, DenseSink, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, DD, VV>, tiles), tiles), tv)
-#define FRB_KH_DU(WW)                                                                                             \
-  if (tv != STREAM_TILE_VECS) { FRB_KH(WW, 4, true); }                                                            \
-  else switch (du) { case 1: FRB_KH(WW, 1, false); break; case 2: FRB_KH(WW, 2, false); break; case 3: FRB_KH(WW, 3, false); break; default: FRB_KH(WW, 4, false); break; }
+  // the dense strategy is only ever forced (tests, comparisons): two geometries are enough
+  const RowGeom geo = row_geom((size_t)row_bytes);
+  const int tv = geo.tv;
+#define FRB_KHD(WW, VV) k_hist<WW, DenseSink, 8, 4, VV><<<stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv)
+#define FRB_KHD_GEO(WW) if (tv != STREAM_TILE_VECS) { FRB_KHD(WW, true); } else { FRB_KHD(WW, false); }
   switch (w) {
-    case 1: FRB_KH_DU(1) break;
-    case 2: FRB_KH_DU(2) break;
-    case 4: FRB_KH_DU(4) break;
-    default: FRB_KH_DU(8) break;
+    case 1: FRB_KHD_GEO(1) break;
+    case 2: FRB_KHD_GEO(2) break;
+    case 4: FRB_KHD_GEO(4) break;
+    default: FRB_KHD_GEO(8) break;
   }
-#undef FRB_KH_DU
-#undef FRB_KH
+#undef FRB_KHD_GEO
+#undef FRB_KHD
   return check_launch("k_hist<dense>");
 }
 
@@ -494,20 +493,26 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
-  const int du = rows_up((size_t)row_bytes);
-  const int tv = stream_tile_vecs((size_t)row_bytes);
-#define FRB_KH(WW, DD, VV) k_hist<WW, HashSink, DD, VV><<<stream_grid(k_hist<WW, HashSink, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, DD, VV>, tiles), tiles), tv)
-#define FRB_KH_DU(WW)                                                                                             \
-  if (tv != STREAM_TILE_VECS) { FRB_KH(WW, 4, true); }                                                            \
-  else switch (du) { case 1: FRB_KH(WW, 1, false); break; case 2: FRB_KH(WW, 2, false); break; case 3: FRB_KH(WW, 3, false); break; default: FRB_KH(WW, 4, false); break; }
+  const RowGeom geo = row_geom((size_t)row_bytes);
+  const int tv = geo.tv;
+#define FRB_KH(WW, II, DD, VV) k_hist<WW, HashSink, II, DD, VV><<<stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
+    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv)
+#define FRB_KH_GEO(WW)                                                        \
+  if (geo.tv != STREAM_TILE_VECS) { FRB_KH(WW, 8, 4, true); }                 \
+  else if (geo.il == 4) { FRB_KH(WW, 4, 1, false); }                          \
+  else if (geo.il == 2) { FRB_KH(WW, 2, 1, false); }                          \
+  else if (geo.il == 1) { FRB_KH(WW, 1, 1, false); }                          \
+  else if (geo.du == 1) { FRB_KH(WW, 8, 1, false); }                          \
+  else if (geo.du == 2) { FRB_KH(WW, 8, 2, false); }                          \
+  else if (geo.du == 3) { FRB_KH(WW, 8, 3, false); }                          \
+  else { FRB_KH(WW, 8, 4, false); }
   switch (w) {
-    case 1: FRB_KH_DU(1) break;
-    case 2: FRB_KH_DU(2) break;
-    case 4: FRB_KH_DU(4) break;
-    default: FRB_KH_DU(8) break;
+    case 1: FRB_KH_GEO(1) break;
+    case 2: FRB_KH_GEO(2) break;
+    case 4: FRB_KH_GEO(4) break;
+    default: FRB_KH_GEO(8) break;
   }
-#undef FRB_KH_DU
+#undef FRB_KH_GEO
 #undef FRB_KH
   return check_launch("k_hist<hash>");
 }
