@@ -595,3 +595,28 @@ def test_full_size_properties_1024(frb):
   fg = frb.foreground(out)
   assert frb.foreground(frb.mask_except(out, keep)) + frb.foreground(frb.mask(out, keep)) == fg
   assert frb.minmax(out) == (0, L) and frb.pixel_pairs(out) == frb.pixel_pairs(vol)
+
+
+# ------------------------------------------------------------------ every row geometry of the read-only kernels
+
+
+@pytest.mark.parametrize("row_bytes", [512, 1024, 2048, 4096, 8192, 12288, 16384, 32768, 8000, 4000, 1040, 20000])
+def test_row_geometries_vs_oracle(frb, oracle, row_bytes):
+  """K1 / k_hist / K7 pick their tile layout from the length of the fastest axis (row_geom: groups of
+  1 / 2 / 4 / 8 interleaved warps, the row slot that lies directly above, tiles of a whole number of
+  rows): one case per branch, C and F order, uint64 and uint16."""
+  for dtype in (np.uint64, np.uint16):
+    w = np.dtype(dtype).itemsize
+    nx = row_bytes // w
+    shape = (3, 7, nx)
+    grid = (2, 3, max(nx // 37, 1))
+    a = synth(shape, grid, dtype, seed=row_bytes % 97 + w, zero_frac=0.15, noise=0.03)
+    par = synth(shape, grid, np.uint32, seed=row_bytes % 97 + w, zero_frac=0.15, noise=0.0, cell_div=3)
+    for arr, p in ((a, par), (np.asfortranarray(a.transpose(2, 1, 0)), np.asfortranarray(par.transpose(2, 1, 0)))):
+      e_out, e_map = oracle.renumber(np.copy(arr, order="K"))
+      g_out, g_map = frb.renumber(np.copy(arr, order="K"))
+      assert g_out.dtype == e_out.dtype and np.array_equal(g_out, e_out) and g_map == e_map
+      eu, ec = oracle.unique(arr, return_counts=True)
+      gu, gc = frb.unique(arr, return_counts=True)
+      assert np.array_equal(eu, gu) and np.array_equal(ec, gc)
+      assert frb.component_map(arr, p) == oracle.component_map(arr, p)
