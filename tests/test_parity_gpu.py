@@ -620,3 +620,31 @@ def test_row_geometries_vs_oracle(frb, oracle, row_bytes):
       gu, gc = frb.unique(arr, return_counts=True)
       assert np.array_equal(eu, gu) and np.array_equal(ec, gc)
       assert frb.component_map(arr, p) == oracle.component_map(arr, p)
+
+
+def test_more_than_2_pow_32_voxels(frb):
+  """64-bit flat indices: a uint8 volume of 2^32 + 2^27 + 5 voxels (4.4 GB).  Checked against torch on
+  the device: counts (bincount), first indices (argmax of an equality mask), encounter-order ids."""
+  n = (1 << 32) + (1 << 27) + 5
+  gen = torch.Generator(device="cuda").manual_seed(3)
+  vol = torch.randint(1, 200, (n // 4096 + 1,), dtype=torch.uint8, device="cuda", generator=gen).repeat_interleave(4096)[:n].contiguous()
+  vol[: 1 << 20] = 7              # a long first run
+  vol[-3:] = 250                  # a label whose first occurrence lies beyond 2^32
+  assert vol.numel() == n
+  u, idx, cts = frb.unique(vol, return_index=True, return_counts=True)
+  hist = torch.zeros(256, dtype=torch.int64, device="cuda")
+  for a in range(0, n, 1 << 30):  # bincount in slices (int64 temporaries)
+    hist += torch.bincount(vol[a:a + (1 << 30)].to(torch.int64), minlength=256)
+  labels = torch.nonzero(hist).reshape(-1)
+  assert u.cpu().numpy().tolist() == labels.cpu().numpy().tolist()
+  assert cts.view(torch.int64).cpu().numpy().tolist() == hist[labels].cpu().numpy().tolist()
+  idx_np = idx.cpu().view(torch.int64).numpy() if idx.dtype == torch.uint64 else idx.cpu().numpy()
+  assert int(idx_np[u.cpu().numpy().tolist().index(250)]) == n - 3
+  assert int(idx_np[u.cpu().numpy().tolist().index(7)]) == 0
+  out, mapping = frb.renumber(vol)
+  assert out.dtype == torch.uint8 and mapping[7] == 1 and mapping[250] == len(mapping) - 1  # 250 is the last label to appear
+  first = {k: int(idx_np[i]) for i, k in enumerate(u.cpu().numpy().tolist())}
+  order = sorted(first, key=first.get)
+  assert [mapping[k] for k in order] == list(range(1, len(order) + 1))
+  assert int(out[n - 1].item()) == mapping[250] and int(out[0].item()) == 1
+  assert frb.foreground(vol) == n and frb.pixel_pairs(vol) >= n - (n // 4096 + 3)
