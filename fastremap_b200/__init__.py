@@ -3,9 +3,8 @@ fastremap_b200 -- B200-native (sm_100a CUDA) implementation of fastremap's relab
 
 Drop-in for the hot-path names of the reference's module surface
 (seung-lab/fastremap, fastremap/__init__.py:1-24): `import fastremap_b200 as fastremap`.
-The names the reference exports that are OUTSIDE this build's scope (in-place
-transposition, tobytes) are present but raise NotImplementedError: by design there is no CPU
-fallback anywhere in this package.
+Every name of the reference's module surface is served by the CUDA library; by design there is no
+CPU fallback anywhere in this package.
 """
 from .api import (  # noqa: F401
   component_map,
@@ -24,23 +23,10 @@ from .api import (  # noqa: F401
   renumber,
   unique,
 )
+from .layout import ascontiguousarray, asfortranarray, tobytes, transpose  # noqa: F401
 from .dtypes import fit_dtype, narrow_dtype, widen_dtype  # noqa: F401
 from ._lib import FastremapB200Error  # noqa: F401
 
-
-def _out_of_scope(name):
-  def fn(*args, **kwargs):
-    raise NotImplementedError(
-      "fastremap_b200.%s is outside the relabel hot path this package implements "
-      "(see SURVEY.md section 8 / DESIGN.md); no CPU fallback is provided." % name)
-  fn.__name__ = name
-  return fn
-
-
-ascontiguousarray = _out_of_scope("ascontiguousarray")
-asfortranarray = _out_of_scope("asfortranarray")
-tobytes = _out_of_scope("tobytes")
-transpose = _out_of_scope("transpose")
 
 __all__ = [
   "ascontiguousarray", "asfortranarray", "component_map", "fit_dtype", "foreground", "indices",

@@ -49,6 +49,8 @@ SIGNATURES = {
   "frb_swap_halves": (_i, [_vp, _vp, _sz, _i, _vp]),
   "frb_pack_pairs": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp]),
   "frb_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
+  "frb_transpose_tiles": (_i, [_vp, _vp, _i, _u64, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
+  "frb_copy_rows": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp, _vp]),
   "frb_hist_dense": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _u64, _vp]),
   "frb_compact_bins_ws_bytes": (_sz, [_u64]),
   "frb_compact_bins_count": (_i, [_vp, _u64, _vp, _vp, _sz, _vp]),

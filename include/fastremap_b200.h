@@ -157,6 +157,23 @@ int frb_pack_pairs(const void* hi, int hi_width, const void* lo, int lo_width, u
 /* refit's astype (fastremap.pyx:301): integer width change, truncating or sign/zero extending */
 int frb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 
+/* ---- memory layout: transposition and chunk serialisation ------------------------------
+ * Replaces pyipt::_ipt2d / _ipt3d / _ipt4d (fastremap.pyx:61-68, ipt.hpp:330-352) behind transpose /
+ * asfortranarray / ascontiguousarray (fastremap.pyx:1140-1273) and the strip loops of tobytes
+ * (fastremap.pyx:1547-1654).  Out of place: `in` and `out` must not overlap.
+ *
+ * Batched 2-D transposition of `width`-byte elements (1, 2, 4, 8): for every batch index and
+ * a < dim_a, b < dim_b:
+ *   out[out_off + a * out_stride_a + b] = in[in_off + b * in_stride_b + a]
+ * where in_off / out_off = sum over the nbatch (<= 6) batch axes of coordinate * stride.  All
+ * strides in elements; batch_dims[0] is the fastest-varying batch axis of the tile order. */
+int frb_transpose_tiles(const void* in, void* out, int width, uint64_t dim_a, uint64_t dim_b, uint64_t in_stride_b,
+                        uint64_t out_stride_a, int nbatch, const uint64_t* batch_dims, const uint64_t* batch_in_strides,
+                        const uint64_t* batch_out_strides, void* stream);
+/* Batched copy of rows of row_bytes contiguous bytes; offsets as above but in BYTES. */
+int frb_copy_rows(const void* in, void* out, uint64_t row_bytes, int nbatch, const uint64_t* batch_dims,
+                  const uint64_t* batch_in_strides_bytes, const uint64_t* batch_out_strides_bytes, void* stream);
+
 /* ---- unique(return_counts) -----------------------------------------------------------
  * Replaces _unique_via_array (fastremap.pyx:1061-1138), _unique_via_shifted_array (:984-1001),
  * _unique_via_renumber (:1003-1022) and _unique_via_sort (:1024-1059).

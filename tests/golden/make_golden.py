@@ -85,6 +85,9 @@ def put_result(case, res, big=False):
       return {"dict": "%s/%s" % (case, slot)}
     if r is None:
       return {"value": None}
+    if isinstance(r, list):  # tobytes: list[bytes]
+      arrays["%s/%s" % (case, slot)] = np.frombuffer(b"".join(r), dtype=np.uint8)
+      return {"bytes_list": "%s/%s" % (case, slot), "lengths": [len(b) for b in r]}
     return {"value": int(r)}
   if isinstance(res, tuple):
     return {"tuple": [one("out%d" % i, r) for i, r in enumerate(res)]}
@@ -257,6 +260,49 @@ for i, dt in enumerate(DTYPES):
   case("indices_absent_%s" % dt, "indices", [flat, 21])
 case("indices_overflow", "indices", [np.array([1, 2, 3], dtype=np.uint8), 300])
 case("indices_empty", "indices", [np.array([], dtype=np.int32), 0])
+
+# ---------------------------------------------------------------- layout changes ("next" rank 4)
+LAYOUT_DTYPES = ["uint8", "uint16", "uint32", "uint64", "int32", "float32", "float64", "bool", "complex64"]
+
+
+def ramp(shape, dt, order):
+  n = int(np.prod(shape))
+  a = (np.arange(n, dtype=np.int64) * 7 + 3) % 251
+  if dt == "complex64":
+    a = (a + 1j * (a[::-1] % 17)).astype(np.complex64)
+  else:
+    a = (a % 2).astype(bool) if dt == "bool" else a.astype(dt)
+  return np.copy(a.reshape(shape), order=order)
+
+
+for dt in LAYOUT_DTYPES:
+  for shape in [(4, 6), (4, 5, 6), (3, 4, 2, 5)]:
+    tag = "%s_%s" % (dt, "x".join(map(str, shape)))
+    case("asfortranarray_%s" % tag, "asfortranarray", [ramp(shape, dt, "C")])
+    case("ascontiguousarray_%s" % tag, "ascontiguousarray", [ramp(shape, dt, "F")])
+    case("transpose_C_%s" % tag, "transpose", [ramp(shape, dt, "C")])
+    case("transpose_F_%s" % tag, "transpose", [ramp(shape, dt, "F")])
+for shape in [(7,), (1, 9), (9, 1), (5, 5), (70, 33), (6, 6, 6), (1, 8, 5), (33, 2, 65), (3, 3, 3, 3), (2, 1, 3, 4), (2, 3, 2, 2, 3)]:
+  tag = "u2_%s" % "x".join(map(str, shape))
+  case("asfortranarray_%s" % tag, "asfortranarray", [ramp(shape, "uint16", "C")])
+  case("asfortranarray_noop_%s" % tag, "asfortranarray", [ramp(shape, "uint16", "F")])
+  case("ascontiguousarray_%s" % tag, "ascontiguousarray", [ramp(shape, "uint16", "F")])
+  case("transpose_C_%s" % tag, "transpose", [ramp(shape, "uint16", "C")])
+  case("transpose_F_%s" % tag, "transpose", [ramp(shape, "uint16", "F")])
+case("asfortranarray_f16", "asfortranarray", [ramp((3, 4), "float16", "C")])
+
+for dt in ["uint8", "uint16", "uint32", "uint64", "int16", "float32", "float64"]:
+  for io in "CF":
+    for oo in "CF":
+      case("tobytes_%s_%s%s" % (dt, io, oo), "tobytes", [ramp((8, 12, 4), dt, io), [4, 3, 2]], {"order": oo})
+for io in "CF":
+  for oo in "CF":
+    case("tobytes_whole_%s%s" % (io, oo), "tobytes", [ramp((5, 6, 7), "int32", io), [5, 6, 7]], {"order": oo})
+    case("tobytes_slabs_%s%s" % (io, oo), "tobytes", [ramp((6, 4, 70), "uint8", io), [3, 4, 35]], {"order": oo})
+    case("tobytes_unit_%s%s" % (io, oo), "tobytes", [ramp((3, 2, 4), "uint16", io), [1, 1, 1]], {"order": oo})
+case("tobytes_misaligned", "tobytes", [ramp((8, 8, 8), "uint8", "C"), [3, 3, 3]])
+case("tobytes_bad_order", "tobytes", [ramp((8, 8, 8), "uint8", "C"), [4, 4, 4]], {"order": "K"})
+case("tobytes_bool", "tobytes", [ramp((4, 4, 4), "bool", "C"), [2, 2, 2]])
 
 np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)
 with open(os.path.join(HERE, "golden_manifest.json"), "w") as f:

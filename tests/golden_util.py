@@ -84,6 +84,10 @@ def _check_one(spec, got, what):
     ka = np.array(ks, dtype=spec["kdtype"])
     va = np.array([got[k] for k in ks], dtype=spec["vdtype"])
     assert [digest(ka), digest(va)] == spec["dict_digest"], "%s: dict digest differs" % what
+  elif "bytes_list" in spec:
+    assert isinstance(got, list) and all(isinstance(b, bytes) for b in got), "%s: expected list[bytes]" % what
+    assert [len(b) for b in got] == spec["lengths"], "%s: chunk lengths differ" % what
+    assert b"".join(got) == npz[spec["bytes_list"]].tobytes(), "%s: bytes differ" % what
   else:
     assert got == spec["value"], "%s: %r != %r" % (what, got, spec["value"])
 

@@ -648,3 +648,132 @@ def test_more_than_2_pow_32_voxels(frb):
   assert [mapping[k] for k in order] == list(range(1, len(order) + 1))
   assert int(out[n - 1].item()) == mapping[250] and int(out[0].item()) == 1
   assert frb.foreground(vol) == n and frb.pixel_pairs(vol) >= n - (n // 4096 + 3)
+
+
+# ------------------------------------------------------------------ layout changes
+
+LAYOUT_DTYPES = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float32, np.float64, bool, np.complex64]
+
+
+@pytest.mark.parametrize("dim", [1, 4, 7, 9, 27, 31, 100, 127, 200])
+def test_asfortranarray_ascontiguousarray_like_reference_suite(frb, dim):  # automated_test.py:262-321
+  for dtype in (LAYOUT_DTYPES if dim < 100 else [np.uint8, np.uint32, np.float64, np.complex64]):
+    shapes = [(dim,), (dim, dim), (dim, dim, dim), (dim, dim + 1), (dim, dim + 1, dim)]
+    if dim < 31:
+      shapes += [(dim, dim, dim, dim), (dim + 1, dim, dim, dim)]
+    for shape in shapes:
+      x = np.arange(int(np.prod(shape))).reshape(shape).astype(dtype)
+      y = np.copy(x)
+      got = frb.asfortranarray(y)
+      assert got.flags.f_contiguous and got.dtype == x.dtype and np.array_equal(np.asfortranarray(x), got)
+      if len(shape) > 1 and dim > 1:
+        assert np.shares_memory(got, y)  # permuted in the caller's buffer
+      xf = np.copy(x, order="F")
+      got = frb.ascontiguousarray(xf)
+      assert got.flags.c_contiguous and np.array_equal(x, got)
+
+
+def test_transpose_vs_oracle_in_place(frb, oracle):
+  rng = np.random.default_rng(11)
+  for shape in [(64, 64), (65, 130), (1, 77), (33, 34, 35), (64, 64, 64), (128, 3, 70), (5, 6, 7, 8), (16, 16, 16, 16), (3, 1, 5, 1)]:
+    for dtype in (np.uint8, np.uint16, np.float32, np.int64, bool):
+      for order in "CF":
+        a = np.copy(rng.integers(0, 200, size=shape).astype(dtype), order=order)
+        b = np.copy(a, order="K")
+        e = oracle.transpose(a)
+        g = frb.transpose(b)
+        assert g is b and g.shape == e.shape and np.array_equal(g, e)
+        assert np.array_equal(D_flat(a), D_flat(b))  # the caller's memory holds the transposed data
+  a = np.arange(24).reshape(2, 3, 4)[:, ::2]  # strided input: copied to C first
+  assert np.array_equal(frb.transpose(a), oracle.transpose(a))
+  v = np.arange(5)
+  assert frb.transpose(v) is not None and np.array_equal(frb.transpose(v), v)
+  with pytest.raises(TypeError):
+    frb.transpose(np.zeros((3, 3), dtype=np.float16))
+  ro = np.zeros((3, 4), dtype=np.uint8)
+  ro.setflags(write=False)
+  with pytest.raises(ValueError):
+    frb.transpose(ro)
+
+
+def D_flat(a):
+  return np.lib.stride_tricks.as_strided(a, shape=(a.size,), strides=(a.dtype.itemsize,))
+
+
+def test_layout_on_cuda_tensors(frb):
+  g = torch.Generator(device="cuda").manual_seed(2)
+  for shape in [(70, 33), (20, 31, 42), (6, 7, 8, 9), (3, 4, 2, 2, 5)]:
+    for tdtype in (torch.uint8, torch.int32, torch.float32, torch.int64, torch.complex64):
+      t = torch.randint(0, 100, shape, device="cuda", generator=g).to(tdtype)
+      keep = t.clone()
+      f = frb.asfortranarray(t)
+      rev = tuple(reversed(range(len(shape))))
+      assert f.shape == keep.shape and f.permute(rev).is_contiguous() and torch.equal(f, keep)
+      assert f.data_ptr() == t.data_ptr()  # in the caller's storage
+      c = frb.ascontiguousarray(f)
+      assert c.is_contiguous() and torch.equal(c, keep) and c.data_ptr() == t.data_ptr()
+      assert frb.ascontiguousarray(c) is c
+  t = torch.arange(64 * 64, device="cuda", dtype=torch.int32).reshape(64, 64)
+  assert torch.equal(frb.transpose(t.clone()), t.T)
+  s = torch.arange(200, device="cuda", dtype=torch.int16).reshape(10, 20)[:, ::2]  # strided
+  assert torch.equal(frb.asfortranarray(s), s) and torch.equal(frb.ascontiguousarray(s), s)
+
+
+@pytest.mark.parametrize("size,cs", [(16, 4), (16, 8), (64, 16), (128, 16), (128, 64)])
+def test_tobytes_like_reference_suite(frb, size, cs):  # automated_test.py:631-652
+  for dtype in (np.uint8, np.uint16, np.uint32, np.uint64, np.int64, np.float32):
+    for io in "CF":
+      image = np.arange(size ** 3, dtype=dtype).reshape((size, size, size), order=io)
+      for oo in "CF":
+        res = frb.tobytes(image, (cs, cs, cs), order=oo)
+        n = size // cs
+        k = 0
+        for z in range(n):
+          for y in range(n):
+            for x in range(n):
+              if k % 37 == 0 or size <= 16:  # every chunk of the small cases, a sample of the big ones
+                assert res[k] == image[x * cs:(x + 1) * cs, y * cs:(y + 1) * cs, z * cs:(z + 1) * cs].tobytes(oo), (k, io, oo)
+              k += 1
+        assert len(res) == n ** 3
+        if size >= 64:  # a checksum over all chunks
+          import hashlib
+          exp = hashlib.sha256()
+          for z in range(n):
+            for y in range(n):
+              for x in range(n):
+                exp.update(image[x * cs:(x + 1) * cs, y * cs:(y + 1) * cs, z * cs:(z + 1) * cs].tobytes(oo))
+          assert hashlib.sha256(b"".join(res)).hexdigest() == exp.hexdigest()
+
+
+def test_tobytes_ragged_and_tensor(frb, oracle):
+  rng = np.random.default_rng(8)
+  for shape, chunk in [((30, 8, 14), (15, 2, 7)), ((6, 6, 6), (6, 6, 6)), ((4, 9, 130), (2, 3, 65)), ((130, 9, 4), (65, 3, 2)), ((5, 5, 5), (1, 5, 1))]:
+    for io in "CF":
+      img = np.copy(rng.integers(0, 2 ** 31, size=shape).astype(np.int32), order=io)
+      for oo in "CF":
+        assert frb.tobytes(img, chunk, order=oo) == oracle.tobytes(img, chunk, order=oo)
+        t = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+        if io == "F":
+          t = t.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+        assert frb.tobytes(t, chunk, order=oo) == oracle.tobytes(img, chunk, order=oo)
+  strided = np.arange(8 * 8 * 16, dtype=np.uint16).reshape(8, 8, 16)[:, :, ::2]
+  assert frb.tobytes(strided, (4, 4, 4), "F") == oracle.tobytes(strided, (4, 4, 4), "F")
+  assert frb.tobytes(np.zeros((0, 4, 4), dtype=np.uint8), (2, 2, 2)) == []
+  with pytest.raises(ValueError):
+    frb.tobytes(np.zeros((4, 4), dtype=np.uint8), (2, 2, 2))
+  with pytest.raises(TypeError):
+    frb.tobytes(np.zeros((4, 4, 4), dtype=np.complex64), (2, 2, 2))
+
+
+def test_transposition_full_size_properties(frb):
+  """1024 x 1024 x 512 uint16 (1 GiB): C -> F -> C is the identity, and the F layout is checked against
+  torch's own permuted copy on the device."""
+  g = torch.Generator(device="cuda").manual_seed(4)
+  t = torch.randint(0, 60000, (1024, 1024, 512), device="cuda", generator=g, dtype=torch.int32).to(torch.uint16)
+  keep = t.clone()
+  f = frb.asfortranarray(t)
+  exp = keep.permute(2, 1, 0).contiguous()  # memory of the F layout
+  assert torch.equal(f.permute(2, 1, 0).view(torch.int16), exp.view(torch.int16))
+  del exp
+  c = frb.ascontiguousarray(f)
+  assert c.is_contiguous() and torch.equal(c.view(torch.int16), keep.view(torch.int16))
