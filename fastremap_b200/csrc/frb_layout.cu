@@ -13,7 +13,8 @@
 //                      are both instances.  Tiles of T x T elements, rows padded so that the column
 //                      reads are bank-conflict free for every element width.
 //   k_copy_rows        batched row copy for layouts whose contiguous axis is the same on both sides
-//                      (tobytes C->C / F->F): one 1..16-byte granule per thread.
+//                      (tobytes C->C / F->F): 1..16-byte granules, four in flight per thread, index
+//                      decoding by multiply-high division with host-made reciprocals.
 //
 // Roofline: HBM, 2 * W bytes per element (one read, one write).
 #include "frb_internal.cuh"
@@ -29,7 +30,10 @@ struct LayoutArgs {
   u64 in_sb, out_sa;   // input stride of axis B, output stride of axis A (elements)
   u64 tiles_a, tiles_b, total;
   int nb;
-  unsigned int bd[LAYOUT_MAX_BATCH];  // batch axis lengths (fastest-decoded first)
+  int fast;                           // every index that is divided fits 32 bits: multiply-high division
+  u64 amagic;                         // ceil(2^64 / A)
+  u64 bmagic[LAYOUT_MAX_BATCH];       // ceil(2^64 / bd[j])
+  unsigned int bd[LAYOUT_MAX_BATCH];  // batch axis lengths (fastest-decoded first), none of them 1
   u64 bis[LAYOUT_MAX_BATCH];          // input strides (elements / granules)
   u64 bos[LAYOUT_MAX_BATCH];          // output strides
 };
@@ -59,6 +63,24 @@ __device__ __forceinline__ void batch_offsets(const LayoutArgs& P, u64 b, u64& i
       }
       in_off += c * P.bis[j];
       out_off += c * P.bos[j];
+    }
+  }
+}
+
+// x / d for x, d < 2^32 with magic = ceil(2^64 / d): exact, because x * (magic - 2^64 / d) < 2^32 <= 2^64 / d
+__device__ __forceinline__ unsigned int fast_div(unsigned int x, u64 magic) { return (unsigned int)__umul64hi((u64)x, magic); }
+
+__device__ __forceinline__ void batch_offsets_fast(const LayoutArgs& P, unsigned int b, u64& in_off, u64& out_off) {
+  in_off = 0;
+  out_off = 0;
+#pragma unroll
+  for (int j = 0; j < LAYOUT_MAX_BATCH; j++) {
+    if (j < P.nb) {
+      const unsigned int q = fast_div(b, P.bmagic[j]);
+      const unsigned int c = b - q * P.bd[j];
+      b = q;
+      in_off += (u64)c * P.bis[j];
+      out_off += (u64)c * P.bos[j];
     }
   }
 }
@@ -127,55 +149,186 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
   }
 }
 
-// one granule of G bytes per thread; A = granules per row, rows decoded as batch indices
-template <int G>
+// 1- and 2-byte elements, R = 4 / W of them per 32-bit word: every global access is a full word, the
+// R x R element blocks are transposed in registers with byte permutes, and shared memory holds words
+// [a][b / R] with the column rotated by a / R so that both the scattered writes (32 different a, one
+// column) and the row reads are bank-conflict free.  The tile is 32HR x 32HR elements: with H = 2 every
+// row segment read or written is 256 bytes, which is what DRAM wants (128-byte segments reach ~0.6 of
+// the copy bandwidth, 256-byte ones ~0.9).  Needs A, B and every stride divisible by R and 4-byte
+// aligned bases.  Dynamic shared memory: (32HR) * (32H) words.
+template <int W, int H>
+__global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant__ LayoutArgs P) {
+  constexpr int R = 4 / W;
+  constexpr int TW = 32 * H;  // tile edge in words
+  constexpr int T = TW * R;   // tile edge in elements
+  extern __shared__ __align__(16) uint32_t S[];  // [T][TW]
+  const uint32_t* __restrict__ in = (const uint32_t*)P.in;
+  uint32_t* __restrict__ out = (uint32_t*)P.out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u64 in_sb_w = P.in_sb / R, out_sa_w = P.out_sa / R;
+  for (u64 t = blockIdx.x; t < P.total; t += gridDim.x) {
+    u64 r = t;
+    const u64 ta = r % P.tiles_a;
+    r /= P.tiles_a;
+    const u64 tb = r % P.tiles_b;
+    r /= P.tiles_b;
+    u64 in_off, out_off;
+    batch_offsets(P, r, in_off, out_off);
+    const u64 a0 = ta * T, b0 = tb * T;
+    const uint32_t* src = in + (in_off + a0) / R + lane;
+    bool a_ok[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) a_ok[h] = a0 + (u64)R * (lane + 32 * h) < P.A;
+    // row groups rb = warp + 8 * i, i < 4H; NB of them (NB * H * R loads per thread) in flight at a time
+    constexpr int NB = (4 * H) < (32 / (H * R)) ? (4 * H) : (32 / (H * R));  // 32 words per thread
+#pragma unroll
+    for (int i0 = 0; i0 < 4 * H; i0 += NB) {
+      uint32_t w[NB][H][R];
+#pragma unroll
+      for (int ii = 0; ii < NB; ii++) {
+        const int rb = warp + 8 * (i0 + ii);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const u64 b = b0 + (u64)R * rb + j;
+#pragma unroll
+          for (int h = 0; h < H; h++) w[ii][h][j] = (a_ok[h] && b < P.B) ? __ldcs(src + b * in_sb_w + 32 * h) : 0u;
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < NB; ii++) {
+        const int rb = warp + 8 * (i0 + ii);
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+          uint32_t tr[R];
+          if constexpr (R == 4) {
+            const uint32_t x0 = __byte_perm(w[ii][h][0], w[ii][h][1], 0x5140), x1 = __byte_perm(w[ii][h][0], w[ii][h][1], 0x7362);
+            const uint32_t y0 = __byte_perm(w[ii][h][2], w[ii][h][3], 0x5140), y1 = __byte_perm(w[ii][h][2], w[ii][h][3], 0x7362);
+            tr[0] = __byte_perm(x0, y0, 0x5410);
+            tr[1] = __byte_perm(x0, y0, 0x7632);
+            tr[2] = __byte_perm(x1, y1, 0x5410);
+            tr[3] = __byte_perm(x1, y1, 0x7632);
+          } else {
+            tr[0] = __byte_perm(w[ii][h][0], w[ii][h][1], 0x5410);
+            tr[1] = __byte_perm(w[ii][h][0], w[ii][h][1], 0x7632);
+          }
+          const int ac = lane + 32 * h;
+#pragma unroll
+          for (int k = 0; k < R; k++) S[(R * ac + k) * TW + ((rb + ac) & (TW - 1))] = tr[k];
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t* dst = out + (out_off + b0) / R + lane;
+    bool b_ok[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) b_ok[h] = b0 + (u64)R * (lane + 32 * h) < P.B;
+#pragma unroll 4
+    for (int i = 0; i < 4 * H * R; i++) {
+      const int a = warp + 8 * i;
+      if (a0 + a < P.A) {
+#pragma unroll
+        for (int h = 0; h < H; h++)
+          if (b_ok[h]) __stcs(dst + (a0 + a) * out_sa_w + 32 * h, S[a * TW + ((lane + 32 * h + a / R) & (TW - 1))]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// U granules of G bytes per thread and iteration; A = granules per row, rows decoded as batch indices
+template <int G, int U>
 __global__ void __launch_bounds__(256) k_copy_rows(const __grid_constant__ LayoutArgs P) {
   using E = typename ElemOf<G>::type;
   const E* __restrict__ in = (const E*)P.in;
   E* __restrict__ out = (E*)P.out;
   const u64 step = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < P.total; i += step) {
-    u64 row, col;
-    if (i <= 0xFFFFFFFFull && P.A <= 0xFFFFFFFFull) {
-      row = (unsigned int)i / (unsigned int)P.A;
-      col = (unsigned int)i % (unsigned int)P.A;
-    } else {
-      row = i / P.A;
-      col = i % P.A;
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < P.total; i0 += step * U) {
+    E v[U];
+    u64 dst[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const u64 i = i0 + (u64)u * step;
+      dst[u] = ~0ull;
+      if (i < P.total) {
+        u64 in_off, out_off, col;
+        if (P.fast) {
+          const unsigned int row = fast_div((unsigned int)i, P.amagic);
+          col = (unsigned int)i - row * (unsigned int)P.A;
+          batch_offsets_fast(P, row, in_off, out_off);
+        } else {
+          const u64 row = i / P.A;
+          col = i % P.A;
+          batch_offsets(P, row, in_off, out_off);
+        }
+        v[u] = __ldcs(in + in_off + col);
+        dst[u] = out_off + col;
+      }
     }
-    u64 in_off, out_off;
-    batch_offsets(P, row, in_off, out_off);
-    out[out_off + col] = in[in_off + col];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (dst[u] != ~0ull) __stcs(out + dst[u], v[u]);
   }
 }
 
 static bool fill_batch(LayoutArgs& P, int nbatch, const uint64_t* dims, const uint64_t* in_strides, const uint64_t* out_strides,
                        u64& count) {
   if (nbatch < 0 || nbatch > LAYOUT_MAX_BATCH || (nbatch > 0 && (!dims || !in_strides || !out_strides))) return false;
-  P.nb = nbatch;
+  P.nb = 0;
+  P.fast = 0;
+  P.amagic = 0;
   count = 1;
   for (int j = 0; j < LAYOUT_MAX_BATCH; j++) {
     P.bd[j] = 1;
-    P.bis[j] = P.bos[j] = 0;
+    P.bis[j] = P.bos[j] = P.bmagic[j] = 0;
   }
   for (int j = 0; j < nbatch; j++) {
     if (dims[j] < 1 || dims[j] > 0xFFFFFFFFull) return false;
-    P.bd[j] = (unsigned int)dims[j];
-    P.bis[j] = in_strides[j];
-    P.bos[j] = out_strides[j];
     count *= dims[j];
+    if (dims[j] == 1) continue;  // a unit axis contributes nothing
+    P.bd[P.nb] = (unsigned int)dims[j];
+    P.bmagic[P.nb] = ~0ull / dims[j] + 1;
+    P.bis[P.nb] = in_strides[j];
+    P.bos[P.nb] = out_strides[j];
+    P.nb++;
   }
   return true;
 }
 
 template <int W>
 static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
+  const u64 max_grid = (u64)sm_count() * 64;
+  if constexpr (W <= 2) {
+    constexpr u64 R = 4 / W;
+    u64 bits = P.A | P.B | P.in_sb | P.out_sa;
+    for (int j = 0; j < P.nb; j++) bits |= P.bis[j] | P.bos[j];
+    const bool aligned = bits % R == 0 && (uintptr_t)P.in % 4 == 0 && (uintptr_t)P.out % 4 == 0;
+    // 256-byte segments (H = 2) when both axes fill most of such a tile; 128-byte ones only pay for bytes
+    const int H = (P.A >= 48 * R && P.B >= 48 * R) ? 2 : ((W == 1 && P.A >= 32 * R && P.B >= 32 * R) ? 1 : 0);
+    if (aligned && H) {
+      const u64 T = 32 * H * R;
+      P.tiles_a = (P.A + T - 1) / T;
+      P.tiles_b = (P.B + T - 1) / T;
+      P.total = P.tiles_a * P.tiles_b * batches;
+      const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
+      const size_t smem = (size_t)T * 32 * H * sizeof(uint32_t);
+      if (H == 2) {
+        static bool attr_set = false;  // once per process and kernel (idempotent, racing threads set the same value)
+        if (!attr_set) {
+          cudaFuncSetAttribute(k_transpose_packed<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          attr_set = true;
+        }
+        k_transpose_packed<W, 2><<<grid, 256, smem, st>>>(P);
+      } else {
+        k_transpose_packed<W, 1><<<grid, 256, smem, st>>>(P);
+      }
+      return check_launch("k_transpose_packed");
+    }
+  }
   const bool small = P.A <= 32 || P.B <= 32;  // short axes: 32 x 32 tiles waste less
   const int T = small ? 32 : 64;
   P.tiles_a = (P.A + T - 1) / T;
   P.tiles_b = (P.B + T - 1) / T;
   P.total = P.tiles_a * P.tiles_b * batches;
-  const u64 max_grid = (u64)sm_count() * 64;
   const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
   if (small) k_transpose_tiles<W, 32><<<grid, 256, 0, st>>>(P);
   else k_transpose_tiles<W, 64><<<grid, 256, 0, st>>>(P);
@@ -233,9 +386,9 @@ int frb_copy_rows(const void* in, void* out, uint64_t row_bytes, int nbatch, con
   }
   // granule: the largest power of two (<= 16) that divides the row length, every stride and both base addresses
   u64 bits = row_bytes | (u64)(uintptr_t)in | (u64)(uintptr_t)out | 16;
-  for (int j = 0; j < nbatch; j++) bits |= P.bis[j] | P.bos[j];
+  for (int j = 0; j < P.nb; j++) bits |= P.bis[j] | P.bos[j];
   const int g = (int)(bits & (~bits + 1));
-  for (int j = 0; j < nbatch; j++) {
+  for (int j = 0; j < P.nb; j++) {
     P.bis[j] /= g;
     P.bos[j] /= g;
   }
@@ -246,16 +399,19 @@ int frb_copy_rows(const void* in, void* out, uint64_t row_bytes, int nbatch, con
   P.in_sb = P.out_sa = 0;
   P.tiles_a = P.tiles_b = 0;
   P.total = P.A * rows;
-  const u64 want = (P.total + 255) / 256;
-  const u64 max_grid = (u64)sm_count() * 32;
+  P.fast = P.total <= 0xFFFFFFFFull && P.A > 1;
+  P.amagic = P.A > 1 ? ~0ull / P.A + 1 : 0;
+  constexpr int U = 4;
+  const u64 want = (P.total + 256 * U - 1) / (256 * U);
+  const u64 max_grid = (u64)sm_count() * 8;
   const unsigned int grid = (unsigned int)(want < max_grid ? want : max_grid);
   cudaStream_t st = (cudaStream_t)stream;
   switch (g) {
-    case 1: k_copy_rows<1><<<grid, 256, 0, st>>>(P); break;
-    case 2: k_copy_rows<2><<<grid, 256, 0, st>>>(P); break;
-    case 4: k_copy_rows<4><<<grid, 256, 0, st>>>(P); break;
-    case 8: k_copy_rows<8><<<grid, 256, 0, st>>>(P); break;
-    default: k_copy_rows<16><<<grid, 256, 0, st>>>(P); break;
+    case 1: k_copy_rows<1, U><<<grid, 256, 0, st>>>(P); break;
+    case 2: k_copy_rows<2, U><<<grid, 256, 0, st>>>(P); break;
+    case 4: k_copy_rows<4, U><<<grid, 256, 0, st>>>(P); break;
+    case 8: k_copy_rows<8, U><<<grid, 256, 0, st>>>(P); break;
+    default: k_copy_rows<16, U><<<grid, 256, 0, st>>>(P); break;
   }
   return check_launch("k_copy_rows");
 }

@@ -675,7 +675,7 @@ def test_asfortranarray_ascontiguousarray_like_reference_suite(frb, dim):  # aut
 
 def test_transpose_vs_oracle_in_place(frb, oracle):
   rng = np.random.default_rng(11)
-  for shape in [(64, 64), (65, 130), (1, 77), (33, 34, 35), (64, 64, 64), (128, 3, 70), (5, 6, 7, 8), (16, 16, 16, 16), (3, 1, 5, 1)]:
+  for shape in [(64, 64), (65, 130), (132, 140), (196, 200), (100, 98), (260, 3, 264), (1, 77), (33, 34, 35), (64, 64, 64), (128, 3, 70), (5, 6, 7, 8), (16, 16, 16, 16), (3, 1, 5, 1)]:
     for dtype in (np.uint8, np.uint16, np.float32, np.int64, bool):
       for order in "CF":
         a = np.copy(rng.integers(0, 200, size=shape).astype(dtype), order=order)
