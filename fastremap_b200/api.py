@@ -491,13 +491,10 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
   narrowed copy is cast and downloaded at the end.
   Returns (result array, mapping) like renumber().
   """
-  L = _L()
-  dev = D.dev()
+  D.dev()
   dtype = arr.dtype
-  w = dtype.itemsize
-  c = D.code(dtype)
   n = arr.size
-  nbytes = n * w
+  nbytes = n * dtype.itemsize
   order = "F" if arr.flags["F_CONTIGUOUS"] else "C"
   host_u8 = D.as_torch_bytes(D.flat_view(arr))
   hint = D.row_bytes(arr.shape, order, dtype)
@@ -514,19 +511,31 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
   s_in.wait_stream(cur)
   s_out.wait_stream(cur)
 
-  ev_in, ev_meta, ev_k3 = [None] * C, [None] * C, [None] * C
-  with torch.cuda.stream(s_in):
-    for i, (a, b) in enumerate(bounds):
-      dev_buf[a:b].copy_(host_u8[a:b], non_blocking=True)
-      ev_in[i] = torch.cuda.Event()
-      ev_in[i].record(s_in)
+  ev_meta, ev_k3 = [None] * C, [None] * C
+  up = D.ChunkUploader(host_u8, dev_buf, bounds, s_in)      # pageable arrays go through a staging ring
+  down = D.ChunkDownloader(host_u8, s_out) if in_place_eff else None
+  try:
+    return _renumber_streamed_run(arr, start, preserve_zero, in_place_eff, dtype, order, hint, bounds, dev_buf, table, rb, flags,
+                                  cur, s_out, up, down, ev_meta, ev_k3)
+  finally:
+    up.abort()
+    if down is not None:
+      down.abort()
 
+
+def _renumber_streamed_run(arr, start, preserve_zero, in_place_eff, dtype, order, hint, bounds, dev_buf, table, rb, flags,
+                           cur, s_out, up, down, ev_meta, ev_k3):
+  L = _L()
+  w = dtype.itemsize
+  c = D.code(dtype)
+  n = arr.size
+  C = len(bounds)
   add = int(np.int64(start))
 
   def enqueue(i):
     a, b = bounds[i]
     ne = (b - a) // w
-    cur.wait_event(ev_in[i])
+    cur.wait_event(up.event(i))
     view = dev_buf[a:b]
     _lib.check(L.frb_renumber_build(D.ptr(view), ne, c, a // w, 1 if preserve_zero else 0, D.ptr(table.slots), table.cap,
                                     D.ptr(table.meta), hint, D.stream()), "frb_renumber_build")
@@ -558,9 +567,7 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
       continue
     if in_place_eff:
       a, b = bounds[done]
-      s_out.wait_event(ev_k3[done])
-      with torch.cuda.stream(s_out):
-        host_u8[a:b].copy_(dev_buf[a:b], non_blocking=True)
+      down.submit(a, b, dev_buf[a:b], ev_k3[done])
     done += 1
 
   cur.synchronize()
@@ -571,15 +578,18 @@ def _renumber_streamed(arr: np.ndarray, start, preserve_zero, in_place_eff, max_
   res.out_dtype = out_dtype = _out_dtype(dtype, start, nl)
   mapping = _mapping_to_dict(res, dtype, preserve_zero)
   if out_dtype == dtype and in_place_eff:
-    s_out.synchronize()
+    down.finish()
     return arr, mapping
   out_buf = dev_buf if out_dtype == dtype else _cast(dev_buf, dtype, out_dtype, n)
-  out = D.host_empty(arr.shape, out_dtype, order)
+  out = D.host_empty(arr.shape, out_dtype, order)  # page-locked
   out_u8 = D.as_torch_bytes(D.flat_view(out))
-  s_out.wait_stream(cur)
-  with torch.cuda.stream(s_out):
+  s_side = torch.cuda.Stream() if down is not None and not down.direct else s_out  # do not queue behind the staged pieces
+  s_side.wait_stream(cur)
+  with torch.cuda.stream(s_side):
     out_u8.copy_(out_buf[: out_u8.numel()], non_blocking=True)
-  s_out.synchronize()
+  if down is not None:
+    down.finish()
+  s_side.synchronize()
   return out, mapping
 
 
@@ -765,16 +775,20 @@ def _relabel_host_streamed(arr: np.ndarray, in_place_eff: bool, table: LabelTabl
   s_in.wait_stream(cur)
   s_out.wait_stream(cur)
   overlap_d2h = policy != _lib.MISS_ERROR
-  ev_in = []
-  with torch.cuda.stream(s_in):
-    for a, b in bounds:
-      dev_buf[a:b].copy_(src_u8[a:b], non_blocking=True)
-      e = torch.cuda.Event()
-      e.record(s_in)
-      ev_in.append(e)
+  up = D.ChunkUploader(src_u8, dev_buf, bounds, s_in)  # pageable arrays go through a staging ring
+  down = D.ChunkDownloader(out_u8, s_out)
+  try:
+    _relabel_host_streamed_run(bounds, dev_buf, nbytes, w, dtype, table, policy, fill_bits, n_labels, message, overlap_d2h, cur, up, down)
+  finally:
+    up.abort()
+    down.abort()
+  return out
+
+
+def _relabel_host_streamed_run(bounds, dev_buf, nbytes, w, dtype, table, policy, fill_bits, n_labels, message, overlap_d2h, cur, up, down):
   batch = _batch_rows(n_labels)
   for i, (a, b) in enumerate(bounds):
-    cur.wait_event(ev_in[i])
+    cur.wait_event(up.event(i))
     view = dev_buf[a:b]
     # the first missing index is relative to the chunk: chunks are visited in memory order and
     # atomicMin keeps the smallest, so a later chunk may only lower it if no earlier chunk set it
@@ -785,18 +799,15 @@ def _relabel_host_streamed(arr: np.ndarray, in_place_eff: bool, table: LabelTabl
     if overlap_d2h:
       e = torch.cuda.Event()
       e.record(cur)
-      s_out.wait_event(e)
-      with torch.cuda.stream(s_out):
-        out_u8[a:b].copy_(view, non_blocking=True)
+      down.submit(a, b, view, e)
   if not overlap_d2h:
     cur.synchronize()
     _check_missing(table, dev_buf, dtype, message)
-    s_out.wait_stream(cur)
-    with torch.cuda.stream(s_out):
-      out_u8.copy_(dev_buf[:nbytes], non_blocking=True)
-  s_out.synchronize()
+    e = torch.cuda.Event()
+    e.record(cur)
+    down.submit(0, nbytes, dev_buf[:nbytes], e)
+  down.finish()
   cur.synchronize()
-  return out
 
 
 def _relabel_chunk_error(view, ne, dtype, table: LabelTable, elem_offset, batch):

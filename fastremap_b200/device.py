@@ -7,8 +7,13 @@ the caller's own container (numpy array or CUDA torch tensor), shape and order.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
+import os
+import queue
+import threading
 import warnings
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -106,14 +111,222 @@ def as_torch_bytes(flat_np: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(b)
 
 
+# ---------------------------------------------------------------------------------- pageable host memory
+# An ordinary numpy array is pageable: the driver moves it through its own bounce buffers with one
+# thread (measured on the B200 box: 11.5 GB/s up, 20.7 GB/s down, against 55 / 54 GB/s for page-locked
+# memory).  A ring of page-locked staging buffers filled / drained by a few memcpy threads (ctypes
+# memmove runs without the GIL: 14 GB/s with one thread, 29 GB/s with eight, 38 with sixteen) keeps the DMA engines
+# busy instead.  Both helpers take the fast path (plain async copies) when the host side is pinned.
+STAGE_BYTES = 32 << 20
+STAGE_SLOTS = 4
+STAGED_MIN_BYTES = 64 << 20
+STAGE_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))  # 12 threads were measured: no faster than 8
+MEMCPY_MIN_PIECE = 1 << 20
+_copy_pool = None
+
+
+def is_pinned(t: torch.Tensor) -> bool:
+  try:
+    return bool(t.is_pinned())
+  except RuntimeError:
+    return False
+
+
+def host_memcpy(dst_ptr: int, src_ptr: int, nbytes: int):
+  """memcpy split over the copy threads (pieces of at least 1 MiB)."""
+  global _copy_pool
+  parts = max(1, min(STAGE_THREADS, nbytes // MEMCPY_MIN_PIECE))
+  if parts == 1:
+    ctypes.memmove(dst_ptr, src_ptr, nbytes)
+    return
+  if _copy_pool is None:
+    _copy_pool = ThreadPoolExecutor(max_workers=STAGE_THREADS, thread_name_prefix="frb-memcpy")
+  per = (nbytes + parts - 1) // parts // 4096 * 4096 + 4096
+  list(_copy_pool.map(lambda k: ctypes.memmove(dst_ptr + k * per, src_ptr + k * per, max(0, min(nbytes, (k + 1) * per) - k * per)),
+                      range(parts)))
+
+
+def _stage_buffers():
+  return [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(STAGE_SLOTS)]
+
+
+class ChunkUploader:
+  """
+  Host -> device copy of the byte ranges `bounds` of host_u8 into the same ranges of dev_buf on
+  `stream`; event(i) is the CUDA event that marks range i as landed.  Pinned source: everything is
+  queued at once.  Pageable source: a background thread stages 32 MiB pieces through page-locked
+  buffers (memcpy of piece k+1 overlaps the DMA of piece k).
+  """
+
+  def __init__(self, host_u8: torch.Tensor, dev_buf: torch.Tensor, bounds, stream):
+    self.host, self.dev_buf, self.bounds, self.stream = host_u8, dev_buf, list(bounds), stream
+    self.events = [None] * len(self.bounds)
+    self.ready = [threading.Event() for _ in self.bounds]
+    self.error = None
+    self.thread = None
+    total = sum(b - a for a, b in self.bounds)
+    if total < STAGED_MIN_BYTES or is_pinned(host_u8):
+      with torch.cuda.stream(stream):
+        for i, (a, b) in enumerate(self.bounds):
+          dev_buf[a:b].copy_(host_u8[a:b], non_blocking=True)
+          self.events[i] = torch.cuda.Event()
+          self.events[i].record(stream)
+          self.ready[i].set()
+    else:
+      self.device = torch.cuda.current_device()
+      self.thread = threading.Thread(target=self._run, name="frb-upload", daemon=True)
+      self.thread.start()
+
+  def _run(self):
+    try:
+      torch.cuda.set_device(self.device)
+      stages = _stage_buffers()
+      slot_ev = [None] * STAGE_SLOTS
+      base = self.host.data_ptr()
+      k = 0
+      for i, (a, b) in enumerate(self.bounds):
+        ev = None
+        for p in range(a, b, STAGE_BYTES):
+          q = min(b, p + STAGE_BYTES)
+          s = k % STAGE_SLOTS
+          k += 1
+          if slot_ev[s] is not None:
+            slot_ev[s].synchronize()
+          host_memcpy(stages[s].data_ptr(), base + p, q - p)
+          with torch.cuda.stream(self.stream):
+            self.dev_buf[p:q].copy_(stages[s][: q - p], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+          slot_ev[s] = ev
+        if ev is None:  # an empty range
+          ev = torch.cuda.Event()
+          ev.record(self.stream)
+        self.events[i] = ev
+        self.ready[i].set()
+    except BaseException as e:  # surfaced by event() / close()
+      self.error = e
+      for r in self.ready:
+        r.set()
+
+  def event(self, i: int):
+    self.ready[i].wait()
+    if self.error is not None:
+      raise self.error
+    return self.events[i]
+
+  def close(self):
+    if self.thread is not None:
+      self.thread.join()
+      self.thread = None
+    if self.error is not None:
+      raise self.error
+
+  def abort(self):
+    """Wait for the worker without raising (cleanup path; the copies it queued are harmless)."""
+    if self.thread is not None:
+      self.thread.join()
+      self.thread = None
+
+
+class ChunkDownloader:
+  """
+  Device -> host copies into byte ranges of host_u8 on `stream`, each after a CUDA event.  Pinned
+  destination: plain async copies.  Pageable destination: a background thread downloads 32 MiB pieces
+  into page-locked staging buffers and the memcpy threads move them on (DMA of piece k+1 overlaps the
+  memcpy of piece k).  finish() returns when every byte is in place.
+  """
+
+  def __init__(self, host_u8: torch.Tensor, stream):
+    self.host, self.stream = host_u8, stream
+    self.direct = is_pinned(host_u8)
+    self.error = None
+    self.thread = None
+    if not self.direct:
+      self.device = torch.cuda.current_device()
+      self.q = queue.Queue()
+      self.thread = threading.Thread(target=self._run, name="frb-download", daemon=True)
+      self.thread.start()
+
+  def submit(self, a: int, b: int, dev_view: torch.Tensor, after_event):
+    """host[a:b] <- dev_view (b - a bytes) once after_event has completed."""
+    if self.direct:
+      self.stream.wait_event(after_event)
+      with torch.cuda.stream(self.stream):
+        self.host[a:b].copy_(dev_view, non_blocking=True)
+    else:
+      self.q.put((a, b, dev_view, after_event))
+
+  def _run(self):
+    try:
+      torch.cuda.set_device(self.device)
+      stages = _stage_buffers()
+      free = list(range(STAGE_SLOTS))
+      pending, inflight = collections.deque(), collections.deque()
+      base = self.host.data_ptr()
+      closed = False
+      while True:
+        block = not pending and not inflight and not closed
+        while True:
+          try:
+            item = self.q.get(block=block)
+          except queue.Empty:
+            break
+          block = False
+          if item is None:
+            closed = True
+            break
+          a, b, view, after = item
+          for p in range(a, b, STAGE_BYTES):
+            q = min(b, p + STAGE_BYTES)
+            pending.append((p, q, view[p - a:q - a], after))
+        while free and pending:
+          p, q, view, after = pending.popleft()
+          s = free.pop()
+          self.stream.wait_event(after)
+          with torch.cuda.stream(self.stream):
+            stages[s][: q - p].copy_(view, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+          inflight.append((ev, s, p, q))
+        if inflight:
+          ev, s, p, q = inflight.popleft()
+          ev.synchronize()
+          host_memcpy(base + p, stages[s].data_ptr(), q - p)
+          free.append(s)
+        elif closed and not pending:
+          break
+    except BaseException as e:
+      self.error = e
+
+  def finish(self):
+    if self.direct:
+      self.stream.synchronize()
+    elif self.thread is not None:
+      self.q.put(None)
+      self.thread.join()
+      self.thread = None
+    if self.error is not None:
+      raise self.error
+
+  def abort(self):
+    """Stop the worker without raising (cleanup path; no-op after finish())."""
+    if self.thread is not None:
+      self.q.put(None)
+      self.thread.join()
+      self.thread = None
+
+
 def upload_bytes(flat_np: np.ndarray) -> torch.Tensor:
-  """Contiguous 1-D numpy array -> fresh 1-D uint8 device tensor (async when the source is pinned)."""
+  """Contiguous 1-D numpy array -> fresh 1-D uint8 device tensor (async when the source is pinned;
+  a large pageable source goes through the staging ring below)."""
   b = flat_np.view(np.uint8) if flat_np.dtype != np.uint8 else flat_np
   with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     src = torch.from_numpy(b)
   out = alloc(b.size)
-  if b.size:
+  if b.size >= STAGED_MIN_BYTES and not is_pinned(src):
+    ChunkUploader(src, out, [(0, b.size)], torch.cuda.current_stream()).close()
+  elif b.size:
     out[: b.size].copy_(src, non_blocking=True)
   return out
 
@@ -130,6 +343,14 @@ def download_into(buf: torch.Tensor, nbytes: int, flat_np: np.ndarray):
   with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     dst = torch.from_numpy(b)
+  if nbytes >= STAGED_MIN_BYTES and not is_pinned(dst):
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    down = ChunkDownloader(dst, cur)
+    down.submit(0, nbytes, buf[:nbytes], ev)
+    down.finish()
+    return
   dst.copy_(buf[:nbytes], non_blocking=False)
 
 

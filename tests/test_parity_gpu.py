@@ -286,12 +286,19 @@ def test_synth_device_equals_numpy_twin(frb, dtype):
 # ------------------------------------------------------------------ chunk pipeline of renumber (host arrays)
 
 
-@pytest.fixture
-def small_chunks(frb, monkeypatch):
-  """Force the H2D / K1-K2-K3 / D2H chunk pipeline on small arrays (chunks of 4 KiB)."""
+@pytest.fixture(params=["direct", "staged"])
+def small_chunks(frb, monkeypatch, request):
+  """Force the H2D / K1-K2-K3 / D2H chunk pipeline on small arrays (chunks of 4 KiB); "staged" also
+  forces the page-locked staging ring that large PAGEABLE arrays go through (1 KiB pieces, 2 threads)."""
   from fastremap_b200 import api
+  from fastremap_b200 import device as D
   monkeypatch.setattr(api, "STREAM_MIN_BYTES", 1)
   monkeypatch.setattr(api, "STREAM_CHUNK_BYTES", 4096)
+  if request.param == "staged":
+    monkeypatch.setattr(D, "STAGED_MIN_BYTES", 1)
+    monkeypatch.setattr(D, "STAGE_BYTES", 1024)
+    monkeypatch.setattr(D, "MEMCPY_MIN_PIECE", 256)
+    monkeypatch.setattr(D, "STAGE_THREADS", 2)
   return api
 
 
@@ -777,3 +784,21 @@ def test_transposition_full_size_properties(frb):
   del exp
   c = frb.ascontiguousarray(f)
   assert c.is_contiguous() and torch.equal(c.view(torch.int16), keep.view(torch.int16))
+
+
+def test_staged_upload_download_of_plain_arrays(frb, oracle, monkeypatch):
+  """upload_bytes / download_into through the staging ring (non-streamed entry points on pageable arrays)."""
+  from fastremap_b200 import device as D
+  monkeypatch.setattr(D, "STAGED_MIN_BYTES", 1)
+  monkeypatch.setattr(D, "STAGE_BYTES", 4096)
+  monkeypatch.setattr(D, "MEMCPY_MIN_PIECE", 512)
+  rng = np.random.default_rng(5)
+  a = rng.integers(0, 50, size=(37, 41, 43)).astype(np.uint32)
+  u, c = frb.unique(a, return_counts=True)
+  eu, ec = oracle.unique(a, return_counts=True)
+  assert np.array_equal(u, eu) and np.array_equal(c, ec)
+  b = np.copy(a)
+  got = frb.remap_from_array(b.reshape(-1), np.arange(50, dtype=np.uint32)[::-1].copy(), in_place=True)
+  assert np.array_equal(got, 49 - a.reshape(-1)) and np.array_equal(b.reshape(-1), got)
+  f = frb.asfortranarray(np.copy(a))
+  assert f.flags.f_contiguous and np.array_equal(f, a)
