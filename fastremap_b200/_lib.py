@@ -36,6 +36,7 @@ SIGNATURES = {
   "frb_table_init": (_i, [_vp, _u64, _vp, _u64, _vp]),
   "frb_table_insert": (_i, [_vp, _i, _vp, _i, _u64, _sz, _i, _i, _vp, _u64, _vp, _vp]),
   "frb_table_insert_gathered": (_i, [_vp, _u64, _i, _vp, _i, _i, _vp, _u64, _vp, _vp]),
+  "frb_table_insert_packed": (_i, [_vp, _u64, _i, _u64, _i, _i, _vp, _u64, _vp, _vp]),
   "frb_table_resolve": (_i, [_vp, _i, _vp, _u64, _vp, _vp]),
   "frb_table_export": (_i, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
   "frb_minmax_pairs": (_i, [_vp, _sz, _i, _vp, _vp]),

@@ -89,6 +89,37 @@ k_table_insert_gathered(const u64* __restrict__ gathered, u64 m, int world, cons
   block_add_to(&meta[FRB_META_COUNT], inserted);
 }
 
+// One block of `block` uint64 per rank: [FRB_META_WORDS words of the rank's table meta | m keys | m values];
+// the exporter dropped pairs beyond m.  Used when m was GUESSED before the counts were known (one
+// collective, no host round trip): a rank whose count exceeds m, whose own build overflowed, or whose
+// table is over its load limit makes the destination's OVERFLOW flag go up, which parks the kernels
+// queued behind this one (K2 / K3 check it) and sends the host down the two-phase path.
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_table_insert_packed(const u64* __restrict__ packed, u64 m, int world, u64 local_cap, int direct, Slot* slots, u64 mask, u64* meta) {
+  const u64 block = FRB_META_WORDS + 2 * m;
+  bool bad = false;
+  for (int r = 0; r < world; r++) {
+    const u64* mt = packed + (size_t)r * block;
+    const u64 cnt = mt[FRB_META_COUNT];
+    bad |= cnt > m || mt[FRB_META_OVERFLOW] != 0 || (local_cap != 0 && 2 * cnt > local_cap);
+  }
+  if (bad) {  // the same decision in every thread
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&meta[FRB_META_OVERFLOW], 1ull);
+    return;
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t total = (size_t)m * (size_t)world;
+  unsigned int inserted = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / m, j = i - r * m;
+    const u64* seg = packed + r * block;
+    if (j >= seg[FRB_META_COUNT]) continue;
+    table_update<OP>(slots, mask, direct, meta, seg[FRB_META_WORDS + j], seg[FRB_META_WORDS + m + j], &inserted);
+  }
+  block_add_to(&meta[FRB_META_COUNT], inserted);
+}
+
 __global__ void __launch_bounds__(256)
 k_table_resolve(const void* __restrict__ vals, int vw, Slot* slots, u64 cap, u64* meta) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -198,6 +229,27 @@ int frb_table_insert_gathered(const uint64_t* gathered, uint64_t m, int world, c
     default: set_error("frb_table_insert_gathered: bad op"); return FRB_ERR_BAD_ARG;
   }
   return check_launch("k_table_insert_gathered");
+}
+
+int frb_table_insert_packed(const uint64_t* packed, uint64_t m, int world, uint64_t local_cap, int op, int direct, void* slots,
+                            uint64_t cap, uint64_t* meta, void* stream) {
+  if (!packed || !slots || !meta || m == 0 || world < 1 || (cap & (cap - 1)) != 0) {
+    set_error("frb_table_insert_packed: bad arguments");
+    return FRB_ERR_BAD_ARG;
+  }
+  Grid g = grid_for((size_t)m * (size_t)world, 256 * 4, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  Slot* s = (Slot*)slots;
+  u64* mt = (u64*)meta;
+  const u64* pp = (const u64*)packed;
+  switch (op) {
+    case FRB_OP_MIN: k_table_insert_packed<FRB_OP_MIN><<<g.blocks, g.threads, 0, st>>>(pp, m, world, local_cap, direct, s, cap - 1, mt); break;
+    case FRB_OP_MAX: k_table_insert_packed<FRB_OP_MAX><<<g.blocks, g.threads, 0, st>>>(pp, m, world, local_cap, direct, s, cap - 1, mt); break;
+    case FRB_OP_ADD: k_table_insert_packed<FRB_OP_ADD><<<g.blocks, g.threads, 0, st>>>(pp, m, world, local_cap, direct, s, cap - 1, mt); break;
+    case FRB_OP_SET: k_table_insert_packed<FRB_OP_SET><<<g.blocks, g.threads, 0, st>>>(pp, m, world, local_cap, direct, s, cap - 1, mt); break;
+    default: set_error("frb_table_insert_packed: bad op"); return FRB_ERR_BAD_ARG;
+  }
+  return check_launch("k_table_insert_packed");
 }
 
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream) {

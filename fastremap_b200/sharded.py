@@ -88,6 +88,15 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   api._ev(timers, "init", 0)
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), _lib.EMPTY)
   api._ev(timers, "init", 1)
+  limits = api._narrow_limits(dtype, start, int(total))
+  key = (id(group), world, dtype.str, int(n_local), local.cap)
+  guess = _exchange_guess.get(key)
+  if guess is not None and limits is not None:
+    res = _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero, write_wide, group, world, offset, total, timers,
+                                     row_bytes, local, limits, guess, key)
+    if res is not None:
+      return res
+    # the guess was too small (or a table overflowed): nothing was written, take the two-phase path
   while True:
     cap_pairs = local.entries_max()
     k64, v64 = D.alloc(cap_pairs * 8), D.alloc(cap_pairs * 8)
@@ -95,7 +104,6 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
                                     local.cap, D.ptr(local.meta), row_bytes, D.stream()), "frb_renumber_build")
     api._ev(timers, "k1", 1)
-    limits = api._narrow_limits(dtype, start, int(total))  # host work while K1 runs (cached across calls)
     api._ev(timers, "merge", 0)
     api._ev(timers, "export", 0)
     _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), cap_pairs,
@@ -112,6 +120,7 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     if not any(overfull):
       break
     local.grow(max(counts))  # all ranks take the same decision: tables stay the same size everywhere
+  _exchange_guess[(id(group), world, dtype.str, int(n_local), local.cap)] = _guess_from(counts)
 
   api._ev(timers, "xchg_pairs", 0)
   m = max(max(counts), 1)
@@ -148,6 +157,77 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   if limits is not None:
     return api._auto_result(src_buf, narrow, dtype, start, merged, rb, meta)
   return api._renumber_finish(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, rb, meta, timers)
+
+
+# One-shot exchange.  The two-phase path above needs the per-rank label counts on the HOST between its
+# two collectives (they size the padded all-gather and the merged table).  Volumes of one job look
+# alike, so the counts of the previous call (+25 %) are used as the sizes of the next one: K1, export,
+# ONE all-gather of [meta | keys | first indices], insert, K2 and K3 are queued without a host round
+# trip, and the insert kernel itself checks the guess (frb_table_insert_packed raises OVERFLOW, which
+# parks K2 and K3) -- the host learns about a miss from the meta block it reads anyway and falls back.
+_exchange_guess = {}
+one_shot_stats = {"hit": 0, "miss": 0}
+
+
+def _guess_from(counts):
+  m = (int(max(counts) * 1.25) + 1024) // 1024 * 1024
+  return m, int(sum(counts) * 1.25) + 1024
+
+
+def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero, write_wide, group, world, offset, total, timers,
+                               row_bytes, local, limits, guess, key):
+  from . import _lib
+  from . import api
+  from . import device as D
+  L = _lib.load()
+  m, total_labels = guess
+  MW = _lib.META_WORDS
+  block = (MW + 2 * m) * 8
+  packed = D.alloc(block)
+  api._ev(timers, "k1", 0)
+  _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
+                                  local.cap, D.ptr(local.meta), row_bytes, D.stream()), "frb_renumber_build")
+  api._ev(timers, "k1", 1)
+  api._ev(timers, "merge", 0)
+  api._ev(timers, "export", 0)
+  keys_out, vals_out = packed[MW * 8:(MW + m) * 8], packed[(MW + m) * 8:block]
+  _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(keys_out), D.ptr(vals_out), m, D.stream()),
+             "frb_table_export")
+  packed[: MW * 8].view(torch.int64).copy_(local.meta)
+  api._ev(timers, "export", 1)
+  api._ev(timers, "xchg_pairs", 0)
+  gathered = torch.empty(world * block, dtype=torch.uint8, device=packed.device)
+  dist.all_gather_into_tensor(gathered, packed[:block], group=group)
+  api._ev(timers, "xchg_pairs", 1)
+  api._ev(timers, "insert", 0)
+  merged = api.LabelTable(dtype, total_labels, _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
+  _lib.check(L.frb_table_insert_packed(D.ptr(gathered), m, world, 0 if local.direct else local.cap, _lib.OP_MIN, merged.direct,
+                                       D.ptr(merged.slots), merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_packed")
+  api._ev(timers, "insert", 1)
+  api._ev(timers, "merge", 1)
+  rb = api._RankBuffers(merged, dtype)
+  api._ev(timers, "k2", 0)
+  api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
+  api._ev(timers, "k2", 1)
+  ranked = torch.cuda.Event()
+  ranked.record()
+  api._ev(timers, "k3", 0)
+  narrow = api._relabel_auto(src_buf, n_local, dtype, merged, preserve_zero, start, write_wide, limits)
+  api._ev(timers, "k3", 1)
+  # host round trip (K3 keeps running): the merged meta and every rank's count, through the side stream
+  side = D.side_stream()
+  side.wait_event(ranked)
+  with torch.cuda.stream(side):
+    counts_h = gathered.view(torch.int64).view(world, MW + 2 * m)[:, _lib.META_COUNT].to("cpu")
+    meta = merged.meta.to("cpu").numpy().view(np.uint64)
+  if meta[_lib.META_OVERFLOW]:
+    one_shot_stats["miss"] += 1
+    _exchange_guess.pop(key, None)
+    torch.cuda.current_stream().synchronize()  # the parked K3 must be out of the way before src is walked again
+    return None
+  one_shot_stats["hit"] += 1
+  _exchange_guess[key] = _guess_from([int(x) for x in counts_h.tolist()])
+  return api._auto_result(src_buf, narrow, dtype, start, merged, rb, meta)
 
 
 # ------------------------------------------------------------------------------------ other ops

@@ -76,6 +76,14 @@ int frb_table_insert(const void* keys, int key_width, const void* vals, int val_
  * FRB_META_WORDS, device memory) whose COUNT word says how many pairs of each segment are valid. */
 int frb_table_insert_gathered(const uint64_t* gathered, uint64_t m, int world, const uint64_t* metas, int op, int direct,
                               void* slots, uint64_t cap, uint64_t* meta, void* stream);
+/* The same merge when the per-rank capacity m was fixed BEFORE the counts were known (one collective,
+ * no host round trip): packed holds, per rank, [FRB_META_WORDS words: the rank's table meta | m keys |
+ * m values] (the exporter dropped pairs beyond m).  If a rank's COUNT exceeds m, its OVERFLOW word is
+ * set, or 2 * COUNT > local_cap (local_cap != 0: the load limit of the per-rank tables), nothing is
+ * inserted and meta[OVERFLOW] of the destination is raised: kernels queued behind (frb_renumber_rank,
+ * frb_relabel with guard_overflow, frb_relabel_auto) do nothing and the host takes the two-phase path. */
+int frb_table_insert_packed(const uint64_t* packed, uint64_t m, int world, uint64_t local_cap, int op, int direct, void* slots,
+                            uint64_t cap, uint64_t* meta, void* stream);
 /* replace every stored value v (a position) by vals[v] -- "later duplicate wins" for
  * remap_from_array_kv (fastremap.pyx:810-811) after an FRB_OP_MAX insert of positions. */
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream);
