@@ -802,3 +802,45 @@ def test_staged_upload_download_of_plain_arrays(frb, oracle, monkeypatch):
   assert np.array_equal(got, 49 - a.reshape(-1)) and np.array_equal(b.reshape(-1), got)
   f = frb.asfortranarray(np.copy(a))
   assert f.flags.f_contiguous and np.array_equal(f, a)
+
+
+# ------------------------------------------------------------------ sharded entry points on a one-rank NCCL group
+
+@pytest.fixture(scope="module")
+def one_rank_group(frb):
+  import torch.distributed as dist
+  if dist.is_initialized():
+    yield None
+    return
+  import socket
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1,
+                          device_id=torch.device("cuda", torch.cuda.current_device()))
+  yield None
+  dist.destroy_process_group()
+
+
+def test_sharded_renumber_world1_two_phase_one_shot_and_miss(frb, oracle, one_rank_group):
+  """renumber_sharded through NCCL with one rank: first call (two-phase exchange), second call (one-shot
+  exchange sized from the first), third call on a volume with ~8x the labels (the one-shot guess is too
+  small: frb_table_insert_packed parks K2 / K3 and the host falls back) -- all bit-exact vs the oracle."""
+  from fastremap_b200 import api, sharded
+  from fastremap_b200 import device as D
+  sharded._exchange_guess.clear()
+  before = dict(sharded.one_shot_stats)
+  shape = (40, 64, 96)
+  for dtype in (np.uint64, np.uint32, np.int64):
+    for rep, grid in enumerate(((6, 7, 8), (6, 7, 8), (13, 15, 17))):
+      a = synth(shape, grid, dtype, seed=21, zero_frac=0.1, noise=0.05)
+      v = D.ingest(a)
+      res = sharded.renumber_sharded(v.buf, v.n, v.dtype, write_wide=True, row_bytes=v.row_bytes)
+      got = D.download(res.out, v.n, res.out_dtype).reshape(shape)
+      mapping = api._mapping_to_dict(res, v.dtype, True)
+      e_out, e_map = oracle.renumber(np.copy(a))
+      assert got.dtype == e_out.dtype and np.array_equal(got, e_out) and mapping == e_map, (dtype, rep)
+      wide = D.download(res.wide, v.n, v.dtype).reshape(shape)
+      assert np.array_equal(wide.astype(e_out.dtype), e_out)
+  assert sharded.one_shot_stats["hit"] - before["hit"] == 3 and sharded.one_shot_stats["miss"] - before["miss"] == 3
