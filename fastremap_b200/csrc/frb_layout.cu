@@ -312,11 +312,7 @@ static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
       const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
       const size_t smem = (size_t)T * 32 * H * sizeof(uint32_t);
       if (H == 2) {
-        static bool attr_set = false;  // once per process and kernel (idempotent, racing threads set the same value)
-        if (!attr_set) {
-          cudaFuncSetAttribute(k_transpose_packed<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          attr_set = true;
-        }
+        cudaFuncSetAttribute(k_transpose_packed<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device: always
         k_transpose_packed<W, 2><<<grid, 256, smem, st>>>(P);
       } else {
         k_transpose_packed<W, 1><<<grid, 256, smem, st>>>(P);

@@ -123,6 +123,7 @@ STAGED_MIN_BYTES = 64 << 20
 STAGE_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))  # 12 threads were measured: no faster than 8
 MEMCPY_MIN_PIECE = 1 << 20
 _copy_pool = None
+_copy_pool_lock = threading.Lock()
 
 
 def is_pinned(t: torch.Tensor) -> bool:
@@ -139,8 +140,9 @@ def host_memcpy(dst_ptr: int, src_ptr: int, nbytes: int):
   if parts == 1:
     ctypes.memmove(dst_ptr, src_ptr, nbytes)
     return
-  if _copy_pool is None:
-    _copy_pool = ThreadPoolExecutor(max_workers=STAGE_THREADS, thread_name_prefix="frb-memcpy")
+  with _copy_pool_lock:
+    if _copy_pool is None:
+      _copy_pool = ThreadPoolExecutor(max_workers=STAGE_THREADS, thread_name_prefix="frb-memcpy")
   per = (nbytes + parts - 1) // parts // 4096 * 4096 + 4096
   list(_copy_pool.map(lambda k: ctypes.memmove(dst_ptr + k * per, src_ptr + k * per, max(0, min(nbytes, (k + 1) * per) - k * per)),
                       range(parts)))
