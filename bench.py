@@ -212,6 +212,7 @@ def run_ours(args):
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   torch.cuda.set_device(local_rank)
+  numa = D.bind_host_to_gpu(local_rank) if world > 1 else None  # host buffers next to this rank's GPU
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   dev = D.dev()
@@ -403,6 +404,7 @@ def run_ours(args):
                            "(~88k labels, ~91%% equal neighbours), refit to %s" % out_dtype,
                "labels": n_labels, "l2": "input 8 GiB >> 126 MB L2; the un-timed restore between steps rewrites it",
                "parallelism": "z-slab x%d, NCCL all-gather key-table merge" % world if world > 1 else "single GPU",
+               "host_binding": numa,
                "hbm_fraction_of_peak_whole_op": ALG_BYTES_PER_VOXEL * n * world * args.steps / (total_ms / 1e3) / 1e9 / (peak * world)},
     "e2e": {"value": e2e_value, "unit": "Gvox/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(d2h),
             "steps": e2e_steps, "api": "fastremap_b200.renumber(pinned numpy array, in_place=True)"},

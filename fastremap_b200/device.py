@@ -83,6 +83,42 @@ def side_stream() -> torch.cuda.Stream:
   return _side_streams[idx]
 
 
+def bind_host_to_gpu(index: int | None = None) -> dict:
+  """
+  Pin the calling process to the CPU cores of the NUMA node the GPU hangs off, so that page-locked
+  buffers (first touch) and the memcpy threads live next to the PCIe root the DMA goes through.
+  One process per GPU should call this before it allocates host memory.  Returns what was found
+  ({"numa_node": .., "cpus": n} or {"skipped": reason}); never raises -- it is an optimisation.
+  """
+  try:
+    import pynvml
+    if index is None:
+      index = torch.cuda.current_device()
+    pynvml.nvmlInit()
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(visible.split(",")[index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else index
+    bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+    bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+    if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+      bus = bus[4:]
+    with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return {"skipped": "no NUMA information for %s" % bus}
+    with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+      cpus = set()
+      for part in f.read().strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = os.sched_getaffinity(0) & cpus
+    if not allowed:
+      return {"skipped": "none of node %d's cpus is in this process's affinity mask" % node, "numa_node": node}
+    os.sched_setaffinity(0, allowed)
+    return {"numa_node": node, "cpus": len(allowed)}
+  except Exception as e:  # noqa: BLE001 -- best effort by design
+    return {"skipped": "%s: %s" % (type(e).__name__, e)}
+
+
 def ptr(t):
   if t is None:
     return None
