@@ -28,6 +28,11 @@ struct LayoutArgs {
   void* out;
   u64 A, B;            // transposition: tile axes; row copy: A = granules per row, B unused
   u64 in_sb, out_sa;   // input stride of axis B, output stride of axis A (elements)
+  // merged tile axes (k_transpose_tiles<.., true>): A = Ai * A1 where the A1 axis continues A contiguously
+  // in the INPUT; its output stride is out_sa1.  Likewise B = Bi * B1, contiguous in the OUTPUT, input
+  // stride in_sb1.  Row offsets are split with the reciprocals ai_magic / bi_magic.
+  u64 in_sb1, out_sa1, ai_magic, bi_magic;
+  unsigned int Ai, Bi;
   u64 tiles_a, tiles_b, total;
   int nb;
   int fast;                           // every index that is divided fits 32 bits: multiply-high division
@@ -85,7 +90,20 @@ __device__ __forceinline__ void batch_offsets_fast(const LayoutArgs& P, unsigned
   }
 }
 
-template <int W, int T>
+template <bool M>
+__device__ __forceinline__ u64 in_row_offset(const LayoutArgs& P, u64 b) {
+  if (!M) return b * P.in_sb;
+  const unsigned int q = fast_div((unsigned int)b, P.bi_magic);
+  return (u64)((unsigned int)b - q * P.Bi) * P.in_sb + (u64)q * P.in_sb1;
+}
+template <bool M>
+__device__ __forceinline__ u64 out_row_offset(const LayoutArgs& P, u64 a) {
+  if (!M) return a * P.out_sa;
+  const unsigned int q = fast_div((unsigned int)a, P.ai_magic);
+  return (u64)((unsigned int)a - q * P.Ai) * P.out_sa + (u64)q * P.out_sa1;
+}
+
+template <int W, int T, bool M>
 __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__ LayoutArgs P) {
   using E = typename ElemOf<W>::type;
   constexpr int PAD = W >= 4 ? 1 : 4 / W;  // row stride = 4 * odd bytes: a column read touches 32 banks
@@ -109,7 +127,7 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
       E v[RPW][CPL];
 #pragma unroll
       for (int i = 0; i < RPW; i++) {
-        const E* row = in + in_off + (b0 + warp + 8 * i) * P.in_sb + a0;
+        const E* row = in + in_off + in_row_offset<M>(P, b0 + warp + 8 * i) + a0;
 #pragma unroll
         for (int c = 0; c < CPL; c++) v[i][c] = __ldcs(row + lane + 32 * c);
       }
@@ -120,7 +138,7 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < RPW; i++) {
-        E* row = out + out_off + (a0 + warp + 8 * i) * P.out_sa + b0;
+        E* row = out + out_off + out_row_offset<M>(P, a0 + warp + 8 * i) + b0;
 #pragma unroll
         for (int c = 0; c < CPL; c++) __stcs(row + lane + 32 * c, tile[lane + 32 * c][warp + 8 * i]);
       }
@@ -131,7 +149,7 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
           const u64 a = a0 + lane + 32 * c;
-          if (a < P.A && b < P.B) tile[warp + 8 * i][lane + 32 * c] = in[in_off + b * P.in_sb + a];
+          if (a < P.A && b < P.B) tile[warp + 8 * i][lane + 32 * c] = in[in_off + in_row_offset<M>(P, b) + a];
         }
       }
       __syncthreads();
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
           const u64 b = b0 + lane + 32 * c;
-          if (a < P.A && b < P.B) out[out_off + a * P.out_sa + b] = tile[lane + 32 * c][warp + 8 * i];
+          if (a < P.A && b < P.B) out[out_off + out_row_offset<M>(P, a) + b] = tile[lane + 32 * c][warp + 8 * i];
         }
       }
     }
@@ -320,14 +338,58 @@ static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
       return check_launch("k_transpose_packed");
     }
   }
+  // A short tile axis makes short row segments (DRAM wants >= 256 bytes).  If a batch axis continues it
+  // contiguously (in the input for A, in the output for B) the two are walked as ONE tile axis, e.g. the
+  // channel axis of an (x, y, z, c) array together with z, or a chunk's rows across the chunk grid.
+  bool merged = false;
+  P.Ai = (unsigned int)P.A;
+  P.Bi = (unsigned int)P.B;
+  P.in_sb1 = P.out_sa1 = 0;
+  auto drop_axis = [&](int j) {
+    for (int k = j; k + 1 < P.nb; k++) {
+      P.bd[k] = P.bd[k + 1];
+      P.bmagic[k] = P.bmagic[k + 1];
+      P.bis[k] = P.bis[k + 1];
+      P.bos[k] = P.bos[k + 1];
+    }
+    P.nb--;
+  };
+  constexpr u64 SHORT = 64;
+  if (P.A < SHORT && P.A > 1)
+    for (int j = 0; j < P.nb; j++)
+      if (P.bis[j] == P.A && P.A * P.bd[j] <= 0xFFFFFFFFull) {
+        P.out_sa1 = P.bos[j];
+        P.A *= P.bd[j];
+        batches /= P.bd[j];
+        drop_axis(j);
+        merged = true;
+        break;
+      }
+  if (P.B < SHORT && P.B > 1)
+    for (int j = 0; j < P.nb; j++)
+      if (P.bos[j] == P.B && P.B * P.bd[j] <= 0xFFFFFFFFull) {
+        P.in_sb1 = P.bis[j];
+        P.B *= P.bd[j];
+        batches /= P.bd[j];
+        drop_axis(j);
+        merged = true;
+        break;
+      }
+  P.ai_magic = P.Ai > 1 ? ~0ull / P.Ai + 1 : 0;
+  P.bi_magic = P.Bi > 1 ? ~0ull / P.Bi + 1 : 0;
   const bool small = P.A <= 32 || P.B <= 32;  // short axes: 32 x 32 tiles waste less
   const int T = small ? 32 : 64;
   P.tiles_a = (P.A + T - 1) / T;
   P.tiles_b = (P.B + T - 1) / T;
   P.total = P.tiles_a * P.tiles_b * batches;
   const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
-  if (small) k_transpose_tiles<W, 32><<<grid, 256, 0, st>>>(P);
-  else k_transpose_tiles<W, 64><<<grid, 256, 0, st>>>(P);
+  if (merged) {
+    if (small) k_transpose_tiles<W, 32, true><<<grid, 256, 0, st>>>(P);
+    else k_transpose_tiles<W, 64, true><<<grid, 256, 0, st>>>(P);
+  } else {
+    if (small) k_transpose_tiles<W, 32, false><<<grid, 256, 0, st>>>(P);
+    else k_transpose_tiles<W, 64, false><<<grid, 256, 0, st>>>(P);
+  }
   return check_launch("k_transpose_tiles");
 }
 
