@@ -76,6 +76,30 @@ __device__ __forceinline__ u64 relabel_one(const RelabelArgs& A, u64 key, u64 h,
   return relabel_miss(A, key, idx);
 }
 
+// All V results of one 16-byte vector of 8-, 16- or 32-bit labels.  Neighbouring voxels mostly carry the
+// same label, and a lookup (one divergent 16- or 32-byte load per lane) costs far more than a compare:
+// with one lookup per voxel K3 cost ~2.1 ms per 2^30 voxels at EVERY width, i.e. 8-, 16- and 32-bit
+// volumes ran at 0.15 / 0.27 / 0.61 of the HBM roofline.  So the voxels of a vector are resolved one after
+// the other with a one-entry cache: a voxel equal to its predecessor reuses the predecessor's result.
+// (Batching 16 probes up front also needed 119 registers.)  64-bit vectors hold 2 voxels, are HBM-bound
+// already and their code is codegen-sensitive: they keep both probes issued up front (see the kernels).
+template <int W, bool HASHED>
+__device__ __forceinline__ void relabel_vector_cached(const RelabelArgs& A, const uint4& cur, size_t i0, u64 (&r)[16 / W]) {
+  constexpr int V = 16 / W;
+  u64 prev_key = 0, prev_r = 0;
+#pragma unroll
+  for (int j = 0; j < V; j++) {
+    const u64 key = vec_get<W>(cur, j);
+    if (j == 0 || key != prev_key) {
+      u64 h;
+      const Probe first = first_probe<HASHED>(A, key, &h);
+      prev_r = relabel_one<HASHED>(A, key, h, first, i0 + j);
+      prev_key = key;
+    }
+    r[j] = prev_r;
+  }
+}
+
 template <int W, int WO, bool WIDE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelArgs A, int run) {
@@ -85,15 +109,20 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;  // uniform: the flag is stable while this kernel runs
   auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
     if (!valid) return;
-    u64 key[V], h[V], r[V];
-    Probe first[V];
+    u64 r[V];
+    if constexpr (W <= 4) {
+      relabel_vector_cached<W, HASHED>(A, cur, i0, r);
+    } else {
+      u64 key[V], h[V];
+      Probe first[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) {
-      key[j] = vec_get<W>(cur, j);
-      first[j] = first_probe<HASHED>(A, key[j], &h[j]);
+      for (int j = 0; j < V; j++) {
+        key[j] = vec_get<W>(cur, j);
+        first[j] = first_probe<HASHED>(A, key[j], &h[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
     }
-#pragma unroll
-    for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
     if (WIDE) store_results<V, W>(dst_wide, i0, r);
     if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
   };
@@ -130,15 +159,20 @@ k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, Rel
   const bool wide = wide_always || wo == 0;
   auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
     if (!valid) return;
-    u64 key[V], h[V], r[V];
-    Probe first[V];
+    u64 r[V];
+    if constexpr (W <= 4) {
+      relabel_vector_cached<W, HASHED>(A, cur, i0, r);
+    } else {
+      u64 key[V], h[V];
+      Probe first[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) {
-      key[j] = vec_get<W>(cur, j);
-      first[j] = first_probe<HASHED>(A, key[j], &h[j]);
+      for (int j = 0; j < V; j++) {
+        key[j] = vec_get<W>(cur, j);
+        first[j] = first_probe<HASHED>(A, key[j], &h[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
     }
-#pragma unroll
-    for (int j = 0; j < V; j++) r[j] = relabel_one<HASHED>(A, key[j], h[j], first[j], i0 + j);
     if (wide) store_results<V, W>(dst_wide, i0, r);
     if (W > 1 && wo == 1) store_results<V, 1>(dst_narrow, i0, r);
     if (W > 2 && wo == 2) store_results<V, (W > 2 ? 2 : 1)>(dst_narrow, i0, r);
