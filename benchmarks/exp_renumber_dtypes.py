@@ -10,7 +10,10 @@ from fastremap_b200.synth import synth_device
 S = 1024
 n = S ** 3
 D.dev()
+only = set(sys.argv[1:])  # e.g. "uint32": that dtype only
 for dtype, grid in ((np.uint8, 6), (np.uint16, 36), (np.uint32, 46), (np.uint64, 46)):
+  if only and np.dtype(dtype).name not in only:
+    continue
   vol = synth_device((S, S, S), (grid,) * 3, dtype, seed=3, zero_frac=0.1).reshape(-1).view(torch.uint8)
   work = torch.empty_like(vol)
   best = None
