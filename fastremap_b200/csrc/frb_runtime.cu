@@ -43,11 +43,7 @@ int sm_count() {
 }
 
 // ---------------------------------------------------------------------------------- table init
-__global__ void __launch_bounds__(256) k_table_init(Slot* slots, u64 cap, u64* meta, u64 init_val) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  ulonglong2 e = make_ulonglong2(FRB_EMPTY, init_val);
-  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride)
-    *reinterpret_cast<ulonglong2*>(slots + s) = e;
+__device__ __forceinline__ void meta_init(u64* meta, u64 init_val) {
   if (blockIdx.x == 0 && threadIdx.x < FRB_META_WORDS) {
     u64 v = 0;
     if (threadIdx.x == FRB_META_MISSING_INDEX) v = FRB_EMPTY;
@@ -55,6 +51,20 @@ __global__ void __launch_bounds__(256) k_table_init(Slot* slots, u64 cap, u64* m
     meta[threadIdx.x] = v;
   }
 }
+// WIDE: two slots (32 bytes, one 256-bit store) per thread and iteration -- needs 32-byte aligned slots and an even cap
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_table_init(Slot* slots, u64 cap, u64* meta, u64 init_val) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (WIDE) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < cap / 2; p += stride)
+      asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(slots + 2 * p), "l"(FRB_EMPTY), "l"(init_val), "l"(FRB_EMPTY), "l"(init_val) : "memory");
+  } else {
+    const ulonglong2 e = make_ulonglong2(FRB_EMPTY, init_val);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < cap; p += stride) *reinterpret_cast<ulonglong2*>(slots + p) = e;
+  }
+  meta_init(meta, init_val);
+}
+__global__ void __launch_bounds__(32) k_meta_init(u64* meta, u64 init_val) { meta_init(meta, init_val); }
 
 // ---------------------------------------------------------------------------------- insert
 template <int OP>
@@ -183,8 +193,17 @@ int frb_table_init(void* slots, uint64_t cap, uint64_t* meta, uint64_t init_val,
     set_error("frb_table_init: bad arguments (cap must be a power of two, slots 16-byte aligned)");
     return FRB_ERR_BAD_ARG;
   }
+  if (init_val == FRB_EMPTY && cap >= (1ull << 16)) {  // every byte is 0xFF: the driver's memset is the fastest fill there is
+    if (cudaMemsetAsync(slots, 0xFF, (size_t)cap * sizeof(Slot), (cudaStream_t)stream) != cudaSuccess) {
+      set_error("frb_table_init: cudaMemsetAsync failed");
+      return FRB_ERR_CUDA;
+    }
+    k_meta_init<<<1, 32, 0, (cudaStream_t)stream>>>((u64*)meta, init_val);
+    return check_launch("k_meta_init");
+  }
   Grid g = grid_for((size_t)cap, 256 * 8, 8);
-  k_table_init<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((Slot*)slots, cap, (u64*)meta, init_val);
+  if (cap >= 2 && ((uintptr_t)slots & 31) == 0) k_table_init<true><<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((Slot*)slots, cap, (u64*)meta, init_val);
+  else k_table_init<false><<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((Slot*)slots, cap, (u64*)meta, init_val);
   return check_launch("k_table_init");
 }
 
