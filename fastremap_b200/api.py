@@ -1242,15 +1242,16 @@ def _first_indices_sorted(buf, n, dtype, nu):
 
 def _inverse_positions(buf, n, dtype, uniq_buf, nu):
   """For every voxel the position of its label in the sorted label list, as a uint64 device buffer:
-  a lookup table label -> position, one relabel pass, and a widening cast for narrow dtypes."""
+  a lookup table label -> position and one relabel pass that stores 8-byte results."""
   dtype = np.dtype(dtype)
   w = dtype.itemsize
   t = table_from_arrays(uniq_buf, None, nu, dtype, op=_lib.OP_SET, positions=True, resolve=False)
-  out = D.alloc(n * w)
-  _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_wide=out, batch_rows=_batch_rows(nu))
+  out = D.alloc(n * 8)
   if w == 8:
-    return out
-  return _cast(out, np.dtype("u%d" % w), np.uint64, n)  # positions < nu <= 2^(8w): they fit the label width
+    _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_wide=out, batch_rows=_batch_rows(nu))
+  else:  # the widening store is fused into the lookup pass (a separate cast cost as much as the lookup)
+    _relabel(buf, n, dtype, t, _lib.MISS_ERROR, dst_narrow=out, narrow_width=8)
+  return out
 
 
 def _two_axis_unique(labels):

@@ -130,7 +130,12 @@ template <int V, int WO>
 __device__ __forceinline__ void store_results(void* dst, size_t i0, const u64 (&r)[V]) {
   constexpr int BYTES = V * WO;
   char* p = (char*)dst + i0 * (size_t)WO;
-  if constexpr (BYTES == 16) {
+  if constexpr (BYTES > 16) {  // widening store (WO == 8 from narrower labels): V / 2 16-byte pieces, lane-contiguous
+    static_assert(WO == 8, "only 8-byte results are wider than the input vector");
+#pragma unroll
+    for (int j = 0; j < V; j += 2)
+      st_stream16(p + 8 * j, make_uint4((uint32_t)r[j], (uint32_t)(r[j] >> 32), (uint32_t)r[j + 1], (uint32_t)(r[j + 1] >> 32)));
+  } else if constexpr (BYTES == 16) {
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < V; j++) {

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(STREAM_THREADS)
 k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int run) {
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
-  static_assert(W >= 4 && R % NB == 0, "hashed tables only");
+  static_assert(W == 8 && R % NB == 0, "64-bit labels, hashed tables only");
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31;
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
@@ -308,7 +308,11 @@ static int dispatch_relabel(const void* src, void* dst_wide, void* dst_narrow, i
   if constexpr (W >= 4) { FRB_CASE(4) }
   if constexpr (W >= 8) { FRB_CASE(8) }
 #undef FRB_CASE
-  set_error("frb_relabel: unsupported width combination (narrow_width must be <= input width; one destination needed)");
+  // the one widening combination: 8-byte results from narrower labels (positions for unique's inverse), second destination only
+  if constexpr (W < 8) {
+    if (wo == 8 && !wide) return launch_relabel<W, 8, false>(src, dst_wide, dst_narrow, n, A, st);
+  }
+  set_error("frb_relabel: unsupported width combination (narrow_width must be <= input width, or 8 without dst_wide; one destination needed)");
   return FRB_ERR_BAD_ARG;
 }
 
@@ -444,8 +448,9 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
   A.add = add;
   A.guard = guard_overflow ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (batch_rows > 1 && !A.direct && w >= 4 && dst_wide && !dst_narrow) {
-    if (w == 4) return batch_rows >= 4 ? launch_relabel_batched<4, 4>(src, dst_wide, n, A, st) : launch_relabel_batched<4, 2>(src, dst_wide, n, A, st);
+  // 64-bit labels only: with 4 labels per vector the batch is 8+ probes per lane (80+ registers) and was
+  // measured 2.5-3x SLOWER than the plain kernel's one-probe-per-distinct-label loop at every table size
+  if (batch_rows > 1 && !A.direct && w == 8 && dst_wide && !dst_narrow) {
     return batch_rows >= 4 ? launch_relabel_batched<8, 4>(src, dst_wide, n, A, st) : launch_relabel_batched<8, 2>(src, dst_wide, n, A, st);
   }
   switch (w) {

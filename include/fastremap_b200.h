@@ -127,7 +127,8 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
  * _mask_except (:516-525) and remap_from_array_kv (:817-825), with the refit astype
  * (:301) fused in as an optional narrow store.
  *   dst_wide   (nullable) receives results at the input width (may alias src: in place)
- *   dst_narrow (nullable) receives results truncated to narrow_width bytes (<= input width)
+ *   dst_narrow (nullable) receives results truncated to narrow_width bytes (<= input width; or 8 with
+ *   dst_wide NULL: zero-extended 8-byte results from narrower labels, e.g. positions for unique's inverse)
  *   policy: FRB_MISS_KEEP   missing label stays as it is           (preserve_missing_labels)
  *           FRB_MISS_ERROR  missing label: meta[MISSING_INDEX] = min(flat index); value kept
  *           FRB_MISS_FILL   missing label := fill; present labels stay as they are (mask_except)
