@@ -138,6 +138,20 @@ def _run_build(fn, table: LabelTable):
 # lane), not the size of the table: measured on B200, remap of 1024^3 uint64 through 10^6 labels
 # takes 6.8 ms at load 0.48, 4.2 ms at 0.24, 3.8 ms at 0.12.  So lookup tables get 8+ slots per label.
 LOOKUP_SLOTS_PER_ENTRY = 8
+# Sparser still pays: a warp walks the slow path (probes beyond the home pair) as soon as ONE of its 64
+# lookups needs it, which at load 1/8 (both slots of a pair taken: 1/64) is most warps.  Measured at 1024^3
+# uint64: remap through 10^6 labels 3.60 / 3.41 / 3.07 ms and mask_except with 5 M kept labels 4.52 / 4.18 /
+# 4.00 ms at 8 / 16 / 32 slots per label (benchmarks/exp_slots_per_entry.py).  So: up to 32, as long as
+# the table stays under 2 GiB.
+LOOKUP_SLOTS_PER_ENTRY_MAX = 32
+LOOKUP_TABLE_MAX_BYTES = 2 << 30
+
+
+def _lookup_slots_per_entry(n_labels: int) -> int:
+  spe = LOOKUP_SLOTS_PER_ENTRY_MAX
+  while spe > LOOKUP_SLOTS_PER_ENTRY and n_labels * spe * 16 > LOOKUP_TABLE_MAX_BYTES:
+    spe //= 2
+  return spe
 # ... and once the table no longer fits L1, K3 issues the table loads of two rows of a warp-tile
 # before it consumes either (mask_except with 5 M labels: 5.0 -> 4.5 ms).
 BATCH_LOOKUP_MIN_LABELS = 1 << 14
@@ -154,7 +168,7 @@ def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positio
   dtype = np.dtype(dtype)
   w = dtype.itemsize
   init = 0
-  table = LabelTable(dtype, L, init, slots_per_entry=LOOKUP_SLOTS_PER_ENTRY)
+  table = LabelTable(dtype, L, init, slots_per_entry=_lookup_slots_per_entry(L))
 
   def build(t):
     _lib.check(_L().frb_table_insert(D.ptr(keys_dev), w, None if positions else D.ptr(vals_dev), w, 0, L, op,
