@@ -161,3 +161,37 @@ def test_product_does_not_import_oracle():
       if f.endswith((".py", ".cu", ".cuh")):
         src = open(os.path.join(dirpath, f)).read()
         assert "import oracle" not in src and "oracle/" not in src and "_ref" not in src, f
+
+
+def test_layout_host_helpers():
+  from fastremap_b200 import layout
+  assert layout._strides_for((3, 4, 5), "C", 2) == (40, 10, 2)
+  assert layout._strides_for((3, 4, 5), "F", 2) == (2, 6, 24)
+  assert layout._mem_dims((3, 4, 5), "C") == (5, 4, 3) and layout._mem_dims((3, 4, 5), "F") == (3, 4, 5)
+  a = np.arange(24, dtype=np.uint16).reshape(2, 3, 4)
+  flat = np.ascontiguousarray(a.T).reshape(-1)                   # memory of the F layout
+  f = layout._restride(flat, a.shape, "F")
+  assert f.flags.f_contiguous and np.array_equal(f, a)
+  assert np.array_equal(np.asfortranarray(a), f)
+
+
+def test_sizing_rules():
+  from fastremap_b200 import api, sharded
+  assert api._lookup_slots_per_entry(1000) == api.LOOKUP_SLOTS_PER_ENTRY_MAX
+  assert api._lookup_slots_per_entry(5_000_000) == 16                      # 32 slots per label would pass 2 GiB
+  assert api._lookup_slots_per_entry(50_000_000) == api.LOOKUP_SLOTS_PER_ENTRY
+  m, total = sharded._guess_from([1000, 3000, 2000])
+  assert m >= 3000 * 1.25 and m % 1024 == 0 and total >= 6000 * 1.25
+
+
+def test_host_memcpy_threads():
+  """The staging ring's parallel memcpy (pure host code)."""
+  from fastremap_b200 import device as D
+  rng = np.random.default_rng(0)
+  src = rng.integers(0, 255, size=(5 << 20) + 123, dtype=np.uint8)
+  dst = np.zeros_like(src)
+  D.host_memcpy(dst.ctypes.data, src.ctypes.data, src.size)
+  assert np.array_equal(src, dst)
+  dst[:] = 0
+  D.host_memcpy(dst.ctypes.data + 7, src.ctypes.data + 7, 1000)    # single piece
+  assert np.array_equal(dst[7:1007], src[7:1007]) and dst[:7].sum() == 0 and dst[1007:].sum() == 0
