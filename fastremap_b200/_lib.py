@@ -56,7 +56,10 @@ SIGNATURES = {
   "frb_compact_bins_ws_bytes": (_sz, [_u64]),
   "frb_compact_bins_count": (_i, [_vp, _u64, _vp, _vp, _sz, _vp]),
   "frb_compact_bins_emit": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _sz, _vp, _vp]),
-  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _u64, _vp]),
+  "frb_hist_ws_bytes": (_sz, [_sz]),
+  "frb_hist_ws_flags_offset": (_sz, []),
+  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _u64, _vp, _sz, _vp]),
+  "frb_hist_apply_log": (_i, [_vp, _sz, _sz, _i, _vp, _u64, _vp, _vp]),
   "frb_sort_pairs_ws_bytes": (_sz, [_sz]),
   "frb_sort_table_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
   "frb_unique_sort_ws_bytes": (_sz, [_sz, _i]),

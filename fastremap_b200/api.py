@@ -116,12 +116,16 @@ class LabelTable:
     return bool(meta[_lib.META_OVERFLOW]) or int(meta[_lib.META_COUNT]) * 2 > self.cap
 
 
-def _default_entries(n: int, max_labels) -> int:
+def _default_entries(n: int, max_labels, voxels_per_label: int = 256) -> int:
   """Initial sizing of a hash table for an n-voxel volume when the label count is unknown:
-  n/256 labels (4.2 M at 1024^3; a 128 MiB table), at least 32 Ki; grown x4 on overflow."""
+  n/256 labels (4.2 M at 1024^3; a 128 MiB table), at least 32 Ki; grown x4 on overflow.  renumber keeps this
+  generous default because K3 looks every voxel up in the same table and a sparser table means shorter probe
+  chains (measured: K3 3.52 ms with the 128 MiB table, 3.80 ms with a 32 MiB one at 88 k labels).  The counting
+  pass of unique only ever ADDS to its table, from a log, and prefers one that stays resident in the 126 MB L2:
+  it passes voxels_per_label=1024 (a 32 MiB table at 1024^3, whose init and export scans are also 4x cheaper)."""
   if max_labels is not None:
     return int(max_labels) + 1
-  return int(min(max(n // 256, 1 << 15), 1 << 27))
+  return int(min(max(n // voxels_per_label, 1 << 15), 1 << 27))
 
 
 def _run_build(fn, table: LabelTable):
@@ -689,6 +693,16 @@ def _dict_to_arrays(table: dict, dtype):
   return keys, vals
 
 
+def _labels_to_array(labels, dtype):
+  """list of Python ints -> typed array; OverflowError if one does not fit the dtype (what Cython's
+  integer conversion raises in the reference, fastremap.pyx:505-506)."""
+  dtype = np.dtype(dtype)
+  try:
+    return np.fromiter(labels, dtype=dtype, count=len(labels))  # numpy >= 2 refuses out-of-range Python ints
+  except (OverflowError, ValueError, TypeError):
+    return np.array([_to_bits(x, dtype) for x in labels], dtype=np.uint64).astype("u%d" % dtype.itemsize).view(dtype)
+
+
 def remap(arr, table, preserve_missing_labels=False, in_place=False):
   """
   Remap the values of `arr` through the dict `table`.  A value missing from `table` is left alone
@@ -850,7 +864,7 @@ def mask_except(arr, labels, in_place=False, value=0):
   adtype = D.numpy_dtype(arr.dtype) if is_t else arr.dtype
   if not D.is_int_dtype(adtype):
     raise TypeError("No matching signature found")
-  lab = np.array([_to_bits(x, adtype) for x in labels], dtype=np.uint64).astype("u%d" % adtype.itemsize).view(adtype)
+  lab = _labels_to_array(labels, adtype)
   fill = _to_bits(value, adtype)
 
   if is_t:
@@ -1192,8 +1206,11 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_byte
                "frb_compact_bins_emit")
     return uniq, cts, nu
   if strategy == "hash":
-    table = LabelTable(dtype, _default_entries(n, max_labels), 0)
+    table = LabelTable(dtype, _default_entries(n, max_labels, voxels_per_label=1024), 0)
     limit = max(n // HASH_MAX_FRACTION, 1 << 16)
+    hws_bytes = int(L.frb_hist_ws_bytes(n))
+    hws = D.alloc(hws_bytes)           # per-warp eviction logs of the counting pass
+    have_logs = False                  # the logs of a finished pass can be folded into a bigger table without re-reading the volume
     while True:
       # count -> export -> sort, queued back to back: the number of labels stays on the device (the sort
       # kernel reads it there) until the one host round trip at the end
@@ -1202,7 +1219,12 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_byte
       ws_bytes = int(L.frb_sort_pairs_ws_bytes(room))
       ws = D.alloc(ws_bytes)
       uniq, cts = D.alloc(room * w), D.alloc(room * 8)
-      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), row_bytes, D.stream()), "frb_hist_hash")
+      if have_logs:
+        _lib.check(L.frb_hist_apply_log(D.ptr(hws), hws_bytes, n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), D.stream()),
+                   "frb_hist_apply_log")
+      else:
+        _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), row_bytes, D.ptr(hws), hws_bytes,
+                                   D.stream()), "frb_hist_hash")
       _lib.check(L.frb_table_export(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.ptr(k64), D.ptr(v64), room, D.stream()),
                  "frb_table_export")
       count_dev = ctypes.c_void_p(table.meta.data_ptr() + 8 * _lib.META_LIST_COUNT)
@@ -1213,6 +1235,8 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_byte
         break
       if table.cap // 2 > limit:  # label set too large to hash profitably
         return unique_counts_device(buf, n, dtype, strategy="sort")
+      off = int(L.frb_hist_ws_flags_offset())
+      have_logs = int(hws[off:off + 4].view(torch.int32).item()) == 0  # no warp bypassed its log: they hold the whole pass
       table.grow(int(meta[_lib.META_COUNT]))
     nu = int(meta[_lib.META_COUNT])
     return uniq, cts, nu

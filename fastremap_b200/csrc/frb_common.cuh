@@ -231,6 +231,29 @@ __device__ __forceinline__ SlotPair ld_pair_ro_batch(const Slot* s) {
   return r;
 }
 
+// Global-memory atomics spelled out in PTX: inside out-of-line (__noinline__) helpers the compiler cannot
+// prove that a table pointer is global memory and emits generic ATOM.E + address-space checks instead of
+// REDG / ATOMG (seen in the SASS of the build and counting kernels' slow paths).
+__device__ __forceinline__ void red_add_u64(u64* p, u64 v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_u64(u64* p, u64 v) {
+  asm volatile("red.global.min.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(u64* p, u64 v) {
+  asm volatile("red.global.max.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 atom_cas_u64(u64* p, u64 cmp, u64 v) {
+  u64 old;
+  asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(__cvta_generic_to_global(p)), "l"(cmp), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ u64 atom_exch_u64(u64* p, u64 v) {
+  u64 old;
+  asm volatile("atom.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+  return old;
+}
+
 template <int OP>
 __device__ __forceinline__ bool op_settled(u64 cur, u64 v) {
   if (OP == FRB_OP_MIN) return cur <= v;
@@ -239,10 +262,10 @@ __device__ __forceinline__ bool op_settled(u64 cur, u64 v) {
 }
 template <int OP>
 __device__ __forceinline__ void op_apply(u64* addr, u64 v) {
-  if (OP == FRB_OP_MIN) atomicMin(addr, v);
-  else if (OP == FRB_OP_MAX) atomicMax(addr, v);
-  else if (OP == FRB_OP_ADD) atomicAdd(addr, v);
-  else atomicExch(addr, v);
+  if (OP == FRB_OP_MIN) red_min_u64(addr, v);
+  else if (OP == FRB_OP_MAX) red_max_u64(addr, v);
+  else if (OP == FRB_OP_ADD) red_add_u64(addr, v);
+  else atom_exch_u64(addr, v);
 }
 
 // Find-or-insert `key` and combine `v` into its value.  `first` is an optional already-loaded
@@ -255,7 +278,7 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
     Slot* s = slots + key;
     Slot cur = ld_slot_cg(s);
     if (cur.key != key) {
-      u64 prev = atomicCAS(&s->key, FRB_EMPTY, key);
+      u64 prev = atom_cas_u64(&s->key, FRB_EMPTY, key);
       if (prev == FRB_EMPTY) (*inserted)++;
     } else if (op_settled<OP>(cur.val, v)) {
       return true;
@@ -264,7 +287,7 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
     return true;
   }
   if (key == FRB_EMPTY) {  // the one key the slot array cannot hold lives in the meta block
-    if (atomicCAS(&meta[FRB_META_SIDE_PRESENT], 0ull, 1ull) == 0ull) (*inserted)++;
+    if (atom_cas_u64(&meta[FRB_META_SIDE_PRESENT], 0ull, 1ull) == 0ull) (*inserted)++;
     op_apply<OP>(&meta[FRB_META_SIDE_VAL], v);
     return true;
   }
@@ -278,7 +301,7 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
       return true;
     }
     if (cur.key == FRB_EMPTY) {
-      u64 prev = atomicCAS(&s->key, FRB_EMPTY, key);
+      u64 prev = atom_cas_u64(&s->key, FRB_EMPTY, key);
       if (prev == FRB_EMPTY) {
         (*inserted)++;
         op_apply<OP>(&s->val, v);
@@ -290,7 +313,7 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
       }
     }
   }
-  atomicExch(&meta[FRB_META_OVERFLOW], 1ull);
+  atom_exch_u64(&meta[FRB_META_OVERFLOW], 1ull);
   return false;
 }
 
@@ -416,46 +439,53 @@ template <bool REVERSE, int DU>
 __device__ __forceinline__ constexpr int ref_slot_ct(int u) {
   return DU == 1 ? (REVERSE ? ((u + 1) & 3) : ((u + 3) & 3)) : DU == 2 ? ((u + 2) & 3) : DU == 3 ? (REVERSE ? ((u + 3) & 3) : ((u + 1) & 3)) : (u & 3);
 }
-struct TileMap {
-  size_t tiles;   // tiles in the whole array
-  size_t run;     // consecutive tiles per run
-  size_t count;   // tiles owned by this CTA
-  size_t tv;      // vectors per tile: STREAM_TILE_VECS, or less when a tile is a whole number of volume rows
-  __device__ __forceinline__ TileMap(size_t nvec, size_t run_, size_t tile_vecs = STREAM_TILE_VECS) {
-    tv = tile_vecs < 32 || tile_vecs > (size_t)STREAM_TILE_VECS ? (size_t)STREAM_TILE_VECS : tile_vecs;
-    tiles = (nvec + tv - 1) / tv;
-    run = run_ < 1 ? 1 : run_;
-    const size_t nruns = (tiles + run - 1) / run;
-    const size_t b = blockIdx.x, g = gridDim.x;
-    const size_t mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA
+// Tile bookkeeping comes in two index widths.  32-bit (TileMap): a tile is 16 KiB, so even a 180 GB volume has
+// ~10^7 of them, and the read-only streaming loops are issue-bound (64-bit adds are two instructions and two
+// registers each).  64-bit (TileMap64): what K3 was tuned with -- its code generation is touchy, and with the
+// 32-bit iterator k_relabel_auto<8> measured 3.75 ms instead of 3.52 ms.
+template <typename IDX>
+struct TileMapT {
+  IDX tiles;   // tiles in the whole array
+  IDX run;     // consecutive tiles per run
+  IDX count;   // tiles owned by this CTA
+  IDX tv;      // vectors per tile: STREAM_TILE_VECS, or less when a tile is a whole number of volume rows
+  __device__ __forceinline__ TileMapT(size_t nvec, size_t run_, size_t tile_vecs = STREAM_TILE_VECS) {
+    tv = tile_vecs < 32 || tile_vecs > (size_t)STREAM_TILE_VECS ? (IDX)STREAM_TILE_VECS : (IDX)tile_vecs;
+    tiles = (IDX)((nvec + tv - 1) / tv);
+    if (sizeof(IDX) == 8) run = run_ < 1 ? (IDX)1 : (IDX)run_;  // (exactly the code K3 was tuned with)
+    else run = run_ < 1 ? (IDX)1 : (run_ > (size_t)tiles ? (tiles ? tiles : (IDX)1) : (IDX)run_);  // clamp: products below stay in 32 bits
+    const IDX nruns = (tiles + run - 1) / run;
+    const IDX b = blockIdx.x, g = gridDim.x;
+    const IDX mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA
     if (mine == 0) { count = 0; return; }
-    const size_t last_start = ((mine - 1) * g + b) * run;
-    const size_t last_len = tiles - last_start < run ? tiles - last_start : run;
+    const IDX last_start = ((mine - 1) * g + b) * run;
+    const IDX last_len = tiles - last_start < run ? tiles - last_start : run;
     count = (mine - 1) * run + last_len;
   }
 };
 // walks the tiles of one CTA in ascending (or descending) order with additions only
-struct TileIter {
-  size_t t;      // current tile
-  size_t o;      // offset of the current tile inside its run
-  size_t run;    // tiles per run
-  size_t jump;   // distance from the last tile of a run to the first tile of this CTA's next run, minus 1
+template <typename IDX>
+struct TileIterT {
+  IDX t;      // current tile
+  IDX o;      // offset of the current tile inside its run
+  IDX run;    // tiles per run
+  IDX jump;   // distance from the last tile of a run to the first tile of this CTA's next run, minus 1
   template <bool REVERSE>
-  __device__ __forceinline__ void init(const TileMap& m) {
+  __device__ __forceinline__ void init(const TileMapT<IDX>& m) {
     run = m.run;
-    jump = ((size_t)gridDim.x - 1) * m.run;
-    const size_t nruns_mine = (m.count + m.run - 1) / m.run;
-    const size_t last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
+    jump = ((IDX)gridDim.x - 1) * m.run;
+    const IDX nruns_mine = (m.count + m.run - 1) / m.run;
+    const IDX last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
     if (REVERSE) {
-      const size_t r = nruns_mine ? nruns_mine - 1 : 0;
+      const IDX r = nruns_mine ? nruns_mine - 1 : 0;
       o = last_len ? last_len - 1 : 0;
       t = (r * gridDim.x + blockIdx.x) * run + o;
     } else {
       o = 0;
-      t = (size_t)blockIdx.x * run;
+      t = (IDX)blockIdx.x * run;
     }
   }
-  __device__ __forceinline__ size_t tile() const { return t; }
+  __device__ __forceinline__ size_t tile() const { return (size_t)t; }
   template <bool REVERSE>
   __device__ __forceinline__ void step() {
     if (REVERSE) {
@@ -467,6 +497,8 @@ struct TileIter {
     }
   }
 };
+typedef TileMapT<unsigned int> TileMap;
+typedef TileMapT<size_t> TileMap64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
@@ -514,8 +546,8 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // read gain from the vertical alignment of a lane's rows.
 // VAR_TILE: the tile length is map.tv (a whole number of volume rows) instead of the constant 16 KiB; a
 // template flag because the constant folds into shifts in loops that are issue-bound (K1 + 18 % otherwise).
-template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename RowFn, typename TileEndFn, typename AfterTileFn>
-__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
@@ -525,8 +557,8 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   uint4* ring = reinterpret_cast<uint4*>(frb_dyn_smem);
   u64* full = reinterpret_cast<u64*>(frb_dyn_smem + (size_t)S * STREAM_STAGE_VECS * 16);
   u64* empty = full + S;
-  const size_t ntiles = map.count;
-  const size_t TV = VAR_TILE ? map.tv : (size_t)STREAM_TILE_VECS;
+  const IDX ntiles = map.count;
+  const size_t TV = VAR_TILE ? (size_t)map.tv : (size_t)STREAM_TILE_VECS;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -539,11 +571,11 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   if (warp == STREAM_WARPS) {
     // ---------------- producer: one elected lane feeds the ring
     if (lane == 0) {
-      TileIter it;
+      TileIterT<IDX> it;
       it.template init<REVERSE>(map);
       int s = 0;
       uint32_t round = 0;
-      for (size_t k = 0; k < ntiles; k++) {
+      for (IDX k = 0; k < ntiles; k++) {
         if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);  // all 8 warps released the previous fill
         const size_t vb = it.tile() * TV;
         it.template step<REVERSE>();
@@ -563,11 +595,11 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
   // ---------------- consumers
   constexpr int ROW_STRIDE = IL ? IL * 32 : 32;  // vectors between two rows of one warp
   const int first = stream_vec<IL>(0, warp, lane);
-  TileIter it;
+  TileIterT<IDX> it;
   it.template init<REVERSE>(map);
   int s = 0;
   uint32_t round = 0;
-  for (size_t k = 0; k < ntiles; k++) {
+  for (IDX k = 0; k < ntiles; k++) {
     const size_t t = it.tile();
     it.template step<REVERSE>();
     if constexpr (IL != 0) {
@@ -661,13 +693,13 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
-template <int W, bool REVERSE, bool NEED_PREV, int IL, typename RowFn, typename TileEndFn, typename AfterTileFn>
-__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+template <int W, bool REVERSE, bool NEED_PREV, int IL, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
   stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, after_tile);
 }
-template <int W, bool REVERSE, bool NEED_PREV, int IL, typename RowFn, typename TileEndFn>
-__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMap& map, RowFn row_fn,
+template <int W, bool REVERSE, bool NEED_PREV, int IL, typename IDX, typename RowFn, typename TileEndFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
                                             TileEndFn tile_end) {
   stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }

@@ -153,7 +153,7 @@ k_relabel(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, RelabelA
     if (WIDE) store_results<V, W>(dst_wide, i0, r);
     if (WO > 0) store_results<V, (WO > 0 ? WO : 1)>(dst_narrow, i0, r);
   };
-  const TileMap map(nvec, (size_t)run);
+  const TileMap64 map(nvec, (size_t)run);
   stream_rows<W, false, false, 0>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
@@ -207,7 +207,7 @@ k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, Rel
     if (W > 2 && wo == 2) store_results<V, (W > 2 ? 2 : 1)>(dst_narrow, i0, r);
     if (W > 4 && wo == 4) store_results<V, (W > 4 ? 4 : 1)>(dst_narrow, i0, r);
   };
-  const TileMap map(nvec, (size_t)run);
+  const TileMap64 map(nvec, (size_t)run);
   stream_rows<W, false, false, 0>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
@@ -266,7 +266,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
       }
     }
   };
-  const TileMap map(nvec, (size_t)run);
+  const TileMap64 map(nvec, (size_t)run);
   stream_rows<W, false, false, 0>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)

@@ -15,17 +15,19 @@
 namespace frb {
 
 struct DenseSink {
+  static constexpr bool USE_LOG = false;  // a dense bin takes a fire-and-forget reduction as it is
   u64* counts;
   u64 min_bits;
   int w;
   __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int*) const {
-    atomicAdd(&counts[trunc_width(key - min_bits, w)], (u64)c);
+    red_add_u64(&counts[trunc_width(key - min_bits, w)], (u64)c);
   }
-  // two-step form used by the drain: nothing to look up for a dense bin
-  __device__ __forceinline__ Slot peek(u64) const { Slot s; s.key = 0; s.val = 0; return s; }
-  __device__ __forceinline__ void commit(u64 key, unsigned int c, const Slot&, unsigned int* ins) const { (*this)(key, c, ins); }
+  // two-step form used by the batched sends: nothing to look up for a dense bin
+  __device__ __forceinline__ u64 peek(u64) const { return 0; }
+  __device__ __forceinline__ void commit(u64 key, unsigned int c, u64, unsigned int* ins) const { (*this)(key, c, ins); }
 };
 struct HashSink {
+  static constexpr bool USE_LOG = true;
   Slot* slots;
   u64 mask;
   int direct;
@@ -33,162 +35,332 @@ struct HashSink {
   __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int* inserted) const {
     table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
   }
-  // two-step form used by the drain: the home slots of all of a lane's entries are read first (the
-  // L2 round trips overlap), then a label already sitting in its home slot costs one fire-and-forget
-  // atomic; anything else takes the probing path
-  __device__ __forceinline__ Slot peek(u64 key) const {
-    return ld_slot_cg_batch(slots + (direct ? key : home_slot(key, mask)));
+  // two-step form used by the batched sends: the home-slot keys of all pairs a warp is about to send are
+  // read first (one L2 round trip for the lot), then a label already sitting in its home slot costs one
+  // fire-and-forget reduction; anything else takes the probing path
+  __device__ __forceinline__ u64 peek(u64 key) const {
+    u64 k;
+    asm("ld.global.cg.u64 %0, [%1];" : "=l"(k) : "l"(&slots[direct ? key : home_slot(key, mask)].key));
+    return k;
   }
-  __device__ __forceinline__ void commit(u64 key, unsigned int c, const Slot& home, unsigned int* inserted) const {
-    if (home.key == key && key != FRB_EMPTY) atomicAdd(&slots[direct ? key : home_slot(key, mask)].val, (u64)c);
+  __device__ __forceinline__ void commit(u64 key, unsigned int c, u64 home_key, unsigned int* inserted) const {
+    if (home_key == key && key != FRB_EMPTY) red_add_u64(&slots[direct ? key : home_slot(key, mask)].val, (u64)c);
     else table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
   }
 };
 
-static constexpr int HIST_CACHE = 2048;        // (label, partial count) entries per CTA
-static constexpr int HIST_SYNC_TILES = 8;      // the consumer warps meet this often ...
-static constexpr int HIST_FLUSH_SYNCS = 8;     // ... and flush the table to memory at least every 8th time
-static constexpr int HIST_FLUSH_CLAIMS = 768;  // or as soon as this many of its entries are taken
+static constexpr int HIST_QUEUE = 64;   // flush requests a warp can hold (it handles 32 at a time: 31 left over + 32 new fit)
+static constexpr int HIST_WMAP = 128;   // (label, partial count) entries of a warp's private map
 
 // Counting pass.  Three levels of aggregation sit between a voxel and a global atomic:
 //   lane   remembers the 16-byte vector it saw directly above (rows of a warp are 4 KiB apart, rows
 //          that lie above one another share a pattern slot: hist_slot) and a repeat count; an
-//          identical vector just bumps the count
-//          (7 integer instructions for V voxels).  A different vector flushes the old one: equal
-//          neighbours inside the vector are merged and (label, multiplicity * repeats) is added to
-//   CTA    a shared-memory hash of (label, partial count) shared by the 8 consumer warps (they walk
-//          adjacent rows of the volume, i.e. the same labels), updated with shared-memory atomics.
-//          Entries are claimed with CAS and never change label between flushes, so a lane can add
-//          to an entry it has seen without locking; a label that finds both of its two candidate
-//          entries taken goes straight to memory.  Every few tiles the consumer warps meet at a
-//          named barrier and, on a schedule or when the table is filling up, drain it with one
-//   global atomic per live entry (dense bins or the label table, see the sinks above); the home-slot
-//          reads of a thread's entries are issued together so their L2 round trips overlap.
+//          identical vector just bumps the count (7 integer instructions for V voxels).  A different
+//          vector retires the old one: the lane pushes (vector, repeats) into its warp's
+//   queue  in shared memory (ballot + popc, one predicated 16-byte store).  Retiring lanes are a
+//          minority of every row, so the retirement work is NOT done in place, where it would run at
+//          10 % lane occupancy in a loop that is issue-bound; as soon as 32 requests are queued the
+//          warp handles them with all lanes busy: every lane splits one vector into (label, count)
+//          runs and adds them to the
+//   map    a 128-entry direct-mapped (label, partial count) table private to the warp (a warp owns a
+//          fixed band of columns, so the labels it meets belong to it and to its two neighbours): a hit
+//          is one shared-memory atomic; on a miss one lane per entry (match.any) replaces the resident
+//          label, and only the evicted (label, count) pair goes to
+//   global memory: dense bins or the label table (the sinks above), a handful of lanes at a time,
+//          whose probes are in flight together.
+// Nothing in the loop is CTA-wide: no barrier, no scheduled drain -- the previous version shared one map
+// among the 8 warps and drained it behind a named barrier, which cost a third of all stall samples
+// (ncu, profiles/r02a_*: all 8 warps parked on the L2 round trip of the drain while the TMA ring ran dry).
 // pattern slot of row u: rows that lie directly above one another (q * 4 KiB apart, q = DU) share a slot
 template <int DU>
 __device__ __forceinline__ constexpr int hist_slot(int u) { return DU == 1 ? 0 : DU == 2 ? (u & 1) : DU == 3 ? (u == 3 ? 0 : u) : u; }
 
-template <int W, typename Sink, int IL, int DU, bool VAR_TILE>
-__global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, Sink sink, u64* count_target, int run,
-                                                            int tile_vecs) {
-  constexpr int V = 16 / W;
-  __shared__ u64 s_key[HIST_CACHE];
-  __shared__ unsigned int s_cnt[HIST_CACHE];
-  __shared__ unsigned int s_claims;
-  const size_t nvec = n / V;
-  const int warp = threadIdx.x >> 5;
-  const bool consumer = warp < STREAM_WARPS;
-  unsigned int inserted = 0;
-  for (int i = threadIdx.x; i < HIST_CACHE; i += STREAM_THREADS) { s_key[i] = FRB_EMPTY; s_cnt[i] = 0; }
-  if (threadIdx.x == 0) s_claims = 0;
-  __syncthreads();
+// per-warp queues and maps of k_hist (file scope, so that the out-of-line helpers below address them as
+// shared memory with 32-bit offsets instead of carrying generic pointers through the hot loop)
+__shared__ uint4 hs_qpat[STREAM_WARPS][HIST_QUEUE];
+__shared__ unsigned int hs_qrep[STREAM_WARPS][HIST_QUEUE];
+__shared__ __align__(16) u64 hs_key[STREAM_WARPS][HIST_WMAP];
+__shared__ unsigned int hs_cnt[STREAM_WARPS][HIST_WMAP];
+__shared__ unsigned int hs_logpos[STREAM_WARPS];  // records the warp has appended to its log region
 
-  unsigned int claimed = 0;  // entries this lane has claimed since the consumer warps last met
-  auto add = [&](u64 key, unsigned int c) {
-    if (key != FRB_EMPTY) {
-      unsigned int e = (unsigned int)(hash_key(key) >> 48) & (HIST_CACHE - 1);
-#pragma unroll
-      for (int attempt = 0; attempt < 2; attempt++, e ^= 1u) {
-        u64 ck = s_key[e];
-        if (ck == FRB_EMPTY) {
-          const u64 old = atomicCAS(&s_key[e], (u64)FRB_EMPTY, key);
-          ck = old == FRB_EMPTY ? key : old;
-          claimed += old == FRB_EMPTY ? 1u : 0u;
-        }
-        if (ck == key) {
-          atomicAdd(&s_cnt[e], c);
-          return;
-        }
-      }
+// Eviction log.  What a warp's map evicts does not go to the label table from inside the streaming loop:
+// an update of the table is a dependent L2 round trip (read the home slot, then add), and a warp that
+// waits for one holds back the CTA's whole TMA ring (measured: a third of all stall samples, whichever
+// way the updates were batched).  Instead every consumer warp APPENDS (label, count) records to a region
+// of its own in global memory -- plain 16-byte stores, fire and forget -- and k_hist_apply_log folds all
+// regions into the table afterwards with every lane busy and four probes in flight per thread.  A warp
+// whose region is full falls back to updating the table directly (and says so in flags[0]); a table that
+// turns out too small then only costs a second apply pass, not a second pass over the volume.
+struct HistLog {
+  ulonglong2* records;    // regions * cap records; region r = records + r * cap
+  unsigned int* counts;   // records written per region
+  unsigned int* flags;    // [0] != 0: some warp ran out of log space and updated the table directly
+  unsigned int cap;       // records per region (0: no log, always update the table directly)
+};
+
+// Add (key, c) of the lanes with `act` to the warp's map; called by all 32 lanes of a consumer warp.
+// A lane that had to take over an entry gets the (label, count) pair it evicted back (key == FRB_EMPTY:
+// nothing evicted); the caller sends those to global memory in batches.
+struct HistEvicted {
+  u64 key;
+  unsigned int cnt;
+};
+__device__ __noinline__ HistEvicted hist_map_add(u64 key, unsigned int c, bool act) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64* const s_key = hs_key[warp];
+  unsigned int* const s_cnt = hs_cnt[warp];
+  HistEvicted ev;
+  ev.key = FRB_EMPTY;
+  ev.cnt = 0;
+  // two-way sets (an aligned pair of entries, both keys in one 16-byte shared load)
+  const unsigned int e0 = (unsigned int)(hash_key(key) >> 48) & (HIST_WMAP - 2);
+  while (__any_sync(FRB_FULL_MASK, act)) {
+    u64 k0 = 0, k1 = 0;
+    if (act) {
+      const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&s_key[e0]);
+      k0 = kk.x;
+      k1 = kk.y;
     }
-    sink(key, c, &inserted);
-  };
-  auto flush_vec = [&](const uint4& p, unsigned int reps) {
-    u64 key = vec_get<W>(p, 0);
-    unsigned int c = 1;
-#pragma unroll
-    for (int j = 1; j < V; j++) {
-      const u64 kj = vec_get<W>(p, j);
-      if (kj == key) {
-        c++;
-      } else {
-        add(key, c * reps);
-        key = kj;
-        c = 1;
-      }
+    if (act && (k0 == key || k1 == key)) {
+      atomicAdd(&s_cnt[e0 + (k0 == key ? 0u : 1u)], c);
+      act = false;
     }
-    add(key, c * reps);
-  };
+    __syncwarp();
+    // the lanes left want a set that does not hold their label: one of them per set installs it
+    const unsigned int m = __match_any_sync(FRB_FULL_MASK, act ? e0 : (0x80000000u | (unsigned int)lane));
+    if (act && (__ffs(m) - 1) == lane) {
+      // victim: a free way, else the way with the SMALLER partial count.  Labels that keep coming back (the
+      // background, segments much larger than a tile) hold large counts and stay put; with plain direct
+      // mapping every 128th new label evicted the background's entry, and the ~650 k background records of a
+      // 1024^3 volume then queued up on ONE table slot (same-address atomics serialise in L2: apply pass 0.6 ms)
+      const unsigned int c0 = s_cnt[e0], c1 = s_cnt[e0 + 1];
+      const unsigned int v = k0 == FRB_EMPTY ? 0u : (k1 == FRB_EMPTY ? 1u : (c0 <= c1 ? 0u : 1u));
+      ev.key = v ? k1 : k0;
+      ev.cnt = v ? c1 : c0;
+      s_key[e0 + v] = key;
+      s_cnt[e0 + v] = c;
+      act = false;
+    }
+    __syncwarp();
+  }
+  return ev;
+}
+
+// element j (run-time index) of a 16-byte vector, zero-extended
+template <int W>
+__device__ __forceinline__ u64 vec_get_dyn(const uint4& v, int j) {
+  constexpr int PER = 4 / (W < 4 ? W : 4);  // elements per 32-bit word (W <= 4)
+  if (W == 8) return j ? ((u64)v.z | ((u64)v.w << 32)) : ((u64)v.x | ((u64)v.y << 32));
+  const int wi = W == 4 ? j : j / PER;
+  const uint32_t w32 = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
+  if (W == 4) return (u64)w32;
+  return (u64)((w32 >> ((j % PER) * 8 * W)) & ((1u << (8 * W)) - 1u));
+}
+
+// Send the (key, cnt) pairs of the lanes with `ev` on their way to global memory; called by all 32 lanes.
+template <typename Sink>
+__device__ __forceinline__ void hist_emit(u64 key, unsigned int cnt, bool ev, const Sink& sink, const HistLog& log, unsigned int* inserted) {
+  if (Sink::USE_LOG) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int m = __ballot_sync(FRB_FULL_MASK, ev);
+    if (m == 0) return;
+    const unsigned int cur = hs_logpos[warp];
+    const unsigned int add = __popc(m);
+    if (cur + add <= log.cap) {
+      if (ev) {
+        ulonglong2* dst = log.records + (size_t)(blockIdx.x * STREAM_WARPS + warp) * log.cap + cur + __popc(m & ((1u << lane) - 1u));
+        asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(__cvta_generic_to_global(dst)), "l"(key), "l"((u64)cnt) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) hs_logpos[warp] = cur + add;
+      __syncwarp();
+      return;
+    }
+    if (lane == 0 && log.cap) atomicOr(log.flags, 1u);
+  }
+  if (ev) sink(key, cnt, inserted);
+}
+
+// Handle `count` (<= 32) queued (vector, repeats) requests starting at ring position qhead, one per lane.
+//  1. every lane splits its vector into runs of equal labels;
+//  2. runs that continue across lane boundaries (the requests of one row are queued in lane order, and a
+//     segment of a volume is usually wider than one 16-byte vector) are merged with a segmented warp scan,
+//     so a label that spans several lanes costs ONE map update, made by the lane in which its run ends;
+//  3. the (label, weighted length) pairs go to the warp's map (hist_map_add), one call per "k-th run that ends
+//     in a lane" -- one or two calls per batch; what the map evicts is appended to the warp's log (hist_emit).
+// Counts are 32-bit: a warp never sees 2^32 voxels (that would take a 15-terabyte volume).
+template <int W, typename Sink>
+__device__ __noinline__ unsigned int hist_process(int qhead, int count, const Sink sink, const HistLog log) {
+  constexpr int V = 16 / W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool has = lane < count;
+  const int pos = (qhead + lane) & (HIST_QUEUE - 1);
+  const uint4 p = has ? hs_qpat[warp][pos] : make_uint4(0, 0, 0, 0);
+  const unsigned int reps = has ? hs_qrep[warp][pos] : 0u;
+  unsigned int inserted = 0;
+
+  // runs inside the lane: bit j of `ends` = the run holding element j ends there (j < V - 1)
+  const u64 kf = vec_get<W>(p, 0), kl = vec_get<W>(p, V - 1);
+  unsigned int ends = 0, cl = 1;
+#pragma unroll
+  for (int j = 1; j < V; j++) {
+    if (vec_get<W>(p, j) != vec_get<W>(p, j - 1)) {
+      ends |= 1u << (j - 1);
+      cl = 1;
+    } else {
+      cl++;
+    }
+  }
+  // across lanes (lanes below `count` are contiguous): T = weighted length of the run open at my right edge
+  const u64 kprev = __shfl_up_sync(FRB_FULL_MASK, kl, 1);
+  const u64 knext = __shfl_down_sync(FRB_FULL_MASK, kf, 1);
+  const bool joins = has && lane > 0 && kprev == kf;  // my first run continues the previous lane's last one
+  unsigned int T = cl * reps;
+  bool seg = !(ends == 0 && joins);                   // my last run starts inside me (or at my left edge)
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int v = __shfl_up_sync(FRB_FULL_MASK, T, d);
+    const bool f = __shfl_up_sync(FRB_FULL_MASK, (int)seg, d) != 0;
+    if (lane >= d && !seg) {
+      T += v;
+      seg = f;
+    }
+  }
+  const unsigned int Tprev = __shfl_up_sync(FRB_FULL_MASK, T, 1);
+  const unsigned int carry = joins ? Tprev : 0u;      // what my first run inherits from the lanes to the left
+  const bool tail_ends = has && (lane + 1 >= count || knext != kl);
+  unsigned int pend = has ? (ends | (tail_ends ? 1u << (V - 1) : 0u)) : 0u;  // element positions at which a run ends in this lane
+
+  int start = 0;  // first element of the lane's next run
+  while (__any_sync(FRB_FULL_MASK, pend != 0)) {
+    bool act = pend != 0;
+    const int j = act ? __ffs(pend) - 1 : 0;
+    const u64 key = vec_get_dyn<W>(p, j);
+    // a run that reaches the right edge carries the scan's total (which includes what it inherited if the
+    // whole lane is one run); a run that ends inside the lane is its own length, plus the carry if it is the first
+    const unsigned int total = j == V - 1 ? T : (unsigned int)(j + 1 - start) * reps + (start == 0 ? carry : 0u);
+    pend &= pend - 1;
+    start = j + 1;
+    HistEvicted ev;
+    if (key == FRB_EMPTY) {  // the map's "free" marker: only a 64-bit all-ones label can collide with it -- bypass the map
+      ev.key = FRB_EMPTY;
+      ev.cnt = 0;
+      if (act) sink(key, total, &inserted);
+      act = false;
+    }
+#ifdef FRB_HIST_NOMAP  // experiment: merged runs straight to the log, no per-warp map
+    ev.key = act ? key : FRB_EMPTY;
+    ev.cnt = total;
+#else
+    ev = hist_map_add(key, total, act);
+#endif
+    hist_emit(ev.key, ev.cnt, ev.key != FRB_EMPTY, sink, log, &inserted);
+  }
+  return inserted;
+}
+
+template <int W, typename Sink, int IL, int DU, bool VAR_TILE>
+__global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, const __grid_constant__ Sink sink,
+                                                            const __grid_constant__ HistLog log, u64* count_target, int run, int tile_vecs) {
+  constexpr int V = 16 / W;
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool consumer = warp < STREAM_WARPS;
+  const int wq = consumer ? warp : 0;  // the producer warp never touches the queues
+  unsigned int inserted = 0;
+  if (consumer) {
+    for (int i = lane; i < HIST_WMAP; i += 32) { hs_key[warp][i] = FRB_EMPTY; hs_cnt[warp][i] = 0; }
+    if (lane == 0) hs_logpos[warp] = 0;
+  }
+  __syncwarp();
+
+  int qhead = 0, qn = 0;  // warp-uniform: ring position of the oldest request, number of requests queued
+  const unsigned int lanes_below = (1u << lane) - 1u;
 
   uint4 pat[STREAM_ROWS];
   unsigned int rep[STREAM_ROWS];
 #pragma unroll
   for (int u = 0; u < STREAM_ROWS; u++) { pat[u] = make_uint4(0, 0, 0, 0); rep[u] = 0; }
-  int syncs_since_flush = 0;
+
+  // queue the lanes' retired patterns; once 32 are waiting, handle 32
+  auto retire = [&](bool push, const uint4& p, unsigned int r) {
+    const unsigned int m = __ballot_sync(FRB_FULL_MASK, push);
+    if (m == 0) return;
+    if (push) {
+      const int pos = (qhead + qn + __popc(m & lanes_below)) & (HIST_QUEUE - 1);
+      hs_qpat[wq][pos] = p;
+      hs_qrep[wq][pos] = r;
+    }
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+      inserted += hist_process<W>(qhead, 32, sink, log);
+      qhead = (qhead + 32) & (HIST_QUEUE - 1);
+      qn -= 32;
+      __syncwarp();
+    }
+  };
 
   auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64, bool) {
-    if (!valid) return;
     const int sl = hist_slot<DU>(u);  // a constant once the row loop is unrolled
     const uint4 l = pat[sl];
     const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
-    if (d == 0 && rep[sl] != 0) {
-      rep[sl]++;
-    } else {
-      if (rep[sl] != 0) flush_vec(l, rep[sl]);
-      pat[sl] = cur;
-      rep[sl] = 1;
-    }
-  };
-  // all consumer threads, between two consumer barriers: nobody is inside add()
-  auto drain = [&]() {
-    constexpr int BATCH = 4;  // home-slot reads in flight per thread (registers: 7 per entry)
-    constexpr int NCONS = STREAM_WARPS * 32;
-#pragma unroll 1
-    for (int q0 = 0; q0 < HIST_CACHE / NCONS; q0 += BATCH) {
-      u64 k[BATCH];
-      unsigned int cnt[BATCH];
-      Slot home[BATCH];
-#pragma unroll
-      for (int q = 0; q < BATCH; q++) {
-        const int e = (q0 + q) * NCONS + threadIdx.x;
-        k[q] = s_key[e];
-        cnt[q] = s_cnt[e];
-        if (k[q] != FRB_EMPTY) {
-          home[q] = sink.peek(k[q]);
-          s_key[e] = FRB_EMPTY;
-          s_cnt[e] = 0;
-        }
+    const bool same = d == 0 && rep[sl] != 0;
+    retire(valid && !same && rep[sl] != 0, l, rep[sl]);
+    if (valid) {
+      if (same) {
+        rep[sl]++;
+      } else {
+        pat[sl] = cur;
+        rep[sl] = 1;
       }
-#pragma unroll
-      for (int q = 0; q < BATCH; q++)
-        if (k[q] != FRB_EMPTY) sink.commit(k[q], cnt[q], home[q], &inserted);
-    }
-  };
-  auto after_tile = [&](size_t k) {
-    if ((k % HIST_SYNC_TILES) != HIST_SYNC_TILES - 1) return;
-    if (claimed) { atomicAdd(&s_claims, claimed); claimed = 0; }
-    consumer_bar();
-    const bool flush = s_claims >= HIST_FLUSH_CLAIMS || ++syncs_since_flush >= HIST_FLUSH_SYNCS;  // the same in every warp
-    consumer_bar();
-    if (flush) {
-      drain();
-      if (threadIdx.x == 0) s_claims = 0;
-      syncs_since_flush = 0;
-      consumer_bar();
     }
   };
 
   const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
-  stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, after_tile);
+  stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, [](size_t) {});
   if (consumer) {
+    // what the lanes still hold, what is still queued, then the map itself
 #pragma unroll
-    for (int u = 0; u < STREAM_ROWS; u++)
-      if (rep[u] != 0) flush_vec(pat[u], rep[u]);
-    consumer_bar();
-    drain();
+    for (int u = 0; u < STREAM_ROWS; u++) retire(rep[u] != 0, pat[u], rep[u]);
+    if (qn > 0) inserted += hist_process<W>(qhead, qn, sink, log);
+    __syncwarp();
+    for (int i = lane; i < HIST_WMAP; i += 32) {
+      const u64 k = hs_key[warp][i];
+      hist_emit(k, hs_cnt[warp][i], k != FRB_EMPTY, sink, log, &inserted);
+    }
+    if (Sink::USE_LOG && log.cap && lane == 0) log.counts[blockIdx.x * STREAM_WARPS + warp] = hs_logpos[warp];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
+  if (count_target) block_add_to(count_target, inserted);
+}
+
+// Fold the eviction logs of all warps into the label table: four records per thread, their home-slot keys
+// read together (one L2 round trip for the four), then a label already sitting in its home slot costs one
+// fire-and-forget reduction; first sightings and collisions take the probing path.
+__global__ void __launch_bounds__(256) k_hist_apply_log(HistLog log, unsigned int regions, HashSink sink, u64* count_target) {
+  unsigned int inserted = 0;
+  for (unsigned int r = blockIdx.x; r < regions; r += gridDim.x) {
+    const unsigned int cnt = log.counts[r];
+    const ulonglong2* rec = log.records + (size_t)r * log.cap;
+    for (unsigned int i0 = threadIdx.x; i0 < cnt; i0 += 4 * 256) {
+      ulonglong2 v[4];
+      u64 home[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned int i = i0 + q * 256;
+        v[q] = make_ulonglong2(FRB_EMPTY, 0ull);
+        if (i < cnt) {
+          asm("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v[q].x), "=l"(v[q].y) : "l"(rec + i));
+          home[q] = sink.peek(v[q].x);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (i0 + q * 256 < cnt) sink.commit(v[q].x, (unsigned int)v[q].y, home[q], &inserted);
+    }
+  }
   if (count_target) block_add_to(count_target, inserted);
 }
 
@@ -451,6 +623,32 @@ using namespace frb;
 
 extern "C" {
 
+// eviction-log workspace: [counts: regions x u32 | flags: 256 B | records: regions x cap x 16 B]
+static inline unsigned int hist_regions_max() { return (unsigned int)sm_count() * 4u * STREAM_WARPS; }  // >= any k_hist grid x 8
+static inline size_t hist_counts_bytes() { return align_up((size_t)hist_regions_max() * sizeof(unsigned int), 256); }
+static inline unsigned int hist_log_cap(size_t n) {
+  // records per warp: a record stands for a segment cross-section, tens to hundreds of voxels; 1/16 of the
+  // warp's share of the volume, between 256 and 4096 records (64 KiB) -- beyond that the warp updates the table itself
+  const size_t share = n / hist_regions_max() / 16;
+  return (unsigned int)(share < 256 ? 256 : (share > 4096 ? 4096 : share));
+}
+size_t frb_hist_ws_bytes(size_t n) { return hist_counts_bytes() + 256 + (size_t)hist_regions_max() * hist_log_cap(n) * sizeof(ulonglong2); }
+
+static HistLog hist_log_of(void* ws, size_t ws_bytes, size_t n) {
+  HistLog log;
+  log.records = nullptr;
+  log.counts = nullptr;
+  log.flags = nullptr;
+  log.cap = 0;
+  if (ws && ws_bytes >= frb_hist_ws_bytes(n)) {
+    log.counts = (unsigned int*)ws;
+    log.flags = (unsigned int*)((char*)ws + hist_counts_bytes());
+    log.records = (ulonglong2*)((char*)ws + hist_counts_bytes() + 256);
+    log.cap = hist_log_cap(n);
+  }
+  return log;
+}
+
 int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64_t* counts, uint64_t bins, uint64_t row_bytes, void* stream) {
   if (!dtype_ok(dtype) || !counts || bins == 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_dense: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
@@ -463,10 +661,11 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   const size_t tiles = stream_tiles(n, w);
   const uint4* p = (const uint4*)a;
   // the dense strategy is only ever forced (tests, comparisons): two geometries are enough
+  const HistLog nolog = hist_log_of(nullptr, 0, n);
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
 #define FRB_KHD(WW, VV) k_hist<WW, DenseSink, 8, 4, VV><<<stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv)
+    p, n, sink, nolog, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv)
 #define FRB_KHD_GEO(WW) if (tv != STREAM_TILE_VECS) { FRB_KHD(WW, true); } else { FRB_KHD(WW, false); }
   switch (w) {
     case 1: FRB_KHD_GEO(1) break;
@@ -479,8 +678,12 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   return check_launch("k_hist<dense>");
 }
 
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream) {
-  if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a)))) { set_error("frb_hist_hash: bad arguments"); return FRB_ERR_BAD_ARG; }
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* ws,
+                  size_t ws_bytes, void* stream) {
+  if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a))) || (ws && (!aligned16(ws) || ws_bytes < frb_hist_ws_bytes(n)))) {
+    set_error("frb_hist_hash: bad arguments (ws must hold frb_hist_ws_bytes(n), or be NULL)");
+    return FRB_ERR_BAD_ARG;
+  }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(dtype);
   HashSink sink;
@@ -495,8 +698,10 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
+  const HistLog log = hist_log_of(ws, ws_bytes, n);
+  if (log.cap) cudaMemsetAsync(ws, 0, hist_counts_bytes() + 256, st);  // regions that no warp owns in this launch stay empty
 #define FRB_KH(WW, II, DD, VV) k_hist<WW, HashSink, II, DD, VV><<<stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv)
+    p, n, sink, log, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv)
 #define FRB_KH_GEO(WW)                                                        \
   if (geo.tv != STREAM_TILE_VECS) { FRB_KH(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_KH(WW, 4, 1, false); }                          \
@@ -514,8 +719,30 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   }
 #undef FRB_KH_GEO
 #undef FRB_KH
-  return check_launch("k_hist<hash>");
+  int rc = check_launch("k_hist<hash>");
+  if (rc || !log.cap) return rc;
+  return frb_hist_apply_log(ws, ws_bytes, n, dtype, slots, cap, meta, stream);
 }
+
+// second step of frb_hist_hash (which calls it itself): fold the eviction logs in ws into the table.  Callable again
+// on a bigger, freshly initialised table when the first one overflowed -- provided ws says that no warp bypassed its
+// log (frb_hist_log_complete): the logs then hold everything the pass over the volume produced.
+int frb_hist_apply_log(const void* ws, size_t ws_bytes, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream) {
+  if (!dtype_ok(dtype) || !ws || ws_bytes < frb_hist_ws_bytes(n) || !slots || !meta || (cap & (cap - 1)) != 0) { set_error("frb_hist_apply_log: bad arguments"); return FRB_ERR_BAD_ARG; }
+  const int w = dtype_width(dtype);
+  HashSink sink;
+  sink.slots = (Slot*)slots;
+  sink.mask = cap - 1;
+  sink.direct = w <= 2 ? 1 : 0;
+  sink.meta = (u64*)meta;
+  const HistLog log = hist_log_of((void*)ws, ws_bytes, n);
+  const unsigned int regions = hist_regions_max();
+  k_hist_apply_log<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(log, regions, sink, &((u64*)meta)[FRB_META_COUNT]);
+  return check_launch("k_hist_apply_log");
+}
+
+// byte offset inside ws of the 32-bit flag word: 0 after a pass = every eviction went through the logs
+size_t frb_hist_ws_flags_offset(void) { return hist_counts_bytes(); }
 
 size_t frb_compact_bins_ws_bytes(uint64_t bins) { return (size_t)compact_blocks((size_t)bins) * sizeof(u64) + 256; }
 

@@ -259,10 +259,12 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None, row_bytes=0
   L = _lib.load()
   dtype = np.dtype(dtype)
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), 0)
+  ws_bytes = int(L.frb_hist_ws_bytes(n_local))
+  ws = D.alloc(ws_bytes)
 
   def build_local(t):
-    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), row_bytes, D.stream()),
-               "frb_hist_hash")
+    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), row_bytes, D.ptr(ws), ws_bytes,
+                               D.stream()), "frb_hist_hash")
 
   api._run_build(build_local, local)
   keys, counts = allgather_pairs(*_export_pairs(local), group)

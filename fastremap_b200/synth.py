@@ -47,6 +47,19 @@ def synth_numpy(shape, grid, dtype, seed=0, zero_frac=0.1, noise=0.0, z0=0, nz_t
   c = (cz[:, None, None] * np.uint64(gy) + cy[None, :, None]) * np.uint64(gx) + cx[None, None, :]
   zero_thresh = int(zero_frac * 16777216.0)
   noise_thresh = int(noise * 16777216.0)
+  if not noise_thresh and nz * ny * nx > 4 * gz * gy * gx:
+    # no per-voxel noise: a voxel's label is its cell's label, so hash the cells once and upsample;
+    # z-planes inside one layer of cells are copies of each other
+    table = synth_cell_labels(grid, dtype, seed, zero_frac, cell_div)
+    out = np.empty((nz, ny, nx), dtype=dtype)
+    iy, ix = cy.astype(np.intp)[:, None], cx.astype(np.intp)[None, :]
+    prev, plane = None, None
+    for z in range(nz):
+      layer = int(cz[z])
+      if layer != prev:
+        plane, prev = table[layer][iy, ix], layer
+      out[z] = plane
+    return out
   if noise_thresh:
     flat = (zg[:, None, None] * np.uint64(ny) + y[None, :, None]) * np.uint64(nx) + x[None, None, :]
     hn = _mix(seed + 2, flat)
@@ -59,6 +72,12 @@ def synth_numpy(shape, grid, dtype, seed=0, zero_frac=0.1, noise=0.0, z0=0, nz_t
   if zero_thresh:
     label = np.where((_mix(seed + 1, c) >> np.uint64(40)) < np.uint64(zero_thresh), np.uint64(0), label)
   return np.ascontiguousarray(label.astype("u%d" % dtype.itemsize).view(dtype))
+
+
+def synth_cell_labels(grid, dtype, seed=0, zero_frac=0.1, cell_div=1) -> np.ndarray:
+  """(gz, gy, gx) array: the label every voxel of cell (cz, cy, cx) carries in a noise-free volume."""
+  gz, gy, gx = (int(g) for g in grid)
+  return synth_numpy((gz, gy, gx), (gz, gy, gx), dtype, seed=seed, zero_frac=zero_frac, noise=0.0, cell_div=cell_div)
 
 
 def synth_device(shape, grid, dtype, seed=0, zero_frac=0.1, noise=0.0, z0=0, nz_total=None, cell_div=1):

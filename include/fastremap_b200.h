@@ -200,7 +200,17 @@ size_t frb_compact_bins_ws_bytes(uint64_t bins);
 int frb_compact_bins_count(const uint64_t* counts, uint64_t bins, uint64_t* meta, void* ws, size_t ws_bytes, void* stream);
 int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint64_t min_bits, void* uniq_out,
                           uint64_t* counts_out, size_t capacity, const void* ws, void* stream);
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* stream);
+/* hash strategy (fastremap.pyx:1003-1022 builds the same label -> count map through renumber + a dense histogram).
+ * The pass over the volume aggregates in registers and shared memory and APPENDS what it evicts to per-warp logs in
+ * ws (frb_hist_ws_bytes(n) bytes; NULL: update the table from inside the pass instead -- slower); the logs are then
+ * folded into the table (frb_hist_apply_log, called by frb_hist_hash itself).  If the table overflows and the flag
+ * word at ws + frb_hist_ws_flags_offset() is 0, frb_hist_apply_log on a bigger table finishes the job without a
+ * second pass over the volume. */
+size_t frb_hist_ws_bytes(size_t n);
+size_t frb_hist_ws_flags_offset(void);
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* ws,
+                  size_t ws_bytes, void* stream);
+int frb_hist_apply_log(const void* ws, size_t ws_bytes, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream);
 size_t frb_sort_pairs_ws_bytes(size_t L);
 /* sort exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are
  * clobbered) and emit typed keys + values.  L = number of pairs, or -- count_dev != NULL -- the
