@@ -78,7 +78,7 @@ def main():
       report("minmax+pixel_pairs u64 (K6)", n, 8, m, mn)
     del vol
     if "unique_dense" in ops:
-      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4), args.reps)
+      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, incl. minmax pre-pass (config 2a)", n, 4, m, mn, n_unique=out[2])
       m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, strategy="hash", row_bytes=S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, forced hash strategy", n, 4, m, mn, n_unique=out[2])
@@ -86,8 +86,10 @@ def main():
 
   if "unique_sparse" in ops:
     vol = flat_u8(synth_device((S, S, S), (max(int(100 * sc), 1),) * 3, np.uint32, seed=1, zero_frac=0.1))
-    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4), args.reps)
+    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), args.reps)
     report("unique(return_counts) u32 sparse ids, incl. minmax pre-pass (config 2b)", n, 4, m, mn, n_unique=out[2])
+    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4), args.reps)
+    report("unique(return_counts) u32 sparse ids, linear walk (no plane hint)", n, 4, m, mn, n_unique=out[2])
     if S <= 512:
       m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, strategy="sort"), max(args.reps // 2, 1))
       report("unique(return_counts) u32 sparse ids, forced sort strategy", n, 4, m, mn, n_unique=out[2])

@@ -26,6 +26,6 @@ dense = api.renumber_device(flat_u8(vol).clone(), n, np.uint64).out
 del vol
 for r in runs:
   L.frb_set_tile_run(r)
-  ms, mn, out = timed(lambda: api.unique_counts_device(sparse, n, np.uint32, row_bytes=S * 4), 5)
-  md, mnd, outd = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4), 5)
+  ms, mn, out = timed(lambda: api.unique_counts_device(sparse, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), 5)
+  md, mnd, outd = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), 5)
   print(json.dumps({"tile_run": r, "unique_sparse_ms": ms, "unique_dense_ms": md, "n_sparse": out[2], "n_dense": outd[2]}), flush=True)

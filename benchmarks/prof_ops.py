@@ -29,7 +29,7 @@ def flat_u8(t):
 if "unique_sparse" in ops:
   vol = flat_u8(synth_device((S, S, S), (max(int(100 * sc), 1),) * 3, np.uint32, seed=1, zero_frac=0.1))
   for _ in range(2):
-    out = api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4)
+    out = api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4)
   print("unique_sparse", out[2])
   del vol
 
@@ -39,7 +39,7 @@ if "unique_dense" in ops:
   dense = res.out
   del vol
   for _ in range(2):
-    out = api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4)
+    out = api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4)
   print("unique_dense", out[2])
   del dense, res
 

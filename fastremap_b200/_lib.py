@@ -38,6 +38,7 @@ SIGNATURES = {
   "frb_table_insert_gathered": (_i, [_vp, _u64, _i, _vp, _i, _i, _vp, _u64, _vp, _vp]),
   "frb_table_insert_packed": (_i, [_vp, _u64, _i, _u64, _i, _i, _vp, _u64, _vp, _vp]),
   "frb_table_resolve": (_i, [_vp, _i, _vp, _u64, _vp, _vp]),
+  "frb_table_project": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
   "frb_table_export": (_i, [_vp, _u64, _vp, _vp, _vp, _sz, _vp]),
   "frb_minmax_pairs": (_i, [_vp, _sz, _i, _vp, _vp]),
   "frb_renumber_build": (_i, [_vp, _sz, _i, _u64, _i, _vp, _u64, _vp, _u64, _vp]),
@@ -58,7 +59,7 @@ SIGNATURES = {
   "frb_compact_bins_emit": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _sz, _vp, _vp]),
   "frb_hist_ws_bytes": (_sz, [_sz]),
   "frb_hist_ws_flags_offset": (_sz, []),
-  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _u64, _vp, _sz, _vp]),
+  "frb_hist_hash": (_i, [_vp, _sz, _i, _vp, _u64, _vp, _u64, _u64, _vp, _sz, _vp]),
   "frb_hist_apply_log": (_i, [_vp, _sz, _sz, _i, _vp, _u64, _vp, _vp]),
   "frb_sort_pairs_ws_bytes": (_sz, [_sz]),
   "frb_sort_table_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

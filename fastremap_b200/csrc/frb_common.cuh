@@ -443,17 +443,27 @@ __device__ __forceinline__ constexpr int ref_slot_ct(int u) {
 // ~10^7 of them, and the read-only streaming loops are issue-bound (64-bit adds are two instructions and two
 // registers each).  64-bit (TileMap64): what K3 was tuned with -- its code generation is touchy, and with the
 // 32-bit iterator k_relabel_auto<8> measured 3.75 ms instead of 3.52 ms.
+struct PlaneWalk {  // see plane_walk_for (host) and TileMapT's second constructor
+  unsigned int plane_tiles, planes, band;
+};
 template <typename IDX>
 struct TileMapT {
   IDX tiles;   // tiles in the whole array
   IDX run;     // consecutive tiles per run
   IDX count;   // tiles owned by this CTA
   IDX tv;      // vectors per tile: STREAM_TILE_VECS, or less when a tile is a whole number of volume rows
+  IDX first;   // first tile of this CTA (forward walks)
+  IDX jump;    // distance from the last tile of a run to the first tile of this CTA's next run, minus 1
+  // linear walk: runs of `run` tiles dealt round-robin to the CTAs
   __device__ __forceinline__ TileMapT(size_t nvec, size_t run_, size_t tile_vecs = STREAM_TILE_VECS) {
     tv = tile_vecs < 32 || tile_vecs > (size_t)STREAM_TILE_VECS ? (IDX)STREAM_TILE_VECS : (IDX)tile_vecs;
     tiles = (IDX)((nvec + tv - 1) / tv);
     if (sizeof(IDX) == 8) run = run_ < 1 ? (IDX)1 : (IDX)run_;  // (exactly the code K3 was tuned with)
     else run = run_ < 1 ? (IDX)1 : (run_ > (size_t)tiles ? (tiles ? tiles : (IDX)1) : (IDX)run_);  // clamp: products below stay in 32 bits
+    if (sizeof(IDX) != 8) {  // the 64-bit iterator derives these itself (K3's tuned code path, left as it was)
+      first = (IDX)blockIdx.x * run;
+      jump = ((IDX)gridDim.x - 1) * run;
+    }
     const IDX nruns = (tiles + run - 1) / run;
     const IDX b = blockIdx.x, g = gridDim.x;
     const IDX mine = nruns > b ? (nruns - b + g - 1) / g : 0;  // runs owned by this CTA
@@ -461,6 +471,24 @@ struct TileMapT {
     const IDX last_start = ((mine - 1) * g + b) * run;
     const IDX last_len = tiles - last_start < run ? tiles - last_start : run;
     count = (mine - 1) * run + last_len;
+  }
+  // Plane walk (forward only; the host checks the preconditions, see plane_walk_ok): the array is `planes` planes of
+  // `plane_tiles` full tiles; a CTA owns ONE band of `band` consecutive tiles (the same rows) of a stack of
+  // consecutive planes and walks it plane after plane.  What a warp has aggregated for the segments of its band
+  // is still in its shared-memory map when the same segments come round again one plane deeper, so a segment
+  // costs one global update per CTA instead of one per plane.  gridDim.x >= plane_tiles / band.
+  __device__ __forceinline__ explicit TileMapT(const PlaneWalk& pw) {
+    const IDX plane_tiles = pw.plane_tiles, planes = pw.planes, band = pw.band;
+    tv = (IDX)STREAM_TILE_VECS;
+    tiles = plane_tiles * planes;
+    run = band;
+    jump = plane_tiles - band;
+    const IDX bands = plane_tiles / band;                  // bands per plane
+    const IDX b = (IDX)blockIdx.x % bands, g = (IDX)blockIdx.x / bands;
+    const IDX stacks = ((IDX)gridDim.x - b + bands - 1) / bands;  // CTAs that share band b: they split the planes
+    const IDX z0 = (IDX)(((size_t)planes * g) / stacks), z1 = (IDX)(((size_t)planes * (g + 1)) / stacks);
+    first = z0 * plane_tiles + b * band;
+    count = (z1 - z0) * band;
   }
 };
 // walks the tiles of one CTA in ascending (or descending) order with additions only
@@ -473,16 +501,16 @@ struct TileIterT {
   template <bool REVERSE>
   __device__ __forceinline__ void init(const TileMapT<IDX>& m) {
     run = m.run;
-    jump = ((IDX)gridDim.x - 1) * m.run;
+    jump = sizeof(IDX) == 8 ? ((IDX)gridDim.x - 1) * m.run : m.jump;
     const IDX nruns_mine = (m.count + m.run - 1) / m.run;
     const IDX last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
-    if (REVERSE) {
+    if (REVERSE) {  // linear walks only
       const IDX r = nruns_mine ? nruns_mine - 1 : 0;
       o = last_len ? last_len - 1 : 0;
       t = (r * gridDim.x + blockIdx.x) * run + o;
     } else {
       o = 0;
-      t = (IDX)blockIdx.x * run;
+      t = sizeof(IDX) == 8 ? (IDX)blockIdx.x * run : m.first;
     }
   }
   __device__ __forceinline__ size_t tile() const { return (size_t)t; }
@@ -716,6 +744,26 @@ inline int fair_run(int grid, size_t tiles) {
   const size_t fair = tiles / (2 * (size_t)(grid < 1 ? 1 : grid));
   const size_t run = (size_t)tile_run();
   return (int)(run > fair ? (fair < 1 ? 1 : fair) : run);
+}
+
+// Plane walk of a read-only streaming kernel (TileMapT's second constructor): possible when the array is a whole
+// number of planes, a plane a whole number of 16 KiB tiles, the grid has a CTA for every band of a plane, and
+// every CTA gets a stack of at least 4 planes (otherwise nothing comes round again).  Returns the band length in
+// tiles (0: walk linearly).  Bands are 8 tiles (128 KiB contiguous, 32 rows of a 1024-wide uint32 volume): short
+// enough for a warp's 128-entry map to hold the segments that cross its columns of the band.
+inline PlaneWalk plane_walk_for(size_t nbytes, size_t plane_bytes, int grid) {
+  PlaneWalk pw = {0, 0, 0};
+  const size_t tile_bytes = (size_t)STREAM_TILE_VECS * 16;
+  if (plane_bytes == 0 || plane_bytes % tile_bytes != 0 || nbytes % plane_bytes != 0) return pw;
+  const size_t pt = plane_bytes / tile_bytes, planes = nbytes / plane_bytes;
+  const size_t band = 8;
+  if (pt % band != 0 || pt / band > (size_t)grid || pt > (1u << 20) || planes > (1u << 20)) return pw;
+  const size_t stacks = (size_t)grid / (pt / band);   // CTAs per band (at least)
+  if (planes / (stacks + 1) < 4) return pw;
+  pw.plane_tiles = (unsigned int)pt;
+  pw.planes = (unsigned int)planes;
+  pw.band = (unsigned int)band;
+  return pw;
 }
 
 // Persistent grid for a streaming kernel (STREAM_THREADS threads, STREAM_SMEM_BYTES of dynamic shared memory):

@@ -130,6 +130,33 @@ k_table_insert_packed(const u64* __restrict__ packed, u64 m, int world, u64 loca
   block_add_to(&meta[FRB_META_COUNT], inserted);
 }
 
+// Project a list of keys through one (hashed) table into another: dst[key] = src[key] for every listed key that
+// src holds.  Used by the multi-GPU renumber: after K2 every rank copies the global ranks of ITS OWN labels from the
+// merged table into a compact lookup table for K3.  The list length may still be on the device (count_dev).
+__global__ void __launch_bounds__(256)
+k_table_project(const u64* __restrict__ keys, const u64* __restrict__ count_dev, u64 max_count, const Slot* __restrict__ src, u64 src_mask,
+                const u64* __restrict__ src_meta, Slot* dst, u64 dst_mask, u64* dst_meta) {
+  if (__ldcg(&src_meta[FRB_META_OVERFLOW]) != 0) {  // the merge failed (sizes guessed too small): park what is queued behind
+    if (blockIdx.x == 0 && threadIdx.x == 0) atom_exch_u64(&dst_meta[FRB_META_OVERFLOW], 1ull);
+    return;
+  }
+  u64 n = max_count;
+  if (count_dev) {
+    const u64 c = __ldcg(count_dev);
+    n = c < n ? c : n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) dst_meta[FRB_META_ASSIGNED] = __ldcg(&src_meta[FRB_META_ASSIGNED]);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned int inserted = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 key = keys[i];
+    u64 val = 0;
+    if (table_find_from(src, src_mask, src_meta, key, home_slot(key, src_mask), &val))
+      table_update<FRB_OP_SET>(dst, dst_mask, 0, dst_meta, key, val, &inserted);
+  }
+  block_add_to(&dst_meta[FRB_META_COUNT], inserted);
+}
+
 __global__ void __launch_bounds__(256)
 k_table_resolve(const void* __restrict__ vals, int vw, Slot* slots, u64 cap, u64* meta) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -269,6 +296,18 @@ int frb_table_insert_packed(const uint64_t* packed, uint64_t m, int world, uint6
     default: set_error("frb_table_insert_packed: bad op"); return FRB_ERR_BAD_ARG;
   }
   return check_launch("k_table_insert_packed");
+}
+
+int frb_table_project(const uint64_t* keys, const uint64_t* count_dev, uint64_t max_count, const void* src_slots, uint64_t src_cap,
+                      const uint64_t* src_meta, void* dst_slots, uint64_t dst_cap, uint64_t* dst_meta, void* stream) {
+  if (!keys || !src_slots || !src_meta || !dst_slots || !dst_meta || (src_cap & (src_cap - 1)) != 0 || (dst_cap & (dst_cap - 1)) != 0 || max_count == 0) {
+    set_error("frb_table_project: bad arguments (hashed tables, power-of-two capacities)");
+    return FRB_ERR_BAD_ARG;
+  }
+  Grid g = grid_for((size_t)max_count, 256 * 2, 8);
+  k_table_project<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>((const u64*)keys, (const u64*)count_dev, max_count, (const Slot*)src_slots,
+                                                                    src_cap - 1, (const u64*)src_meta, (Slot*)dst_slots, dst_cap - 1, (u64*)dst_meta);
+  return check_launch("k_table_project");
 }
 
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream) {

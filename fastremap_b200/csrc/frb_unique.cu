@@ -82,6 +82,8 @@ __shared__ unsigned int hs_qrep[STREAM_WARPS][HIST_QUEUE];
 __shared__ __align__(16) u64 hs_key[STREAM_WARPS][HIST_WMAP];
 __shared__ unsigned int hs_cnt[STREAM_WARPS][HIST_WMAP];
 __shared__ unsigned int hs_logpos[STREAM_WARPS];  // records the warp has appended to its log region
+__shared__ unsigned char hs_claim[STREAM_WARPS][HIST_WMAP / 2];  // per set: the lane that may install a new label this round
+__shared__ unsigned char hs_mru[STREAM_WARPS][HIST_WMAP / 2];    // per set: the way that was used last
 
 // Eviction log.  What a warp's map evicts does not go to the label table from inside the streaming loop:
 // an update of the table is a dependent L2 round trip (read the home slot, then add), and a warp that
@@ -122,19 +124,26 @@ __device__ __noinline__ HistEvicted hist_map_add(u64 key, unsigned int c, bool a
       k1 = kk.y;
     }
     if (act && (k0 == key || k1 == key)) {
-      atomicAdd(&s_cnt[e0 + (k0 == key ? 0u : 1u)], c);
+      const unsigned int way = k0 == key ? 0u : 1u;
+      atomicAdd(&s_cnt[e0 + way], c);
+      hs_mru[warp][e0 >> 1] = (unsigned char)way;
       act = false;
     }
     __syncwarp();
-    // the lanes left want a set that does not hold their label: one of them per set installs it
-    const unsigned int m = __match_any_sync(FRB_FULL_MASK, act ? e0 : (0x80000000u | (unsigned int)lane));
-    if (act && (__ffs(m) - 1) == lane) {
-      // victim: a free way, else the way with the SMALLER partial count.  Labels that keep coming back (the
-      // background, segments much larger than a tile) hold large counts and stay put; with plain direct
-      // mapping every 128th new label evicted the background's entry, and the ~650 k background records of a
-      // 1024^3 volume then queued up on ONE table slot (same-address atomics serialise in L2: apply pass 0.6 ms)
+    // the lanes left want a set that does not hold their label: one of them per set installs it.  The winner is
+    // whoever's lane number survives in the set's claim byte (match.any did the same job at ~10x the latency)
+    if (act) hs_claim[warp][e0 >> 1] = (unsigned char)lane;
+    __syncwarp();
+    if (act && hs_claim[warp][e0 >> 1] == (unsigned char)lane) {
+      // victim: a free way, else the way that was NOT used last.  Labels that keep coming back (the background,
+      // segments much larger than a tile, and -- on a plane walk -- everything that continues one plane deeper)
+      // stay; what has ended leaves.  (Plain direct mapping evicted the background's entry with every 128th new
+      // label, and the ~650 k background records of a 1024^3 volume then queued up on ONE table slot: same-address
+      // atomics serialise in L2.  "Keep the larger count" protected the background but let dead segments with
+      // large counts squat in the sets for the rest of a plane walk.)
       const unsigned int c0 = s_cnt[e0], c1 = s_cnt[e0 + 1];
-      const unsigned int v = k0 == FRB_EMPTY ? 0u : (k1 == FRB_EMPTY ? 1u : (c0 <= c1 ? 0u : 1u));
+      const unsigned int v = k0 == FRB_EMPTY ? 0u : (k1 == FRB_EMPTY ? 1u : (hs_mru[warp][e0 >> 1] ? 0u : 1u));
+      hs_mru[warp][e0 >> 1] = (unsigned char)v;
       ev.key = v ? k1 : k0;
       ev.cnt = v ? c1 : c0;
       s_key[e0 + v] = key;
@@ -232,6 +241,7 @@ __device__ __noinline__ unsigned int hist_process(int qhead, int count, const Si
   unsigned int pend = has ? (ends | (tail_ends ? 1u << (V - 1) : 0u)) : 0u;  // element positions at which a run ends in this lane
 
   int start = 0;  // first element of the lane's next run
+  bool first_round = true;
   while (__any_sync(FRB_FULL_MASK, pend != 0)) {
     bool act = pend != 0;
     const int j = act ? __ffs(pend) - 1 : 0;
@@ -252,7 +262,15 @@ __device__ __noinline__ unsigned int hist_process(int qhead, int count, const Si
     ev.key = act ? key : FRB_EMPTY;
     ev.cnt = total;
 #else
-    ev = hist_map_add(key, total, act);
+    if (first_round) {
+      ev = hist_map_add(key, total, act);
+    } else {
+      // a lane's second, third ... run end: segments narrower than a 16-byte vector.  They bypass the map (a map
+      // call costs ~100 warp instructions whether 1 or 32 lanes take part) and go to the log as they are
+      ev.key = act ? key : FRB_EMPTY;
+      ev.cnt = total;
+    }
+    first_round = false;
 #endif
     hist_emit(ev.key, ev.cnt, ev.key != FRB_EMPTY, sink, log, &inserted);
   }
@@ -261,7 +279,8 @@ __device__ __noinline__ unsigned int hist_process(int qhead, int count, const Si
 
 template <int W, typename Sink, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, const __grid_constant__ Sink sink,
-                                                            const __grid_constant__ HistLog log, u64* count_target, int run, int tile_vecs) {
+                                                            const __grid_constant__ HistLog log, u64* count_target, int run, int tile_vecs,
+                                                            PlaneWalk pw) {
   constexpr int V = 16 / W;
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,7 +336,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
     }
   };
 
-  const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+  const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw)
+                                             : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
   stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, [](size_t) {});
   if (consumer) {
     // what the lanes still hold, what is still queued, then the map itself
@@ -334,6 +354,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
   if (count_target) block_add_to(count_target, inserted);
+}
+
+// Pull a table into L2 (one prefetch per 128-byte line, nothing lands in a register).  The counting pass has
+// just streamed the whole volume through L2, so the table initialised before it is back in HBM; folding the
+// logs into it is millions of RANDOM 32-byte accesses, which HBM serves at a small fraction of its streaming
+// rate (measured: 0.31 ms for 3.1 M records into a 64 MiB table, against 0.05 ms when the table is cache-resident).
+__global__ void __launch_bounds__(256) k_prefetch_l2(const char* base, size_t bytes) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 128;
+  for (size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes; off += stride)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
 // Fold the eviction logs of all warps into the label table: four records per thread, their home-slot keys
@@ -662,10 +692,11 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   const uint4* p = (const uint4*)a;
   // the dense strategy is only ever forced (tests, comparisons): two geometries are enough
   const HistLog nolog = hist_log_of(nullptr, 0, n);
+  const PlaneWalk nowalk = {0, 0, 0};
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
 #define FRB_KHD(WW, VV) k_hist<WW, DenseSink, 8, 4, VV><<<stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, nolog, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv)
+    p, n, sink, nolog, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv, nowalk)
 #define FRB_KHD_GEO(WW) if (tv != STREAM_TILE_VECS) { FRB_KHD(WW, true); } else { FRB_KHD(WW, false); }
   switch (w) {
     case 1: FRB_KHD_GEO(1) break;
@@ -678,8 +709,8 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   return check_launch("k_hist<dense>");
 }
 
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* ws,
-                  size_t ws_bytes, void* stream) {
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes,
+                  uint64_t plane_bytes, void* ws, size_t ws_bytes, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!a || !aligned16(a))) || (ws && (!aligned16(ws) || ws_bytes < frb_hist_ws_bytes(n)))) {
     set_error("frb_hist_hash: bad arguments (ws must hold frb_hist_ws_bytes(n), or be NULL)");
     return FRB_ERR_BAD_ARG;
@@ -701,7 +732,8 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   const HistLog log = hist_log_of(ws, ws_bytes, n);
   if (log.cap) cudaMemsetAsync(ws, 0, hist_counts_bytes() + 256, st);  // regions that no warp owns in this launch stay empty
 #define FRB_KH(WW, II, DD, VV) k_hist<WW, HashSink, II, DD, VV><<<stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, log, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv)
+    p, n, sink, log, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv, \
+    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles)))
 #define FRB_KH_GEO(WW)                                                        \
   if (geo.tv != STREAM_TILE_VECS) { FRB_KH(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_KH(WW, 4, 1, false); }                          \
@@ -737,6 +769,12 @@ int frb_hist_apply_log(const void* ws, size_t ws_bytes, size_t n, int dtype, voi
   sink.meta = (u64*)meta;
   const HistLog log = hist_log_of((void*)ws, ws_bytes, n);
   const unsigned int regions = hist_regions_max();
+  const size_t table_bytes = (size_t)cap * sizeof(Slot);
+  if (table_bytes <= ((size_t)96 << 20)) {  // fits the 126 MB L2 next to the log records that stream through
+    k_prefetch_l2<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>((const char*)slots, table_bytes);
+    int rc = check_launch("k_prefetch_l2");
+    if (rc) return rc;
+  }
   k_hist_apply_log<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(log, regions, sink, &((u64*)meta)[FRB_META_COUNT]);
   return check_launch("k_hist_apply_log");
 }

@@ -260,10 +260,16 @@ class ChunkUploader:
       raise self.error
 
   def abort(self):
-    """Wait for the worker without raising (cleanup path; the copies it queued are harmless)."""
+    """Wait for the worker and for the copies it queued, without raising (cleanup path): the device buffer and the
+    staging buffers go back to the caching allocators right after, and a copy still in flight on this stream would
+    be writing into memory that the next allocation on another stream may be handed."""
     if self.thread is not None:
       self.thread.join()
       self.thread = None
+    try:
+      self.stream.synchronize()
+    except Exception:
+      pass
 
 
 class ChunkDownloader:
@@ -347,11 +353,16 @@ class ChunkDownloader:
       raise self.error
 
   def abort(self):
-    """Stop the worker without raising (cleanup path; no-op after finish())."""
+    """Stop the worker and drain the copies it queued, without raising (cleanup path; cheap after finish()): see
+    ChunkUploader.abort."""
     if self.thread is not None:
       self.q.put(None)
       self.thread.join()
       self.thread = None
+    try:
+      self.stream.synchronize()
+    except Exception:
+      pass
 
 
 def upload_bytes(flat_np: np.ndarray) -> torch.Tensor:
@@ -423,10 +434,24 @@ class Vol:
     return row_bytes(self.shape, self.order, self.dtype)
 
 
+  @property
+  def plane_bytes(self):
+    """Bytes per plane of the two fastest-varying axes (0 for arrays of fewer than 3 axes): a hint for the
+    plane walk of the counting kernel."""
+    return plane_bytes(self.shape, self.order, self.dtype)
+
+
 def row_bytes(shape, order, dtype) -> int:
   if len(shape) == 0:
     return 0
   return int(shape[0] if order == "F" else shape[-1]) * np.dtype(dtype).itemsize
+
+
+def plane_bytes(shape, order, dtype) -> int:
+  if len(shape) < 3:
+    return 0
+  a, b = (shape[0], shape[1]) if order == "F" else (shape[-1], shape[-2])
+  return int(a) * int(b) * np.dtype(dtype).itemsize
 
 
 def ingest(arr, alias_ok: bool = False) -> Vol:

@@ -86,24 +86,49 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     offset, total = shard_offsets(n_local, group)
 
   api._ev(timers, "init", 0)
+  # volumes of one job look alike: the previous call's exchange sizes AND the local table size it ended up with are
+  # remembered per (group, world, dtype, slab size, hint), so a table that had to grow once starts grown next time
+  key = (id(group), world, dtype.str, int(n_local), max_labels)
+  guess = _exchange_guess.get(key)
   local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), _lib.EMPTY)
+  if guess is not None and not local.direct and guess[2] > local.cap:
+    local.cap = guess[2]
+    local.slots = D.alloc(local.cap * 16)
+    local.clear()
   api._ev(timers, "init", 1)
   limits = api._narrow_limits(dtype, start, int(total))
-  key = (id(group), world, dtype.str, int(n_local), local.cap)
-  guess = _exchange_guess.get(key)
   if guess is not None and limits is not None:
     res = _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero, write_wide, group, world, offset, total, timers,
                                      row_bytes, local, limits, guess, key)
     if res is not None:
       return res
     # the guess was too small (or a table overflowed): nothing was written, take the two-phase path
+
+  def build(t):
+    api._ev(timers, "k1", 0)
+    _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(t.slots),
+                                    t.cap, D.ptr(t.meta), row_bytes, D.stream()), "frb_renumber_build")
+    api._ev(timers, "k1", 1)
+
+  merged, counts, own_keys = _two_phase_merge(build, local, dtype, group, world, timers)
+  _exchange_guess[key] = _guess_from(counts, local.cap)
+  return _rank_and_relabel(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, own_keys, counts[dist.get_rank(group)],
+                           total, limits, timers)
+
+
+def _two_phase_merge(build, local, dtype, group, world, timers=None):
+  """Export this rank's (label, first index) pairs, all-gather them (sizes first: one host round trip) and insert
+  everybody's pairs into a fresh table with atomicMin.  `build(table)` runs K1 over the slab; it is repeated on a
+  grown table when any rank's table overflowed (all ranks take the same decision).
+  Returns (merged table, per-rank label counts, this rank's exported keys as a uint64 device buffer)."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  L = _lib.load()
   while True:
     cap_pairs = local.entries_max()
     k64, v64 = D.alloc(cap_pairs * 8), D.alloc(cap_pairs * 8)
-    api._ev(timers, "k1", 0)
-    _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
-                                    local.cap, D.ptr(local.meta), row_bytes, D.stream()), "frb_renumber_build")
-    api._ev(timers, "k1", 1)
+    build(local)
     api._ev(timers, "merge", 0)
     api._ev(timers, "export", 0)
     _lib.check(L.frb_table_export(D.ptr(local.slots), local.cap, D.ptr(local.meta), D.ptr(k64), D.ptr(v64), cap_pairs,
@@ -120,7 +145,6 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     if not any(overfull):
       break
     local.grow(max(counts))  # all ranks take the same decision: tables stay the same size everywhere
-  _exchange_guess[(id(group), world, dtype.str, int(n_local), local.cap)] = _guess_from(counts)
 
   api._ev(timers, "xchg_pairs", 0)
   m = max(max(counts), 1)
@@ -139,15 +163,42 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
                                          merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_gathered")
   api._ev(timers, "insert", 1)
   api._ev(timers, "merge", 1)
+  return merged, counts, k64
+
+
+def _own_table(merged, own_keys, own_count_dev, own_capacity, dtype):
+  """A lookup table for K3 that holds only THIS slab's labels with the global ranks K2 has just written into the
+  merged table.  At 8 GPUs the merged table is 8x the size of a single GPU's and later ranks' labels sit deeper in
+  its probe chains (K3 3.53 -> 3.69 ms); looked up through its own compact table every rank's K3 costs what a
+  single GPU's does.  Direct tables (8 / 16-bit labels) are used as they are."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  if merged.direct:
+    return merged
+  own = api.LabelTable(dtype, own_capacity, _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
+  _lib.check(_lib.load().frb_table_project(D.ptr(own_keys), own_count_dev, own_capacity, D.ptr(merged.slots), merged.cap, D.ptr(merged.meta),
+                                           D.ptr(own.slots), own.cap, D.ptr(own.meta), D.stream()), "frb_table_project")
+  return own
+
+
+def _rank_and_relabel(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, own_keys, own_count, total, limits, timers):
+  """K2 on the merged table (identical on every rank), then K3 of the own slab through the rank's compact table."""
+  import ctypes
+  from . import _lib
+  from . import api
   rb = api._RankBuffers(merged, dtype)
   api._ev(timers, "k2", 0)
   api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
   api._ev(timers, "k2", 1)
+  api._ev(timers, "project", 0)
+  lookup = _own_table(merged, own_keys, None, max(int(own_count), 1), dtype)
+  api._ev(timers, "project", 1)
   if limits is not None:  # K3 queued behind K2: the refit width is picked on the device
     ranked = torch.cuda.Event()
     ranked.record()
     api._ev(timers, "k3", 0)
-    narrow = api._relabel_auto(src_buf, n_local, dtype, merged, preserve_zero, start, write_wide, limits)
+    narrow = api._relabel_auto(src_buf, n_local, dtype, lookup, preserve_zero, start, write_wide, limits)
     api._ev(timers, "k3", 1)
     meta = merged.read_meta_after(ranked)                                  # host round trip 2 (K3 keeps running)
   else:
@@ -156,7 +207,97 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
     raise api.FastremapB200Error("renumber_sharded: merged label table overflowed")
   if limits is not None:
     return api._auto_result(src_buf, narrow, dtype, start, merged, rb, meta)
-  return api._renumber_finish(src_buf, n_local, dtype, start, preserve_zero, write_wide, merged, rb, meta, timers)
+  return api._renumber_finish(src_buf, n_local, dtype, start, preserve_zero, write_wide, lookup, rb, meta, timers)
+
+
+def renumber_host_sharded(arr, start=1, preserve_zero=True, group=None, offset=None, total=None, max_labels=None):
+  """renumber(in_place=True) of this rank's HOST slab (a C- or F-contiguous, writeable numpy array) of a sharded
+  volume: the caller's array receives the ids at the old width, the narrowed copy is returned with the GLOBAL
+  mapping -- what fastremap.renumber(whole_volume, in_place=True) leaves in these planes (fastremap.pyx:121-161).
+
+  A chunk pipeline around the one exchange step: K1 consumes 128 MiB chunks as they arrive from the host (upload of
+  chunk c+1 under K1 of chunk c); after the merge and K2, K3 relabels chunk by chunk and both result streams (ids
+  at the old width, narrowed copy) go back while the next chunk is relabelled; the mapping dict is built meanwhile.
+  No id is final before the merge, so the two PCIe directions cannot overlap: the floor is upload + download time."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  L = _lib.load()
+  D.dev()
+  dtype = arr.dtype
+  w = dtype.itemsize
+  c = D.code(dtype)
+  n = arr.size
+  nbytes = n * w
+  world = dist.get_world_size(group)
+  rank = dist.get_rank(group)
+  if offset is None or total is None:
+    offset, total = shard_offsets(n, group)
+  order = "F" if arr.flags["F_CONTIGUOUS"] and not arr.flags["C_CONTIGUOUS"] else "C"
+  host_u8 = D.as_torch_bytes(D.flat_view(arr))
+  hint = D.row_bytes(arr.shape, order, dtype)
+  chunk = max(api.STREAM_CHUNK_BYTES // 16 * 16, 16)
+  bounds = [(a, min(a + chunk, nbytes)) for a in range(0, nbytes, chunk)]
+  cur = torch.cuda.current_stream()
+  s_in, s_out, s_out2 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+  dev_buf = D.alloc(nbytes)
+  for s_ in (s_in, s_out, s_out2):
+    s_.wait_stream(cur)
+  up = D.ChunkUploader(host_u8, dev_buf, bounds, s_in)
+  down_w = D.ChunkDownloader(host_u8, s_out)
+  down_n = None
+  try:
+    local = api.LabelTable(dtype, api._default_entries(n, max_labels), _lib.EMPTY)
+
+    def build(t):
+      for i, (a, b) in enumerate(bounds):
+        cur.wait_event(up.event(i))
+        _lib.check(L.frb_renumber_build(D.ptr(dev_buf[a:b]), (b - a) // w, c, offset + a // w, 1 if preserve_zero else 0, D.ptr(t.slots),
+                                        t.cap, D.ptr(t.meta), hint, D.stream()), "frb_renumber_build")
+
+    merged, counts, own_keys = _two_phase_merge(build, local, dtype, group, world)
+    rb = api._RankBuffers(merged, dtype)
+    api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
+    lookup = _own_table(merged, own_keys, None, max(int(counts[rank]), 1), dtype)
+    meta = merged.read_meta()
+    if meta[_lib.META_OVERFLOW]:
+      raise api.FastremapB200Error("renumber_host_sharded: merged label table overflowed")
+    nl = int(meta[_lib.META_ASSIGNED])
+    out_dtype = api._out_dtype(dtype, start, nl)
+    wo = out_dtype.itemsize
+    narrowed = wo < w
+    out = arr
+    if out_dtype != dtype:
+      out = D.host_empty(arr.shape, out_dtype, order)
+      down_n = D.ChunkDownloader(D.as_torch_bytes(D.flat_view(out)), s_out2)
+    narrow = D.alloc(n * wo) if narrowed else None
+    add = int(np.int64(start))
+    for a, b in bounds:
+      ne = (b - a) // w
+      e0 = a // w
+      view = dev_buf[a:b]
+      nview = narrow[e0 * wo:(e0 + ne) * wo] if narrowed else None
+      api._relabel(view, ne, dtype, lookup, _lib.MISS_ERROR, 0, preserve_zero, view, nview, wo if narrowed else 0, add=add)
+      if out_dtype != dtype and not narrowed:  # widened ids (start so large that the next id needs a wider dtype)
+        nview = api._cast(view, dtype, out_dtype, ne)
+      ev = torch.cuda.Event()
+      ev.record(cur)
+      down_w.submit(a, b, view, ev)
+      if down_n is not None:
+        down_n.submit(e0 * wo, (e0 + ne) * wo, nview[: ne * wo], ev)
+    res = api.RenumberResult()
+    res.keys, res.ids, res.n_labels = rb.keys, rb.ids, nl
+    mapping = api._mapping_to_dict(res, dtype, preserve_zero)   # host work under the downloads
+    down_w.finish()
+    if down_n is not None:
+      down_n.finish()
+    cur.synchronize()
+    return out, mapping
+  finally:
+    up.abort()
+    down_w.abort()
+    if down_n is not None:
+      down_n.abort()
 
 
 # One-shot exchange.  The two-phase path above needs the per-rank label counts on the HOST between its
@@ -169,9 +310,9 @@ _exchange_guess = {}
 one_shot_stats = {"hit": 0, "miss": 0}
 
 
-def _guess_from(counts):
+def _guess_from(counts, local_cap):
   m = (int(max(counts) * 1.25) + 1024) // 1024 * 1024
-  return m, int(sum(counts) * 1.25) + 1024
+  return m, int(sum(counts) * 1.25) + 1024, int(local_cap)
 
 
 def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero, write_wide, group, world, offset, total, timers,
@@ -180,7 +321,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   from . import api
   from . import device as D
   L = _lib.load()
-  m, total_labels = guess
+  m, total_labels = guess[0], guess[1]
   MW = _lib.META_WORDS
   block = (MW + 2 * m) * 8
   packed = D.alloc(block)
@@ -209,10 +350,15 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   api._ev(timers, "k2", 0)
   api._rank(merged, rb, dtype, start, 0, max(int(total), 1))
   api._ev(timers, "k2", 1)
+  api._ev(timers, "project", 0)
+  import ctypes
+  own_count_dev = ctypes.c_void_p(packed.data_ptr() + 8 * _lib.META_COUNT)   # this rank's label count, still on the device
+  lookup = _own_table(merged, keys_out, own_count_dev, m, dtype)
+  api._ev(timers, "project", 1)
   ranked = torch.cuda.Event()
   ranked.record()
   api._ev(timers, "k3", 0)
-  narrow = api._relabel_auto(src_buf, n_local, dtype, merged, preserve_zero, start, write_wide, limits)
+  narrow = api._relabel_auto(src_buf, n_local, dtype, lookup, preserve_zero, start, write_wide, limits)
   api._ev(timers, "k3", 1)
   # host round trip (K3 keeps running): the merged meta and every rank's count, through the side stream
   side = D.side_stream()
@@ -226,7 +372,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
     torch.cuda.current_stream().synchronize()  # the parked K3 must be out of the way before src is walked again
     return None
   one_shot_stats["hit"] += 1
-  _exchange_guess[key] = _guess_from([int(x) for x in counts_h.tolist()])
+  _exchange_guess[key] = _guess_from([int(x) for x in counts_h.tolist()], local.cap)
   return api._auto_result(src_buf, narrow, dtype, start, merged, rb, meta)
 
 
@@ -250,7 +396,7 @@ def _export_pairs(table):
   return k64[: nl * 8].view(torch.int64), v64[: nl * 8].view(torch.int64)
 
 
-def unique_sharded(buf, n_local, dtype, max_labels=None, group=None, row_bytes=0):
+def unique_sharded(buf, n_local, dtype, max_labels=None, group=None, row_bytes=0, plane_bytes=0):
   """unique(return_counts=True) of the whole sharded volume, replicated on every rank.
   Returns (uniq_buf, counts_buf, n_unique) like api.unique_counts_device."""
   from . import _lib
@@ -263,8 +409,8 @@ def unique_sharded(buf, n_local, dtype, max_labels=None, group=None, row_bytes=0
   ws = D.alloc(ws_bytes)
 
   def build_local(t):
-    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), row_bytes, D.ptr(ws), ws_bytes,
-                               D.stream()), "frb_hist_hash")
+    _lib.check(L.frb_hist_hash(D.ptr(buf), n_local, D.code(dtype), D.ptr(t.slots), t.cap, D.ptr(t.meta), row_bytes, plane_bytes,
+                               D.ptr(ws), ws_bytes, D.stream()), "frb_hist_hash")
 
   api._run_build(build_local, local)
   keys, counts = allgather_pairs(*_export_pairs(local), group)

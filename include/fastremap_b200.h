@@ -84,6 +84,12 @@ int frb_table_insert_gathered(const uint64_t* gathered, uint64_t m, int world, c
  * frb_relabel with guard_overflow, frb_relabel_auto) do nothing and the host takes the two-phase path. */
 int frb_table_insert_packed(const uint64_t* packed, uint64_t m, int world, uint64_t local_cap, int op, int direct, void* slots,
                             uint64_t cap, uint64_t* meta, void* stream);
+/* dst[key] = src[key] for every key of the list that the hashed table src holds (values copied as they are; dst must be
+ * initialised, sized for max_count keys).  count_dev != NULL: the list holds min(*count_dev, max_count) keys, the count
+ * still being on the device.  Copies meta[FRB_META_ASSIGNED]; a raised OVERFLOW flag in src_meta is passed on instead.
+ * Multi-GPU renumber: a rank's own labels with their global ranks, as a compact lookup table for K3. */
+int frb_table_project(const uint64_t* keys, const uint64_t* count_dev, uint64_t max_count, const void* src_slots, uint64_t src_cap,
+                      const uint64_t* src_meta, void* dst_slots, uint64_t dst_cap, uint64_t* dst_meta, void* stream);
 /* replace every stored value v (a position) by vals[v] -- "later duplicate wins" for
  * remap_from_array_kv (fastremap.pyx:810-811) after an FRB_OP_MAX insert of positions. */
 int frb_table_resolve(const void* vals, int val_width, void* slots, uint64_t cap, uint64_t* meta, void* stream);
@@ -205,11 +211,14 @@ int frb_compact_bins_emit(const uint64_t* counts, uint64_t bins, int dtype, uint
  * ws (frb_hist_ws_bytes(n) bytes; NULL: update the table from inside the pass instead -- slower); the logs are then
  * folded into the table (frb_hist_apply_log, called by frb_hist_hash itself).  If the table overflows and the flag
  * word at ws + frb_hist_ws_flags_offset() is 0, frb_hist_apply_log on a bigger table finishes the job without a
- * second pass over the volume. */
+ * second pass over the volume.
+ * plane_bytes: bytes per plane of the two fastest axes, or 0 (performance hint): when the volume is a stack of planes
+ * of whole 16 KiB tiles, a CTA walks one band of rows through a stack of consecutive planes, so the segments it has
+ * aggregated in shared memory come round again one plane deeper. */
 size_t frb_hist_ws_bytes(size_t n);
 size_t frb_hist_ws_flags_offset(void);
-int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes, void* ws,
-                  size_t ws_bytes, void* stream);
+int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, uint64_t row_bytes,
+                  uint64_t plane_bytes, void* ws, size_t ws_bytes, void* stream);
 int frb_hist_apply_log(const void* ws, size_t ws_bytes, size_t n, int dtype, void* slots, uint64_t cap, uint64_t* meta, void* stream);
 size_t frb_sort_pairs_ws_bytes(size_t L);
 /* sort exported (key bits, value) pairs ascending in the dtype's own order (keys / vals are

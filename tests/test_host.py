@@ -180,8 +180,10 @@ def test_sizing_rules():
   assert api._lookup_slots_per_entry(1000) == api.LOOKUP_SLOTS_PER_ENTRY_MAX
   assert api._lookup_slots_per_entry(5_000_000) == 16                      # 32 slots per label would pass 2 GiB
   assert api._lookup_slots_per_entry(50_000_000) == api.LOOKUP_SLOTS_PER_ENTRY
-  m, total = sharded._guess_from([1000, 3000, 2000])
-  assert m >= 3000 * 1.25 and m % 1024 == 0 and total >= 6000 * 1.25
+  m, total, cap = sharded._guess_from([1000, 3000, 2000], 1 << 20)
+  assert m >= 3000 * 1.25 and m % 1024 == 0 and total >= 6000 * 1.25 and cap == 1 << 20   # the grown table size is remembered
+  assert api._default_entries(1 << 30, None) == (1 << 30) // 256 and api._default_entries(1 << 30, None, 512) == (1 << 30) // 512
+  assert api._default_entries(1 << 30, 1000) == 1001 and api._default_entries(1000, None) == 1 << 15
 
 
 def test_host_memcpy_threads():
