@@ -61,8 +61,10 @@ def main():
   ap.add_argument("--side", type=int, default=1024)
   ap.add_argument("--reps", type=int, default=5)
   ap.add_argument("--ops", default="unique_dense,unique_sparse,remap,mask_except,component_map,minmax")
+  ap.add_argument("--no-plane", action="store_true", help="withhold the plane_bytes hint: linear walk everywhere (A/B runs)")
   args = ap.parse_args()
   S, ops = args.side, set(args.ops.split(","))
+  PL = 0 if args.no_plane else 1
   n = S ** 3
   sc = S / 1024.0
   D.dev()
@@ -78,7 +80,7 @@ def main():
       report("minmax+pixel_pairs u64 (K6)", n, 8, m, mn)
     del vol
     if "unique_dense" in ops:
-      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), args.reps)
+      m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, row_bytes=S * 4, plane_bytes=PL * S * S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, incl. minmax pre-pass (config 2a)", n, 4, m, mn, n_unique=out[2])
       m, mn, out = timed(lambda: api.unique_counts_device(dense, n, np.uint32, strategy="hash", row_bytes=S * 4), args.reps)
       report("unique(return_counts) u32 dense ids, forced hash strategy", n, 4, m, mn, n_unique=out[2])
@@ -86,7 +88,7 @@ def main():
 
   if "unique_sparse" in ops:
     vol = flat_u8(synth_device((S, S, S), (max(int(100 * sc), 1),) * 3, np.uint32, seed=1, zero_frac=0.1))
-    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4, plane_bytes=S * S * 4), args.reps)
+    m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4, plane_bytes=PL * S * S * 4), args.reps)
     report("unique(return_counts) u32 sparse ids, incl. minmax pre-pass (config 2b)", n, 4, m, mn, n_unique=out[2])
     m, mn, out = timed(lambda: api.unique_counts_device(vol, n, np.uint32, row_bytes=S * 4), args.reps)
     report("unique(return_counts) u32 sparse ids, linear walk (no plane hint)", n, 4, m, mn, n_unique=out[2])
@@ -104,7 +106,7 @@ def main():
     m, mn, table = timed(lambda: api.table_from_arrays(keys, vals, L, np.uint64), args.reps)
     print(json.dumps({"op": "remap table build from %d-entry key/value arrays" % L, "ms": m, "ms_min": mn}), flush=True)
     work = torch.empty_like(vol)
-    m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L)), args.reps,
+    m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L), plane_bytes=PL * S * S * 8), args.reps,
                      setup=lambda: work.copy_(vol))
     report("remap u64 in place, %d-entry table, preserve_missing_labels (config 3)" % L, n, 16, m, mn, labels_in_volume=nu)
     del vol, work, table
@@ -119,13 +121,13 @@ def main():
       m, mn, table = timed(lambda: api.table_from_arrays(kb, kb, keep.numel(), np.uint64), args.reps)
       print(json.dumps({"op": "mask_except table build from %d labels" % keep.numel(), "ms": m, "ms_min": mn}), flush=True)
       work = torch.empty_like(cc)
-      m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel())), args.reps,
+      m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel()), plane_bytes=PL * S * S * 8), args.reps,
                        setup=lambda: work.copy_(cc))
       report("mask_except u64 in place, %d kept of %d labels (config 5)" % (keep.numel(), nu), n, 16, m, mn)
       del work, table, uniq, keep, kb
     if "component_map" in ops:
       par = flat_u8(synth_device((S, S, S), (g, g, g), np.uint64, seed=5, zero_frac=0.0, cell_div=4))
-      m, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8), args.reps)
+      m, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8, plane_bytes=PL * S * S * 8), args.reps)
       report("component_map (u64, u64) device arrays (config 5)", n, 16, m, mn, n_components=out[2])
       del par
     del cc

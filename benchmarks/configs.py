@@ -163,7 +163,7 @@ def config3(ref, kind, peak, reps, slab_planes=256, **_):
   vals_dev = flat_u8(torch.arange(1, L + 1, dtype=torch.int64, device=vol.device))
   tb_ms, _, table = timed(lambda: api.table_from_arrays(keys_dev, vals_dev, L, np.uint64), reps)
   work = torch.empty_like(vol)
-  ms, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L)), reps,
+  ms, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L), plane_bytes=S * S * 8), reps,
                     setup=lambda: work.copy_(vol))
   del table
   # the public call on the whole volume (dict -> arrays -> upload -> table -> K3), in place on a device copy
@@ -217,7 +217,7 @@ def config5a(ref, kind, peak, reps, slab_planes=256, **_):
   nk = keep.numel()
   tb_ms, _, table = timed(lambda: api.table_from_arrays(kb, kb, nk, np.uint64), reps)
   work = torch.empty_like(cc)
-  ms, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(nk)),
+  ms, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(nk), plane_bytes=S * S * 8),
                     reps, setup=lambda: work.copy_(cc))
   del table
   keep_list = D.download(kb, nk, np.uint64).tolist()
@@ -255,7 +255,7 @@ def config5b(ref, kind, peak, reps, slab_planes=256, **_):
   cc_t = _cc_volume(S, g)
   par_t = synth_device((S, S, S), (g, g, g), np.uint64, seed=5, zero_frac=0.0, cell_div=4)
   cc, par = flat_u8(cc_t), flat_u8(par_t)
-  ms, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8), reps)
+  ms, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8, plane_bytes=S * S * 8), reps)
   keys, pars, nl = out
   # full size, closed form: parent is a function of the cell, so the map must be {label(cell): parent label(cell)}
   k_np, p_np = D.download(keys, nl, np.uint64), D.download(pars, nl, np.uint64)

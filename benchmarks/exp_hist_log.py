@@ -34,3 +34,12 @@ for plane in (0, S * S * 4):
                     "min": int(live.min()), "median": float(np.median(live)), "max": int(live.max()), "direct_flag": flag,
                     "pct": [int(x) for x in np.percentile(live, [1, 10, 25, 50, 75, 90, 99])],
                     "labels": int(table.read_meta()[_lib.META_COUNT])}), flush=True)
+
+# which labels dominate the records of the plane walk (same-address atomics serialise when the logs are folded)
+cap = (ws_bytes - off - 256) // 16 // counts.size
+rec = ws[off + 256: off + 256 + counts.size * cap * 16].view(torch.int64).reshape(counts.size, cap, 2)
+valid = torch.arange(cap, device=rec.device)[None, :] < torch.from_numpy(counts.astype(np.int64)).to(rec.device)[:, None]
+keys = rec[:, :, 0][valid]
+u, c = torch.unique(keys, return_counts=True)
+top = torch.topk(c, 8)
+print(json.dumps({"records": int(keys.numel()), "distinct": int(u.numel()), "top_keys": u[top.indices].tolist(), "top_counts": top.values.tolist()}))

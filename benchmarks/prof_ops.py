@@ -53,7 +53,7 @@ if "remap" in ops:
   work = torch.empty_like(vol)
   for _ in range(2):
     work.copy_(vol)
-    api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L))
+    api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L), plane_bytes=S * S * 8)
   print("remap", L)
   del vol, work, table
 
@@ -68,13 +68,13 @@ if "mask_except" in ops or "component_map" in ops:
     work = torch.empty_like(cc)
     for _ in range(2):
       work.copy_(cc)
-      api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel()))
+      api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel()), plane_bytes=S * S * 8)
     print("mask_except", keep.numel())
     del work, table, uniq, keep, kb
   if "component_map" in ops:
     par = flat_u8(synth_device((S, S, S), (g, g, g), np.uint64, seed=5, zero_frac=0.0, cell_div=4))
     for _ in range(2):
-      out = api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8)
+      out = api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8, plane_bytes=S * S * 8)
     print("component_map", out[2])
 torch.cuda.synchronize()
 print("ok")

@@ -44,7 +44,7 @@ SIGNATURES = {
   "frb_renumber_build": (_i, [_vp, _sz, _i, _u64, _i, _vp, _u64, _vp, _u64, _vp]),
   "frb_renumber_rank_ws_bytes": (_sz, [_sz]),
   "frb_renumber_rank": (_i, [_vp, _u64, _vp, _i, _i64, _u64, _u64, _vp, _vp, _sz, _vp, _sz, _vp]),
-  "frb_relabel": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _u64, _i, _i, _vp]),
+  "frb_relabel": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _u64, _i, _i, _u64, _vp]),
   "frb_relabel_auto": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _u64, _i, _vp, _i, _u64, _i, _u64, _u64, _u64, _vp]),
   "frb_replace_one": (_i, [_vp, _vp, _sz, _i, _u64, _u64, _vp]),
   "frb_remap_from_array": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
@@ -75,7 +75,7 @@ SIGNATURES = {
   "frb_sort_pairs_u64_ws_bytes": (_sz, [_sz]),
   "frb_sort_pairs_u64": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
   "frb_unravel_u16": (_i, [_vp, _sz, _i, _u64, _u64, _vp, _vp]),
-  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _vp]),
+  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _u64, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
   "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),

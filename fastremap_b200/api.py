@@ -186,11 +186,11 @@ def table_from_arrays(keys_dev, vals_dev, L: int, dtype, op=_lib.OP_SET, positio
 
 
 def _relabel(src_buf, n, dtype, table: LabelTable, policy, fill_bits=0, zero_fixed=False, dst_wide=None, dst_narrow=None,
-             narrow_width=0, add=0, guard_overflow=False, batch_rows=0):
+             narrow_width=0, add=0, guard_overflow=False, batch_rows=0, plane_bytes=0):
   _lib.check(_L().frb_relabel(D.ptr(src_buf), D.ptr(dst_wide), D.ptr(dst_narrow), narrow_width, n, D.code(dtype),
                               D.ptr(table.slots), table.cap, table.direct, D.ptr(table.meta), policy, fill_bits,
                               1 if zero_fixed else 0, add & _lib.EMPTY, 1 if guard_overflow else 0, batch_rows,
-                              D.stream()), "frb_relabel")
+                              plane_bytes, D.stream()), "frb_relabel")
 
 
 def _cast(src_buf, src_dtype, dst_dtype, n):
@@ -766,7 +766,7 @@ def remap(arr, table, preserve_missing_labels=False, in_place=False):
     kd, vd = D.upload_array(keys), D.upload_array(vals)
     t = table_from_arrays(kd, vd, len(keys), adtype, op=_lib.OP_SET)
     policy = _lib.MISS_KEEP if preserve_missing_labels else _lib.MISS_ERROR
-    _relabel(v.buf, v.n, adtype, t, policy, dst_wide=v.buf, batch_rows=_batch_rows(len(keys)))
+    _relabel(v.buf, v.n, adtype, t, policy, dst_wide=v.buf, batch_rows=_batch_rows(len(keys)), plane_bytes=v.plane_bytes)
     if not preserve_missing_labels:
       _check_missing(t, v.buf, adtype, "{} was not in the remap table.")
 
@@ -884,7 +884,8 @@ def mask_except(arr, labels, in_place=False, value=0):
   if v.n:
     kd = D.upload_array(lab)
     t = table_from_arrays(kd, kd, len(lab), adtype, op=_lib.OP_SET)
-    _relabel(v.buf, v.n, adtype, t, _lib.MISS_FILL, fill_bits=fill, dst_wide=v.buf, batch_rows=_batch_rows(len(lab)))
+    _relabel(v.buf, v.n, adtype, t, _lib.MISS_FILL, fill_bits=fill, dst_wide=v.buf, batch_rows=_batch_rows(len(lab)),
+             plane_bytes=v.plane_bytes)
   if is_t:
     return arr if v.aliases_input else D.emit(v.buf, adtype, v.shape, v.order, True)
   if in_place_eff:
@@ -990,11 +991,12 @@ def component_map_arrays(component_labels, parent_labels, max_labels=None):
     vc, vp = D.ingest(component_labels), D.ingest(parent_labels)
   _require_int(vc.dtype, "component_map")
   _require_int(vp.dtype, "component_map")
-  keys, pars, nl = component_map_device(vc.buf, vc.n, vc.dtype, vp.buf, vp.dtype, max_labels=max_labels, row_bytes=vc.row_bytes)
+  keys, pars, nl = component_map_device(vc.buf, vc.n, vc.dtype, vp.buf, vp.dtype, max_labels=max_labels, row_bytes=vc.row_bytes,
+                                        plane_bytes=vc.plane_bytes)
   return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
 
 
-def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None, row_bytes=0):
+def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None, row_bytes=0, plane_bytes=0):
   """K7 on flat device buffers: returns (keys_buf, parents_buf, n_labels), unordered."""
   cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
   L = _L()
@@ -1002,7 +1004,7 @@ def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labe
 
   def build(t):
     _lib.check(L.frb_component_build(D.ptr(cc_buf), n, D.code(cc_dtype), 0, D.ptr(t.slots), t.cap, D.ptr(t.meta),
-                                     row_bytes, D.stream()), "frb_component_build")
+                                     row_bytes, plane_bytes, D.stream()), "frb_component_build")
 
   meta = _run_build(build, table)
   nl = int(meta[_lib.META_COUNT])

@@ -37,7 +37,7 @@ __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct
 template <int W, int OP, bool REVERSE, bool HEADS, int IL, int DU, bool VAR_TILE>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run,
-                                           int tile_vecs) {
+                                           int tile_vecs, PlaneWalk pw) {
   constexpr int V = 16 / W;
   typedef typename UIntOf<W>::type T;
   __shared__ u64 s_seen[8][BUILD_CACHE];
@@ -173,7 +173,10 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     }
   };
 
-  const TileMap map(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+  // plane walk (frb_common.cuh): a CTA follows one band of rows through a stack of planes, so the labels of the band
+  // are still in the warps' sets of "already offered" when they come round again -- with tables too big for L2 an
+  // offer is a random HBM access, and those, not the streaming, are what bounds the pass at 10^7 labels
+  const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw) : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
   stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
   resolve_pending();
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);

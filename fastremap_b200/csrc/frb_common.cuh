@@ -454,6 +454,7 @@ struct TileMapT {
   IDX tv;      // vectors per tile: STREAM_TILE_VECS, or less when a tile is a whole number of volume rows
   IDX first;   // first tile of this CTA (forward walks)
   IDX jump;    // distance from the last tile of a run to the first tile of this CTA's next run, minus 1
+  bool planar; // plane walk (second constructor)
   // linear walk: runs of `run` tiles dealt round-robin to the CTAs
   __device__ __forceinline__ TileMapT(size_t nvec, size_t run_, size_t tile_vecs = STREAM_TILE_VECS) {
     tv = tile_vecs < 32 || tile_vecs > (size_t)STREAM_TILE_VECS ? (IDX)STREAM_TILE_VECS : (IDX)tile_vecs;
@@ -463,6 +464,7 @@ struct TileMapT {
     if (sizeof(IDX) != 8) {  // the 64-bit iterator derives these itself (K3's tuned code path, left as it was)
       first = (IDX)blockIdx.x * run;
       jump = ((IDX)gridDim.x - 1) * run;
+      planar = false;
     }
     const IDX nruns = (tiles + run - 1) / run;
     const IDX b = blockIdx.x, g = gridDim.x;
@@ -483,6 +485,7 @@ struct TileMapT {
     tiles = plane_tiles * planes;
     run = band;
     jump = plane_tiles - band;
+    planar = true;
     const IDX bands = plane_tiles / band;                  // bands per plane
     const IDX b = (IDX)blockIdx.x % bands, g = (IDX)blockIdx.x / bands;
     const IDX stacks = ((IDX)gridDim.x - b + bands - 1) / bands;  // CTAs that share band b: they split the planes
@@ -504,7 +507,10 @@ struct TileIterT {
     jump = sizeof(IDX) == 8 ? ((IDX)gridDim.x - 1) * m.run : m.jump;
     const IDX nruns_mine = (m.count + m.run - 1) / m.run;
     const IDX last_len = m.count - (nruns_mine ? (nruns_mine - 1) * m.run : 0);
-    if (REVERSE) {  // linear walks only
+    if (REVERSE && sizeof(IDX) != 8 && m.planar) {  // last tile of the band in the deepest plane of the stack (count > 0 here)
+      o = run - 1;
+      t = m.first + (m.count / run - 1) * (run + jump) + o;
+    } else if (REVERSE) {
       const IDX r = nruns_mine ? nruns_mine - 1 : 0;
       o = last_len ? last_len - 1 : 0;
       t = (r * gridDim.x + blockIdx.x) * run + o;

@@ -15,8 +15,8 @@ namespace frb {
 template <int W, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
-                  u64* __restrict__ meta, int run, int tile_vecs) {
-  build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs);
+                  u64* __restrict__ meta, int run, int tile_vecs, PlaneWalk pw) {
+  build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs, pw);
 }
 
 // gather: scan the table (frb_scan.cuh) and emit (label, parent[winning run start]) for every label
@@ -100,7 +100,7 @@ using namespace frb;
 extern "C" {
 
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, uint64_t row_bytes, void* stream) {
+                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, void* stream) {
   if (!dtype_ok(cc_dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!cc || !aligned16(cc)))) { set_error("frb_component_build: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(cc_dtype);
@@ -114,7 +114,8 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
 #define FRB_K7(WW, II, DD, VV) k_component_build<WW, II, DD, VV><<<stream_grid(k_component_build<WW, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, II, DD, VV>, tiles), tiles), tv)
+    p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, II, DD, VV>, tiles), tiles), tv, \
+    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_component_build<WW, II, DD, VV>, tiles)))
 #define FRB_K7_GEO(WW)                                                        \
   if (geo.tv != STREAM_TILE_VECS) { FRB_K7(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_K7(WW, 4, 1, false); }                          \

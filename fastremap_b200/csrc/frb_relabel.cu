@@ -228,7 +228,7 @@ k_relabel_auto(const uint4* src, void* dst_wide, void* dst_narrow, size_t n, Rel
 // out of place at the input width only (what the remap family needs).
 template <int W, int NB>
 __global__ void __launch_bounds__(STREAM_THREADS)
-k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int run) {
+k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int run, PlaneWalk pw) {
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
   static_assert(W == 8 && R % NB == 0, "64-bit labels, hashed tables only");
@@ -266,7 +266,14 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
       }
     }
   };
-  const TileMap64 map(nvec, (size_t)run);
+  // pw: a plane walk (frb_common.cuh) is possible here but measured SLOWER than the linear walk (remap through 10^6
+  // labels 3.49 vs 3.07 ms, mask_except with 5 M labels 5.04 vs 4.18 ms at 1024^3): the hint is accepted and ignored
+  // unless the experiment flag is set
+#ifdef FRB_K3_PLANE_WALK
+  const TileMap map = pw.band ? TileMap(pw) : TileMap(nvec, (size_t)run);
+#else
+  const TileMap map(nvec, (size_t)run);
+#endif
   stream_rows<W, false, false, 0>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
@@ -280,9 +287,11 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 }
 
 template <int W, int NB>
-static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, cudaStream_t st) {
+static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, size_t plane_bytes, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);
-  k_relabel_batched<W, NB><<<stream_grid(k_relabel_batched<W, NB>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, fair_run(stream_grid(k_relabel_batched<W, NB>, tiles), tiles));
+  const int grid = stream_grid(k_relabel_batched<W, NB>, tiles);
+  const PlaneWalk pw = plane_walk_for(n * (size_t)W, (n % (16 / W)) ? 0 : plane_bytes, grid);
+  k_relabel_batched<W, NB><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, fair_run(grid, tiles), pw);
   return check_launch("k_relabel_batched");
 }
 
@@ -427,7 +436,7 @@ extern "C" {
 
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill, int zero_fixed,
-                uint64_t add, int guard_overflow, int batch_rows, void* stream) {
+                uint64_t add, int guard_overflow, int batch_rows, uint64_t plane_bytes, void* stream) {
   if (!dtype_ok(dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (!dst_wide && !dst_narrow) ||
       (n && (!src || !aligned16(src) || (dst_wide && !aligned16(dst_wide)) || (dst_narrow && !aligned16(dst_narrow)))) ||
       policy < 0 || policy > 2) {
@@ -451,7 +460,8 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
   // 64-bit labels only: with 4 labels per vector the batch is 8+ probes per lane (80+ registers) and was
   // measured 2.5-3x SLOWER than the plain kernel's one-probe-per-distinct-label loop at every table size
   if (batch_rows > 1 && !A.direct && w == 8 && dst_wide && !dst_narrow) {
-    return batch_rows >= 4 ? launch_relabel_batched<8, 4>(src, dst_wide, n, A, st) : launch_relabel_batched<8, 2>(src, dst_wide, n, A, st);
+    return batch_rows >= 4 ? launch_relabel_batched<8, 4>(src, dst_wide, n, A, (size_t)plane_bytes, st)
+                           : launch_relabel_batched<8, 2>(src, dst_wide, n, A, (size_t)plane_bytes, st);
   }
   switch (w) {
     case 1: return dispatch_relabel<1>(src, dst_wide, dst_narrow, narrow_width, n, A, st);

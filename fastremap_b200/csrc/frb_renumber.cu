@@ -99,8 +99,8 @@ __global__ void k_minmax_init(u64* out, int is_signed) {
 template <int W, int IL, int DU, bool VAR_TILE>
 __global__ void __launch_bounds__(STREAM_THREADS)
 k_renumber_build(const uint4* __restrict__ a, size_t n, u64 flat_offset, int skip_zero, Slot* __restrict__ slots,
-                 u64 mask, int direct, u64* __restrict__ meta, int run, int tile_vecs) {
-  build_pass<W, FRB_OP_MIN, false, false, IL, DU, VAR_TILE>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run, tile_vecs);
+                 u64 mask, int direct, u64* __restrict__ meta, int run, int tile_vecs, PlaneWalk pw) {
+  build_pass<W, FRB_OP_MIN, false, false, IL, DU, VAR_TILE>(a, n, FRB_RANK_TAG | flat_offset, skip_zero, slots, mask, direct, meta, run, tile_vecs, pw);
 }
 
 // ------------------------------------------------------------------------------------------ probes
@@ -183,7 +183,7 @@ int frb_renumber_build(const void* a, size_t n, int dtype, uint64_t flat_offset,
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
 #define FRB_K1(WW, II, DD, VV) k_renumber_build<WW, II, DD, VV><<<stream_grid(k_renumber_build<WW, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, II, DD, VV>, tiles), tiles), tv)
+    p, n, flat_offset, skip_zero, s, cap - 1, direct, m, fair_run(stream_grid(k_renumber_build<WW, II, DD, VV>, tiles), tiles), tv, PlaneWalk{0, 0, 0})
 #define FRB_K1_GEO(WW)                                                        \
   if (geo.tv != STREAM_TILE_VECS) { FRB_K1(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_K1(WW, 4, 1, false); }                          \

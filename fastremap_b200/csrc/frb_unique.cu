@@ -366,30 +366,62 @@ __global__ void __launch_bounds__(256) k_prefetch_l2(const char* base, size_t by
     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-// Fold the eviction logs of all warps into the label table: four records per thread, their home-slot keys
-// read together (one L2 round trip for the four), then a label already sitting in its home slot costs one
-// fire-and-forget reduction; first sightings and collisions take the probing path.
+// Fold the eviction logs of all warps into the label table.  A CTA takes one region (one warp's log) at a time:
+//   1. its records are aggregated in a shared-memory (label, count) table first.  Labels that are everywhere -- the
+//      background, segments that cross many warps' bands -- are evicted from thousands of warp maps, and their
+//      records would otherwise queue up on ONE slot of the label table: same-address atomics serialise in L2
+//      (measured: 79 k records of label 0 among 3.1 M made this kernel take 0.3 ms whatever the table's size);
+//   2. the distinct labels of the region then go to the table, four per thread with their home-slot keys read
+//      together (one L2 round trip for the four); a label already sitting in its home slot costs one
+//      fire-and-forget reduction, first sightings and collisions take the probing path.
+static constexpr int APPLY_SLOTS = 2048;  // >= 2 x the 4096-record cap of a region / 4 ... regions hold ~10^3 records
 __global__ void __launch_bounds__(256) k_hist_apply_log(HistLog log, unsigned int regions, HashSink sink, u64* count_target) {
+  __shared__ u64 a_key[APPLY_SLOTS];
+  __shared__ unsigned int a_cnt[APPLY_SLOTS];
   unsigned int inserted = 0;
   for (unsigned int r = blockIdx.x; r < regions; r += gridDim.x) {
     const unsigned int cnt = log.counts[r];
+    if (cnt == 0) continue;  // (the same in every thread)
     const ulonglong2* rec = log.records + (size_t)r * log.cap;
-    for (unsigned int i0 = threadIdx.x; i0 < cnt; i0 += 4 * 256) {
-      ulonglong2 v[4];
-      u64 home[4];
+    for (int e = threadIdx.x; e < APPLY_SLOTS; e += 256) { a_key[e] = FRB_EMPTY; a_cnt[e] = 0; }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < cnt; i += 256) {
+      ulonglong2 v;
+      asm("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(rec + i));
+      bool done = false;
+      if (v.x != FRB_EMPTY) {
+        unsigned int e = (unsigned int)(hash_key(v.x) >> 40) & (APPLY_SLOTS - 1);
+#pragma unroll 1
+        for (int probe = 0; probe < 8 && !done; probe++, e = (e + 1) & (APPLY_SLOTS - 1)) {
+          u64 k = a_key[e];
+          if (k == FRB_EMPTY) {
+            const u64 old = atomicCAS((unsigned long long*)&a_key[e], (unsigned long long)FRB_EMPTY, (unsigned long long)v.x);
+            k = old == FRB_EMPTY ? v.x : old;
+          }
+          if (k == v.x) {
+            atomicAdd(&a_cnt[e], (unsigned int)v.y);
+            done = true;
+          }
+        }
+      }
+      if (!done) sink(v.x, (unsigned int)v.y, &inserted);  // the all-ones label, or a crowded corner of the shared table
+    }
+    __syncthreads();
+    for (int e0 = threadIdx.x; e0 < APPLY_SLOTS; e0 += 4 * 256) {
+      u64 k[4], home[4];
+      unsigned int c[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const unsigned int i = i0 + q * 256;
-        v[q] = make_ulonglong2(FRB_EMPTY, 0ull);
-        if (i < cnt) {
-          asm("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v[q].x), "=l"(v[q].y) : "l"(rec + i));
-          home[q] = sink.peek(v[q].x);
-        }
+        k[q] = a_key[e0 + q * 256];
+        c[q] = a_cnt[e0 + q * 256];
+        home[q] = 0;
+        if (k[q] != FRB_EMPTY) home[q] = sink.peek(k[q]);
       }
 #pragma unroll
       for (int q = 0; q < 4; q++)
-        if (i0 + q * 256 < cnt) sink.commit(v[q].x, (unsigned int)v[q].y, home[q], &inserted);
+        if (k[q] != FRB_EMPTY) sink.commit(k[q], c[q], home[q], &inserted);
     }
+    __syncthreads();
   }
   if (count_target) block_add_to(count_target, inserted);
 }

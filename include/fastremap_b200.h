@@ -144,11 +144,13 @@ int frb_renumber_rank(void* slots, uint64_t cap, uint64_t* meta, int dtype, int6
  *   relabel before the host has seen whether the build of that chunk overflowed).
  *   batch_rows: 0 / 1 = look up row by row (a table whose live part sits in L1: renumber); 2 or 4 =
  *   issue the table loads of that many rows of a warp-tile before consuming any (tables of 10^5+
- *   labels that live in L2 / HBM; wide destination only). */
+ *   labels that live in L2 / HBM; wide destination only).
+ *   plane_bytes: bytes per plane of the two fastest axes or 0 (performance hint for the batched form: walk the
+ *   volume band by band through stacks of planes, so that table sectors are still in L2 one plane deeper). */
 enum { FRB_MISS_KEEP = 0, FRB_MISS_ERROR = 1, FRB_MISS_FILL = 2 };
 int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_width, size_t n, int dtype,
                 const void* slots, uint64_t cap, int direct, uint64_t* meta, int policy, uint64_t fill,
-                int zero_fixed, uint64_t add, int guard_overflow, int batch_rows, void* stream);
+                int zero_fixed, uint64_t add, int guard_overflow, int batch_rows, uint64_t plane_bytes, void* stream);
 /* renumber's K3 queued straight behind K2: the refit width is chosen ON THE DEVICE from the number of
  * labels nl = meta[FRB_META_ASSIGNED]: 1 byte if nl < lim1, else 2 if nl < lim2, else 4 if nl < lim4
  * (widths >= the input width are ignored), else no narrow copy.  The host derives lim* from fit_dtype
@@ -257,9 +259,10 @@ int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint
 /* ---- component_map -------------------------------------------------------------------
  * Replaces _component_map (fastremap.pyx:565-587): at every run start of cc the table
  * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])
- * for the winning run start of every label.  count in meta[FRB_META_LIST_COUNT]. */
+ * for the winning run start of every label.  count in meta[FRB_META_LIST_COUNT].
+ * row_bytes / plane_bytes: performance hints (0 = unknown), see frb_renumber_build / frb_hist_hash. */
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, uint64_t row_bytes, void* stream);
+                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, void* stream);
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
                          uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream);
 
