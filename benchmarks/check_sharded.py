@@ -55,6 +55,26 @@ def main():
         print("sharded renumber %s world=%d call=%d labels=%d -> %s" % (np.dtype(dtype).name, world, rep + 1, len(e_map),
                                                                       "OK" if same else "MISMATCH"), flush=True)
         ok = ok and same
+    # ---- the chunked host path: a numpy slab in, ids at the old width back in it + the narrowed copy + the mapping
+    host_slab = np.ascontiguousarray(slab.cpu().numpy())
+    saved_chunk = api.STREAM_CHUNK_BYTES
+    api.STREAM_CHUNK_BYTES = 1 << 16  # several chunks even for these small slabs
+    try:
+      h_out, h_map = sharded.renumber_host_sharded(host_slab, start=start, preserve_zero=pz)
+    finally:
+      api.STREAM_CHUNK_BYTES = saved_chunk
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (np.asarray(h_out), host_slab))
+    if rank == 0:
+      import oracle as orc
+      full = synth_numpy(shape, grid, dtype, seed=7, zero_frac=0.15, noise=0.05)
+      e_in = np.copy(full)
+      e_out, e_map = orc.renumber(e_in, start=start, preserve_zero=pz, in_place=True)
+      got = np.concatenate([x[0] for x in gathered]).reshape(shape)
+      got_in = np.concatenate([x[1] for x in gathered]).reshape(shape)
+      same = got.dtype == e_out.dtype and np.array_equal(got, e_out) and np.array_equal(got_in, e_in) and h_map == e_map
+      print("sharded renumber_host_sharded %s world=%d -> %s" % (np.dtype(dtype).name, world, "OK" if same else "MISMATCH"), flush=True)
+      ok = ok and same
     # ---- unique / component_map / remap / mask_except / minmax+pixel_pairs on the same slabs
     from fastremap_b200 import _lib
     n_local = (z1 - z0) * shape[1] * shape[2]

@@ -76,6 +76,7 @@ SIGNATURES = {
   "frb_sort_pairs_u64": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
   "frb_unravel_u16": (_i, [_vp, _sz, _i, _u64, _u64, _vp, _vp]),
   "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _u64, _vp]),
+  "frb_component_unhead": (_i, [_vp, _i, _u64, _u64, _vp, _u64, _vp, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
   "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),

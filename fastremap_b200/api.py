@@ -996,8 +996,10 @@ def component_map_arrays(component_labels, parent_labels, max_labels=None):
   return D.download(keys, nl, vc.dtype), D.download(pars, nl, vp.dtype)
 
 
-def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None, row_bytes=0, plane_bytes=0):
-  """K7 on flat device buffers: returns (keys_buf, parents_buf, n_labels), unordered."""
+def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labels=None, row_bytes=0, plane_bytes=0, prev_label_bits=None):
+  """K7 on flat device buffers: returns (keys_buf, parents_buf, n_labels), unordered.
+  prev_label_bits (sharded volumes): the label the previous slab ended with -- a first voxel that carries it continues a
+  run and does not (re)assign its label (fastremap.pyx:581)."""
   cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
   L = _L()
   table = LabelTable(cc_dtype, _default_entries(n, max_labels), 0)
@@ -1008,10 +1010,15 @@ def component_map_device(cc_buf, n, cc_dtype, parent_buf, parent_dtype, max_labe
 
   meta = _run_build(build, table)
   nl = int(meta[_lib.META_COUNT])
+  if prev_label_bits is not None and n:
+    _lib.check(L.frb_component_unhead(D.ptr(cc_buf), D.code(cc_dtype), int(prev_label_bits) & _lib.EMPTY, 0, D.ptr(table.slots), table.cap,
+                                      D.ptr(table.meta), D.stream()), "frb_component_unhead")
   keys = D.alloc(nl * cc_dtype.itemsize)
   pars = D.alloc(nl * parent_dtype.itemsize)
   _lib.check(L.frb_component_gather(D.ptr(table.slots), table.cap, D.ptr(table.meta), D.code(cc_dtype), D.ptr(parent_buf),
                                     D.code(parent_dtype), 0, D.ptr(keys), D.ptr(pars), nl, D.stream()), "frb_component_gather")
+  if prev_label_bits is not None and n:
+    nl = int(table.read_meta()[_lib.META_LIST_COUNT])  # one label fewer if the slab's first voxel continued a run
   return keys, pars, nl
 
 

@@ -26,14 +26,30 @@ struct GatherSel {
   void* parents_out;
   u64 flat_offset;
   int wc, wp;
-  __device__ __forceinline__ bool pick(u64 key, u64) const { return key != FRB_EMPTY; }
+  __device__ __forceinline__ bool pick(u64 key, u64 val) const { return key != FRB_EMPTY && val != 0; }  // 0: withdrawn (frb_component_unhead)
   __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64) const {
     st_elem_rt(keys_out, wc, pos, key);
     st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(val - 1 - flat_offset)));
   }
 };
+// Sharded volumes: a slab's first voxel was offered as a run start; if it carries the label the previous slab ended
+// with it is not one (fastremap.pyx:581: only cc[i] != cc[i-1] starts a run).  Withdraw that offer -- unless a later
+// run start of the label in this slab has overtaken it anyway.
+__global__ void k_component_unhead(const void* cc, int w, u64 prev_bits, u64 flat_offset, Slot* slots, u64 mask, int direct, u64* meta) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const u64 key = ld_elem_rt(cc, w, 0);
+  if (key != prev_bits) return;
+  if (key == FRB_EMPTY && !direct) { atom_cas_u64(&meta[FRB_META_SIDE_VAL], flat_offset + 1, 0ull); return; }
+  u64 h = direct ? key : home_slot(key, mask);
+  for (int probe = 0; probe < FRB_MAX_PROBE; probe++, h = (h + 1) & mask) {
+    const Slot cur = ld_slot_cg(slots + h);
+    if (cur.key == key) { atom_cas_u64(&slots[h].val, flat_offset + 1, 0ull); return; }
+    if (cur.key == FRB_EMPTY || direct) return;
+  }
+}
+
 __global__ void k_gather_side(u64* meta, GatherSel sel, u64 capacity) {
-  if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {  // the out-of-band all-ones label
+  if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT] && meta[FRB_META_SIDE_VAL] != 0) {  // the out-of-band all-ones label
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
     if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], 0);
   }
@@ -134,6 +150,14 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
 #undef FRB_K7_GEO
 #undef FRB_K7
   return check_launch("k_component_build");
+}
+
+int frb_component_unhead(const void* cc, int cc_dtype, uint64_t prev_bits, uint64_t flat_offset, void* slots, uint64_t cap, uint64_t* meta,
+                         void* stream) {
+  if (!dtype_ok(cc_dtype) || !cc || !slots || !meta || (cap & (cap - 1)) != 0) { set_error("frb_component_unhead: bad arguments"); return FRB_ERR_BAD_ARG; }
+  const int w = dtype_width(cc_dtype);
+  k_component_unhead<<<1, 32, 0, (cudaStream_t)stream>>>(cc, w, trunc_width(prev_bits, w), flat_offset, (Slot*)slots, cap - 1, w <= 2 ? 1 : 0, (u64*)meta);
+  return check_launch("k_component_unhead");
 }
 
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,

@@ -441,8 +441,23 @@ def component_map_sharded(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, m
   from . import device as D
   L = _lib.load()
   cc_dtype, parent_dtype = np.dtype(cc_dtype), np.dtype(parent_dtype)
+  # a run that crosses a slab boundary starts in the EARLIER slab: every rank learns the label its predecessor ended with
+  wc = cc_dtype.itemsize
+  world, rank = dist.get_world_size(group), dist.get_rank(group)
+  last = torch.zeros(2, dtype=torch.int64, device=cc_buf.device)  # [has voxels, last label bits]
+  if n_local:
+    last[0] = 1
+    last[1:2].view(torch.uint8)[:wc] = cc_buf[(n_local - 1) * wc: n_local * wc]
+  lasts = torch.zeros(2 * world, dtype=torch.int64, device=cc_buf.device)
+  dist.all_gather_into_tensor(lasts, last, group=group)
+  lasts_h = lasts.cpu().view(world, 2).tolist()
+  prev = None
+  for r in range(rank - 1, -1, -1):  # nearest non-empty slab in front of this one
+    if lasts_h[r][0]:
+      prev = lasts_h[r][1] & 0xFFFFFFFFFFFFFFFF
+      break
   keys_l, pars_l, nl = api.component_map_device(cc_buf, n_local, cc_dtype, parent_buf, parent_dtype, max_labels=max_labels,
-                                                row_bytes=row_bytes)
+                                                row_bytes=row_bytes, prev_label_bits=prev)
   # widen the raw bit patterns to 64 bits for the exchange
   ucc, upar = np.dtype("u%d" % cc_dtype.itemsize), np.dtype("u%d" % parent_dtype.itemsize)
   k64 = api._cast(keys_l, ucc, np.uint64, nl)[: nl * 8].view(torch.int64)

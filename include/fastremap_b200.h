@@ -263,6 +263,11 @@ int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint
  * row_bytes / plane_bytes: performance hints (0 = unknown), see frb_renumber_build / frb_hist_hash. */
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
                         uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, void* stream);
+/* z-sharded volumes: withdraw the offer frb_component_build made for the slab's first voxel if that voxel carries
+ * prev_bits, the label the previous slab ended with (it continues a run, :581) and no later run start of the label in
+ * this slab has overtaken it; frb_component_gather skips withdrawn labels. */
+int frb_component_unhead(const void* cc, int cc_dtype, uint64_t prev_bits, uint64_t flat_offset, void* slots, uint64_t cap, uint64_t* meta,
+                         void* stream);
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
                          uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream);
 
