@@ -130,11 +130,23 @@ template <int V, int WO>
 __device__ __forceinline__ void store_results(void* dst, size_t i0, const u64 (&r)[V]) {
   constexpr int BYTES = V * WO;
   char* p = (char*)dst + i0 * (size_t)WO;
-  if constexpr (BYTES > 16) {  // widening store (WO == 8 from narrower labels): V / 2 16-byte pieces, lane-contiguous
-    static_assert(WO == 8, "only 8-byte results are wider than the input vector");
+  if constexpr (BYTES > 16 && WO == 8) {  // widening store to 8-byte results: V / 2 16-byte pieces, lane-contiguous
 #pragma unroll
     for (int j = 0; j < V; j += 2)
       st_stream16(p + 8 * j, make_uint4((uint32_t)r[j], (uint32_t)(r[j] >> 32), (uint32_t)r[j + 1], (uint32_t)(r[j + 1] >> 32)));
+  } else if constexpr (BYTES > 16) {  // widening store to 2- or 4-byte results (refit's astype): BYTES / 16 pieces of 16 / WO results
+    constexpr int PER = 16 / WO;
+#pragma unroll
+    for (int q = 0; q < V / PER; q++) {
+      uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const uint32_t x = (uint32_t)r[q * PER + j];
+        if constexpr (WO == 4) { w[j] = x; }
+        else { w[j >> 1] |= (x & 0xFFFFu) << ((j & 1) * 16); }
+      }
+      st_stream16(p + 16 * q, make_uint4(w[0], w[1], w[2], w[3]));
+    }
   } else if constexpr (BYTES == 16) {
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -581,8 +593,8 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // VAR_TILE: the tile length is map.tv (a whole number of volume rows) instead of the constant 16 KiB; a
 // template flag because the constant folds into shifts in loops that are issue-bound (K1 + 18 % otherwise).
 template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
-__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
-                                            TileEndFn tile_end, AfterTileFn after_tile) {
+__device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
+                                                 TileEndFn tile_end, AfterTileFn after_tile) {
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
   constexpr int S = STREAM_STAGES;
@@ -727,15 +739,20 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
     after_tile(k);  // every consumer warp, every tile of the CTA (k is the same in all of them)
   }
 }
+template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
+__device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
+                                            TileEndFn tile_end, AfterTileFn after_tile) {
+  stream_rows_impl<W, REVERSE, NEED_PREV, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, after_tile);
+}
 template <int W, bool REVERSE, bool NEED_PREV, int IL, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
                                             TileEndFn tile_end, AfterTileFn after_tile) {
-  stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, after_tile);
+  stream_rows_impl<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, after_tile);
 }
 template <int W, bool REVERSE, bool NEED_PREV, int IL, typename IDX, typename RowFn, typename TileEndFn>
 __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
                                             TileEndFn tile_end) {
-  stream_rows<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  stream_rows_impl<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }
 // barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }

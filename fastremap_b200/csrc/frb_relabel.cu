@@ -265,6 +265,8 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
         store_results<V, W>(dst_wide, i0, r);
       }
     }
+    // (tried: prefetch.global.L2 of the table sectors the NEXT tile will want while it waits in the ring: 3-4x SLOWER,
+    // remap 3.07 -> 12.4 ms -- two prefetch instructions per voxel swamp the LSU.  Not used.)
   };
   // pw: a plane walk (frb_common.cuh) is possible here but measured SLOWER than the linear walk (remap through 10^6
   // labels 3.49 vs 3.07 ms, mask_except with 5 M labels 5.04 vs 4.18 ms at 1024^3): the hint is accepted and ignored
@@ -325,60 +327,58 @@ static int dispatch_relabel(const void* src, void* dst_wide, void* dst_narrow, i
   return FRB_ERR_BAD_ARG;
 }
 
-// ---------------------------------------------------------------------- single pair replace
-template <int W>
-__global__ void __launch_bounds__(256)
-k_replace_one(const uint4* src, void* dst, size_t n, u64 before, u64 after) {
+// ---------------------------------------------------------------------- element-wise passes on the streaming loop
+// replace_one, remap_from_array and refit's cast are "read a vector, write a vector": the volume comes in through the
+// TMA ring of stream_rows (it may be the destination too: a tile is staged in shared memory before any of it is
+// written), results leave with 16-byte streaming stores.  Fn: void operator()(const uint4& cur, size_t i0, u64 (&r)[V])
+template <int W, int WO, typename Fn>
+__global__ void __launch_bounds__(STREAM_THREADS) k_map_stream(const uint4* src, void* dst, size_t n, Fn fn, int run) {
   constexpr int V = 16 / W;
   const size_t nvec = n / V;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
-    const uint4 v = ld_stream16(src + vi);
+  auto row_fn = [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
+    if (!valid) return;
     u64 r[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) {
-      const u64 k = vec_get<W>(v, j);
-      r[j] = k == before ? after : k;
-    }
-    store_results<V, W>(dst, vi * V, r);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (size_t i = nvec * V; i < n; i++) {
-      const u64 k = ld_elem<W>(src, i);
-      st_elem<W>(dst, i, k == before ? after : k);
-    }
+    for (int j = 0; j < V; j++) r[j] = fn(vec_get<W>(cur, j));
+    store_results<V, WO>(dst, i0, r);
+  };
+  const TileMap map(nvec, (size_t)run);
+  stream_rows<W, false, false, 0>(src, nvec, map, row_fn, [](const uint4*, size_t) {});
+  if (blockIdx.x == 0 && threadIdx.x == 0)  // scalar tail (< V elements)
+    for (size_t i = nvec * V; i < n; i++) st_elem<WO>(dst, i, fn(ld_elem<W>(src, i)));
+}
+template <int W, int WO, typename Fn>
+static int launch_map_stream(const void* src, void* dst, size_t n, const Fn& fn, const char* what, cudaStream_t st) {
+  const size_t tiles = stream_tiles(n, W);
+  const int grid = stream_grid(k_map_stream<W, WO, Fn>, tiles);
+  k_map_stream<W, WO, Fn><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst, n, fn, fair_run(grid, tiles));
+  return check_launch(what);
 }
 
-// ---------------------------------------------------------------------- remap_from_array
+// single pair replace: remap's one-entry fast path (fastremap.pyx:721-729)
+struct ReplaceOne {
+  u64 before, after;
+  __device__ __forceinline__ u64 operator()(u64 k) const { return k == before ? after : k; }
+};
+// remap_from_array (fastremap.pyx:785-789): arr[i] = vals[arr[i]] where arr[i] < len(vals)
 template <int W>
-__global__ void __launch_bounds__(256)
-k_remap_from_array(const uint4* src, void* dst, size_t n, const void* __restrict__ vals, u64 nvals) {
-  constexpr int V = 16 / W;
-  const size_t nvec = n / V;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
-    const uint4 v = ld_stream16(src + vi);
-    u64 r[V];
-#pragma unroll
-    for (int j = 0; j < V; j++) {
-      const u64 k = vec_get<W>(v, j);
-      r[j] = k < nvals ? (u64)__ldg(((const typename UIntOf<W>::type*)vals) + k) : k;
-    }
-    store_results<V, W>(dst, vi * V, r);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (size_t i = nvec * V; i < n; i++) {
-      const u64 k = ld_elem<W>(src, i);
-      st_elem<W>(dst, i, k < nvals ? ld_elem<W>(vals, (size_t)k) : k);
-    }
-}
+struct FromArray {
+  const void* vals;
+  u64 nvals;
+  __device__ __forceinline__ u64 operator()(u64 k) const { return k < nvals ? (u64)__ldg(((const typename UIntOf<W>::type*)vals) + k) : k; }
+};
+// refit's astype (fastremap.pyx:301): widen with the source's signedness, narrow by truncation
+template <int WI, bool SIGNED_IN>
+struct CastElem {
+  __device__ __forceinline__ u64 operator()(u64 k) const { return SIGNED_IN ? sign_extend(k, WI) : k; }
+};
 
 // ---------------------------------------------------------------------- swap halves (edge lists)
 // dst[i] = src[i] with its low and high halves exchanged: an (N, 2) C-order array of w-byte ints,
 // read as N ints of 2w bytes, becomes "column 0 is the high half" -- sorting those ints sorts the
 // rows lexicographically.  The (N,2) packing trick of _two_axis_unique (fastremap.pyx:967-982).
 template <int W>
-__global__ void __launch_bounds__(256) k_swap_halves(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
+__global__ void __launch_bounds__(256) k_swap_halves(const void* src, void* dst, size_t n) {  // dst may be src (no __restrict__)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   constexpr int H = 4 * W;  // bits in a half
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -399,33 +399,27 @@ k_pack_pairs(const void* __restrict__ hi, int whi, const void* __restrict__ lo, 
     out[i] = (ld_elem_rt(hi, whi, i) << lo_bits) | ld_elem_rt(lo, wlo, i);
 }
 
-// ---------------------------------------------------------------------- cast (refit astype)
+// ---------------------------------------------------------------------- cast (refit astype): unaligned fallback
+// (buffers that are not 16-byte aligned cannot go through the TMA ring)
 template <int WI, int WO, bool SIGNED_IN>
-__global__ void __launch_bounds__(256) k_cast(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
-  // element-strided, ELEMS per thread unrolled: each warp instruction touches 32 consecutive elements
-  constexpr int ELEMS = 8;
+__global__ void __launch_bounds__(256) k_cast_elems(const void* __restrict__ src, void* __restrict__ dst, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t base = ((size_t)blockIdx.x * blockDim.x) * ELEMS; base < n; base += stride * ELEMS) {
-    u64 v[ELEMS];
-#pragma unroll
-    for (int e = 0; e < ELEMS; e++) {
-      const size_t i = base + (size_t)e * blockDim.x + threadIdx.x;
-      v[e] = i < n ? ld_elem<WI>(src, i) : 0;
-    }
-#pragma unroll
-    for (int e = 0; e < ELEMS; e++) {
-      const size_t i = base + (size_t)e * blockDim.x + threadIdx.x;
-      if (i < n) st_elem<WO>(dst, i, SIGNED_IN ? sign_extend(v[e], WI) : v[e]);
-    }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 v = ld_elem<WI>(src, i);
+    st_elem<WO>(dst, i, SIGNED_IN ? sign_extend(v, WI) : v);
   }
 }
 
 template <int WI, int WO>
 static int launch_cast(const void* src, void* dst, size_t n, bool signed_in, cudaStream_t st) {
+  if (aligned16(src) && aligned16(dst)) {
+    if (signed_in) return launch_map_stream<WI, WO>(src, dst, n, CastElem<WI, true>(), "k_map_stream<cast>", st);
+    return launch_map_stream<WI, WO>(src, dst, n, CastElem<WI, false>(), "k_map_stream<cast>", st);
+  }
   Grid g = grid_for(n, 256 * 8, 16);
-  if (signed_in) k_cast<WI, WO, true><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
-  else k_cast<WI, WO, false><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
-  return check_launch("k_cast");
+  if (signed_in) k_cast_elems<WI, WO, true><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
+  else k_cast_elems<WI, WO, false><<<g.blocks, g.threads, 0, st>>>(src, dst, n);
+  return check_launch("k_cast_elems");
 }
 
 }  // namespace frb
@@ -511,15 +505,15 @@ int frb_replace_one(const void* src, void* dst, size_t n, int dtype, uint64_t be
   if (n == 0) return FRB_OK;
   const int w = dtype_width(dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, 256 * 4, 16);
-  const u64 b = trunc_width(before, w), af = trunc_width(after, w);
+  ReplaceOne fn;
+  fn.before = trunc_width(before, w);
+  fn.after = trunc_width(after, w);
   switch (w) {
-    case 1: k_replace_one<1><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
-    case 2: k_replace_one<2><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
-    case 4: k_replace_one<4><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
-    default: k_replace_one<8><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, b, af); break;
+    case 1: return launch_map_stream<1, 1>(src, dst, n, fn, "k_map_stream<replace_one>", st);
+    case 2: return launch_map_stream<2, 2>(src, dst, n, fn, "k_map_stream<replace_one>", st);
+    case 4: return launch_map_stream<4, 4>(src, dst, n, fn, "k_map_stream<replace_one>", st);
+    default: return launch_map_stream<8, 8>(src, dst, n, fn, "k_map_stream<replace_one>", st);
   }
-  return check_launch("k_replace_one");
 }
 
 int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals, size_t nvals, int dtype, void* stream) {
@@ -530,14 +524,14 @@ int frb_remap_from_array(const void* src, void* dst, size_t n, const void* vals,
   if (n == 0) return FRB_OK;
   const int w = dtype_width(dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  Grid g = grid_for(n / (16 / w) + 1, 256 * 4, 16);
+#define FRB_FA(WW) { FromArray<WW> fn; fn.vals = vals; fn.nvals = nvals; return launch_map_stream<WW, WW>(src, dst, n, fn, "k_map_stream<remap_from_array>", st); }
   switch (w) {
-    case 1: k_remap_from_array<1><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
-    case 2: k_remap_from_array<2><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
-    case 4: k_remap_from_array<4><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
-    default: k_remap_from_array<8><<<g.blocks, g.threads, 0, st>>>((const uint4*)src, dst, n, vals, nvals); break;
+    case 1: FRB_FA(1)
+    case 2: FRB_FA(2)
+    case 4: FRB_FA(4)
+    default: FRB_FA(8)
   }
-  return check_launch("k_remap_from_array");
+#undef FRB_FA
 }
 
 int frb_swap_halves(const void* src, void* dst, size_t n, int width, void* stream) {

@@ -20,6 +20,9 @@ import torch
 import torch.distributed as dist
 
 
+MERGED_SLOTS_PER_ENTRY = 4
+
+
 def allgather_varlen(t: torch.Tensor, group=None):
   """All-gather of 1-D tensors whose lengths differ per rank (NCCL has no allgatherv): exchange the
   counts, pad to the maximum, gather, slice.  Returns the list of per-rank tensors."""
@@ -90,7 +93,9 @@ def renumber_sharded(src_buf, n_local, dtype, start=1, preserve_zero=True, write
   # remembered per (group, world, dtype, slab size, hint), so a table that had to grow once starts grown next time
   key = (id(group), world, dtype.str, int(n_local), max_labels)
   guess = _exchange_guess.get(key)
-  local = api.LabelTable(dtype, api._default_entries(n_local, max_labels), _lib.EMPTY)
+  # the local table is only built and exported (K3 looks labels up in the rank's compact table): small, so that its
+  # init and export scans are cheap and it stays in L2 while K1 streams the slab
+  local = api.LabelTable(dtype, api._default_entries(n_local, max_labels, voxels_per_label=1024), _lib.EMPTY)
   if guess is not None and not local.direct and guess[2] > local.cap:
     local.cap = guess[2]
     local.slots = D.alloc(local.cap * 16)
@@ -156,8 +161,9 @@ def _two_phase_merge(build, local, dtype, group, world, timers=None):
   api._ev(timers, "xchg_pairs", 1)
 
   api._ev(timers, "insert", 0)
-  # K3 looks every voxel up in this table: size it like a lookup table (load <= 1/8, see api.LOOKUP_SLOTS_PER_ENTRY)
-  merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
+  # the merged table is inserted into, ranked (one scan) and projected from -- K3 never sees it: 4 slots per label
+  # keep its init and K2's scan short (it used to be sized like a per-voxel lookup table, 8+ slots per label)
+  merged = api.LabelTable(dtype, sum(counts), _lib.EMPTY, slots_per_entry=MERGED_SLOTS_PER_ENTRY)
   # the local COUNT word is what every rank exported (export never drops pairs: cap_pairs >= count)
   _lib.check(L.frb_table_insert_gathered(D.ptr(gathered), m, world, D.ptr(metas), _lib.OP_MIN, merged.direct, D.ptr(merged.slots),
                                          merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_gathered")
@@ -247,7 +253,7 @@ def renumber_host_sharded(arr, start=1, preserve_zero=True, group=None, offset=N
   down_w = D.ChunkDownloader(host_u8, s_out)
   down_n = None
   try:
-    local = api.LabelTable(dtype, api._default_entries(n, max_labels), _lib.EMPTY)
+    local = api.LabelTable(dtype, api._default_entries(n, max_labels, voxels_per_label=1024), _lib.EMPTY)
 
     def build(t):
       for i, (a, b) in enumerate(bounds):
@@ -341,7 +347,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   dist.all_gather_into_tensor(gathered, packed[:block], group=group)
   api._ev(timers, "xchg_pairs", 1)
   api._ev(timers, "insert", 0)
-  merged = api.LabelTable(dtype, total_labels, _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
+  merged = api.LabelTable(dtype, total_labels, _lib.EMPTY, slots_per_entry=MERGED_SLOTS_PER_ENTRY)
   _lib.check(L.frb_table_insert_packed(D.ptr(gathered), m, world, 0 if local.direct else local.cap, _lib.OP_MIN, merged.direct,
                                        D.ptr(merged.slots), merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_packed")
   api._ev(timers, "insert", 1)
