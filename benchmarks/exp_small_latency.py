@@ -6,6 +6,8 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 import fastremap_b200 as fr
 from fastremap_b200.synth import synth_numpy
+import bench
+ref, kind = bench.cpu_impl()   # the compiled reference (oracle/_ref) on this box's host, else the oracle port
 for side in (32, 64, 128, 256):
   g = max(side // 22, 1)
   a = synth_numpy((side, side, side), (g, g, g), np.uint64, seed=1, zero_frac=0.1)
@@ -25,4 +27,16 @@ for side in (32, 64, 128, 256):
       if i >= 2:
         best = dt if best is None else min(best, dt)
     row[name + "_ms"] = round(best * 1e3, 3)
+  ref_ops = {"renumber": lambda x: ref.renumber(x, in_place=False), "unique_counts": lambda x: ref.unique(x, return_counts=True),
+             "remap_100": lambda x: ref.remap(x, table, preserve_missing_labels=True), "mask_except_3": lambda x: ref.mask_except(x, [1, 2, 3]),
+             "minmax": ref.minmax}
+  for name, fn in ref_ops.items():
+    best = None
+    for i in range(4):
+      t0 = time.perf_counter()
+      fn(a)
+      dt = time.perf_counter() - t0
+      if i >= 1:
+        best = dt if best is None else min(best, dt)
+    row[name + "_%s_cpu_ms" % kind] = round(best * 1e3, 3)
   print(json.dumps(row), flush=True)

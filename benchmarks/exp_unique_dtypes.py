@@ -22,7 +22,7 @@ for dtype, grid in ((np.uint8, 6), (np.uint16, 36), (np.uint32, 46), (np.uint64,
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    uniq, cts, nu = api.unique_counts_device(vol, n, dtype, row_bytes=S * w)
+    uniq, cts, nu = api.unique_counts_device(vol, n, dtype, row_bytes=S * w, plane_bytes=S * S * w)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

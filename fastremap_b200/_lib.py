@@ -79,6 +79,11 @@ SIGNATURES = {
   "frb_component_unhead": (_i, [_vp, _i, _u64, _u64, _vp, _u64, _vp, _vp]),
   "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
+  "frb_small_table_cap": (_u64, [_sz, _i]),
+  "frb_small_list_capacity": (_sz, [_sz, _i]),
+  "frb_small_ws_bytes": (_sz, [_sz, _i]),
+  "frb_renumber_small": (_i, [_vp, _sz, _i, _i64, _i, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
+  "frb_unique_small": (_i, [_vp, _sz, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
   "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),
   "frb_set_device": (_i, [_i]),
   "frb_set_tile_run": (None, [_i]),

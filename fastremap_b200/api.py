@@ -313,7 +313,10 @@ def refit(arr, value=None, increase_only=False, exotics=False):
 
 class RenumberResult:
   """Device-side result of the renumber kernels (all buffers are flat uint8 CUDA tensors)."""
-  __slots__ = ("out", "out_dtype", "keys", "ids", "n_labels", "table", "wide")
+  __slots__ = ("out", "out_dtype", "keys", "ids", "n_labels", "table", "wide", "keys_host", "ids_host")
+
+  def __init__(self):
+    self.keys_host = self.ids_host = None  # set by the small-array path: the mapping came back with the counters
 
 
 def _ev(timers, name, which):
@@ -475,6 +478,81 @@ def _renumber_finish(src_buf, n, dtype, start, preserve_zero, write_wide, table,
   return res
 
 
+# ------------------------------------------------------------------------------------- small arrays
+# Up to this many voxels renumber / unique run as ONE cooperative kernel (csrc/frb_small.cu): a dozen launches and two
+# host round trips are what a 32^3 call used to cost (0.4-0.5 ms; the reference's serial loop: 0.1 ms).
+SMALL_MAX_VOXELS = 1 << 21
+
+
+def _small_buffers(n, dtype):
+  """(workspace, head) for the small kernels: head = [meta | keys | ids] comes back to the host with one copy."""
+  L = _L()
+  c = D.code(dtype)
+  w = np.dtype(dtype).itemsize
+  cap_list = int(L.frb_small_list_capacity(n, c))
+  ws_bytes = int(L.frb_small_ws_bytes(n, c))
+  ws = D.alloc(ws_bytes)
+  lb = (cap_list * max(w, 8) + 255) // 256 * 256
+  head = D.alloc(128 + 2 * lb)
+  return ws, ws_bytes, head, lb, cap_list
+
+
+def _renumber_small(src_buf, n, dtype, start, preserve_zero, write_wide):
+  """renumber of a small flat device buffer with one kernel launch.  Returns a RenumberResult (mapping already on the
+  host), or None when the array holds more labels than the small table takes (src_buf is untouched then) or the
+  refit width is not a monotone function of the label count (negative / wrapping `start`)."""
+  dtype = np.dtype(dtype)
+  limits = _narrow_limits(dtype, start, n)
+  if limits is None:
+    return None
+  L = _L()
+  w = dtype.itemsize
+  ws, ws_bytes, head, lb, cap_list = _small_buffers(n, dtype)
+  narrow = D.alloc(n * w)
+  wide = src_buf if write_wide else D.alloc(n * w)  # the relabel phase reads a[i] and writes out[i]: aliasing is safe
+  meta_ptr = ctypes.c_void_p(head.data_ptr())
+  keys_ptr = ctypes.c_void_p(head.data_ptr() + 128)
+  ids_ptr = ctypes.c_void_p(head.data_ptr() + 128 + lb)
+  _lib.check(L.frb_renumber_small(D.ptr(src_buf), n, D.code(dtype), int(np.int64(start)), 1 if preserve_zero else 0, D.ptr(wide), D.ptr(narrow),
+                                  limits[0], limits[1], limits[2], keys_ptr, ids_ptr, meta_ptr, D.ptr(ws), ws_bytes, D.stream()),
+             "frb_renumber_small")
+  host = head.cpu().numpy()                       # the one host round trip: counters + mapping
+  meta = host[:128].view(np.uint64)
+  if meta[_lib.META_OVERFLOW]:
+    return None
+  nl = int(meta[_lib.META_ASSIGNED])
+  res = RenumberResult()
+  res.n_labels, res.table = nl, None
+  res.keys, res.ids = head[128:128 + lb], head[128 + lb:128 + 2 * lb]
+  res.keys_host = host[128:128 + nl * w].view(dtype)
+  res.ids_host = host[128 + lb:128 + lb + nl * w].view(dtype)
+  res.out_dtype = _out_dtype(dtype, start, nl)
+  res.wide = wide
+  if res.out_dtype.itemsize < w:
+    res.out = narrow
+  elif res.out_dtype.itemsize == w:
+    res.out = wide
+  else:
+    res.out = _cast(wide, dtype, res.out_dtype, n)
+  return res
+
+
+def _unique_small(buf, n, dtype):
+  """(uniq_buf, counts_buf, n_unique) of a small flat device buffer with one kernel launch, or None (too many labels)."""
+  dtype = np.dtype(dtype)
+  L = _L()
+  w = dtype.itemsize
+  ws, ws_bytes, head, lb, cap_list = _small_buffers(n, dtype)
+  meta_ptr = ctypes.c_void_p(head.data_ptr())
+  uniq_ptr = ctypes.c_void_p(head.data_ptr() + 128)
+  cts_ptr = ctypes.c_void_p(head.data_ptr() + 128 + lb)
+  _lib.check(L.frb_unique_small(D.ptr(buf), n, D.code(dtype), uniq_ptr, cts_ptr, meta_ptr, D.ptr(ws), ws_bytes, D.stream()), "frb_unique_small")
+  meta = D.read_u64(head[:128].view(torch.int64))
+  if meta[_lib.META_OVERFLOW]:
+    return None
+  return head[128:128 + lb], head[128 + lb:128 + 2 * lb], int(meta[_lib.META_LIST_COUNT])
+
+
 # Host arrays at least this large are renumbered by the chunk pipeline below.
 STREAM_MIN_BYTES = 256 << 20
 STREAM_CHUNK_BYTES = 128 << 20
@@ -612,8 +690,11 @@ def _renumber_streamed_run(arr, start, preserve_zero, in_place_eff, dtype, order
 
 
 def _mapping_to_dict(res: RenumberResult, dtype, preserve_zero) -> dict:
-  keys = D.download(res.keys, res.n_labels, dtype).tolist()
-  ids = D.download(res.ids, res.n_labels, dtype).tolist()
+  if res.keys_host is not None:
+    keys, ids = res.keys_host.tolist(), res.ids_host.tolist()
+  else:
+    keys = D.download(res.keys, res.n_labels, dtype).tolist()
+    ids = D.download(res.ids, res.n_labels, dtype).tolist()
   mapping = {0: 0} if preserve_zero else {}
   mapping.update(zip(keys, ids))
   return mapping
@@ -649,8 +730,10 @@ def renumber(arr, start=1, preserve_zero=True, in_place=False, *, max_labels=Non
         arr = np.copy(arr, order="C")
       return _renumber_streamed(arr, start, preserve_zero, in_place_eff, max_labels)
     v = D.ingest(arr)
-  res = renumber_device(v.buf, v.n, v.dtype, start=start, preserve_zero=preserve_zero, write_wide=in_place_eff,
-                        max_labels=max_labels, row_bytes=v.row_bytes)
+  res = _renumber_small(v.buf, v.n, v.dtype, start, preserve_zero, in_place_eff) if v.n <= SMALL_MAX_VOXELS else None
+  if res is None:
+    res = renumber_device(v.buf, v.n, v.dtype, start=start, preserve_zero=preserve_zero, write_wide=in_place_eff,
+                          max_labels=max_labels, row_bytes=v.row_bytes)
   mapping = _mapping_to_dict(res, v.dtype, preserve_zero)
 
   if is_t:
@@ -1193,6 +1276,10 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_byte
   c = D.code(dtype)
   L = _L()
   if strategy is None:
+    if n <= SMALL_MAX_VOXELS:
+      small = _unique_small(buf, n, dtype)
+      if small is not None:
+        return small
     # The per-warp aggregating cache in front of the table makes the hash strategy as fast as the
     # dense histogram, and it needs no min/max pre-pass over the volume.
     strategy = "hash"

@@ -324,7 +324,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
     const int sl = hist_slot<DU>(u);  // a constant once the row loop is unrolled
     const uint4 l = pat[sl];
     const uint32_t d = (cur.x ^ l.x) | (cur.y ^ l.y) | (cur.z ^ l.z) | (cur.w ^ l.w);
-    const bool same = d == 0 && rep[sl] != 0;
+    const bool same = valid && d == 0 && rep[sl] != 0;
+    // the common case first, and cheap (this loop is issue-bound): every lane saw the row above again
+    if (__all_sync(FRB_FULL_MASK, same)) {
+      rep[sl]++;
+      return;
+    }
     retire(valid && !same && rep[sl] != 0, l, rep[sl]);
     if (valid) {
       if (same) {
@@ -580,6 +585,10 @@ template <int W, typename Pred, typename Emit>
 __global__ void __launch_bounds__(256)
 k_select_emit(const uint4* __restrict__ a, size_t n, size_t chunk, Pred pred, const u64* __restrict__ block_offs, Emit emit, size_t capacity) {
   constexpr int V = 16 / W;
+  // positions (inside the step's 256 * V voxels) of the hits, in order: the hits of a step leave the CTA through
+  // this list so that consecutive threads write consecutive output elements -- written straight from the vector
+  // loop, a dense selection (point_cloud: 90 % foreground) stored with a stride of V elements per lane, 0.30 of peak
+  __shared__ unsigned short s_off[256 * V];
   const size_t beg = (size_t)blockIdx.x * chunk;
   size_t end = beg + chunk;
   if (end > n) end = n;
@@ -587,21 +596,26 @@ k_select_emit(const uint4* __restrict__ a, size_t n, size_t chunk, Pred pred, co
   u64 run = block_offs[blockIdx.x];
   for (size_t base = beg / V; base < vend; base += 256) {
     const size_t vi = base + threadIdx.x;
-    uint4 v = make_uint4(0, 0, 0, 0);
     unsigned int m = 0;
     if (vi < vend) {
-      v = ld_stream16(a + vi);
+      const uint4 v = ld_stream16(a + vi);
 #pragma unroll
       for (int j = 0; j < V; j++) m |= pred(vec_get<W>(v, j)) ? (1u << j) : 0u;
     }
     unsigned int tot;
-    u64 pos = run + block_count_scan((unsigned int)__popc(m), &tot);
+    unsigned int p = block_count_scan((unsigned int)__popc(m), &tot);
 #pragma unroll
     for (int j = 0; j < V; j++)
-      if ((m >> j) & 1u) {
-        if (pos < capacity) emit(pos, vec_get<W>(v, j), (u64)(vi * V + j));
-        pos++;
+      if ((m >> j) & 1u) s_off[p++] = (unsigned short)(threadIdx.x * V + j);
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < tot; q += 256) {
+      const u64 pos = run + q;
+      if (pos < capacity) {
+        const size_t i = base * V + s_off[q];
+        emit(pos, ld_elem<W>(a, i), (u64)i);  // the element has just been read: an L1 / L2 hit
       }
+    }
+    __syncthreads();
     run += tot;
   }
   if (threadIdx.x == 0)

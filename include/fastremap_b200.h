@@ -294,6 +294,23 @@ void frb_set_tile_run(int run);
 uint64_t frb_launch_count(void);
 const char* frb_last_error(void);
 
+/* ---- small arrays (up to ~2^21 voxels): one cooperative kernel per call ---------------------------
+ * renumber (fastremap.pyx:196-257 + the refit astype :301) and unique(return_counts) (:855-965) with every phase --
+ * table init, build, compaction, sort, rank / emit, relabel -- inside ONE cooperatively launched kernel, grid barriers
+ * in between: a 32^3 chunk costs one launch instead of a dozen.  Same results as the volume-sized entry points.
+ * meta[FRB_META_OVERFLOW] != 0 afterwards: more labels than the small table holds (frb_small_list_capacity) -- nothing
+ * usable was written, take the volume-sized path.  meta[FRB_META_ASSIGNED] (renumber) / meta[FRB_META_LIST_COUNT]
+ * (unique): number of labels.  narrow_out (n * width bytes) receives the ids at the refit width picked from
+ * lim1 / lim2 / lim4 like frb_relabel_auto (nothing if no narrower dtype fits: use wide_out, which may alias src). */
+uint64_t frb_small_table_cap(size_t n, int dtype);
+size_t frb_small_list_capacity(size_t n, int dtype);
+size_t frb_small_ws_bytes(size_t n, int dtype);
+int frb_renumber_small(const void* src, size_t n, int dtype, int64_t start, int skip_zero, void* wide_out, void* narrow_out,
+                       uint64_t lim1, uint64_t lim2, uint64_t lim4, void* keys_out, void* ids_out, uint64_t* meta, void* ws,
+                       size_t ws_bytes, void* stream);
+int frb_unique_small(const void* src, size_t n, int dtype, void* uniq_out, uint64_t* counts_out, uint64_t* meta, void* ws,
+                     size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,18 @@ def synth(*a, **k):
   return synth_numpy(*a, **k)
 
 
+@pytest.fixture(autouse=True, params=["fused_small_kernels", "volume_kernels"])
+def both_size_regimes(request):
+  """Arrays of up to 2^21 voxels take the one-launch kernels of csrc/frb_small.cu; every test of this module runs a
+  second time with that path switched off, so that the volume-sized kernels keep seeing the same (small) cases."""
+  from fastremap_b200 import api
+  saved = api.SMALL_MAX_VOXELS
+  if request.param == "volume_kernels":
+    api.SMALL_MAX_VOXELS = 0
+  yield
+  api.SMALL_MAX_VOXELS = saved
+
+
 # ------------------------------------------------------------------ committed fixtures of the compiled reference
 
 _SKIP_FNS = ()
