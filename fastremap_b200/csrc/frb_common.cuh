@@ -1,11 +1,12 @@
 // frb_common.cuh -- shared device helpers for the fastremap_b200 kernels (sm_100a).
 //
-// Every kernel in this library is an HBM-bound integer streaming kernel.  The common
-// shape is: a warp reads one "row" of 32 x 16 B = 512 contiguous bytes per load
-// instruction (ld.global.nc.L1::no_allocate.v4 -- the volume is read once, keep it out of
-// L1 so the label table can live there), each lane unpacks V = 16 / W elements of width W,
-// and a CTA of 256 threads owns a tile of ROWS_PER_WARP rows per warp.  Grids are sized to
-// a multiple of the SM count (148 on B200) and walk tiles with a grid stride.
+// Every kernel in this library is an HBM-bound integer streaming kernel.  The common shape (stream_rows below): the
+// volume is staged through shared memory by the TMA engine -- a producer warp issues one 1-D bulk copy
+// (cp.async.bulk, SASS UBLKCP) per 16 KiB tile into a 3-deep ring guarded by mbarriers -- and 8 consumer warps read
+// rows of 32 x 16 B = 512 contiguous bytes with conflict-free LDS.128, each lane unpacking V = 16 / W elements of
+// width W.  Grids are persistent (co-resident CTAs x 148 SMs on B200); tiles are dealt to CTAs in runs (TileMap) or,
+// for the kernels that aggregate per label, band by band through stacks of planes (PlaneWalk).  Label tables are
+// open-addressing arrays of 16-byte slots with even home slots (one 32-byte sector = the first two probes).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -566,8 +567,29 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Polling an mbarrier is a shared-memory access; warps that spin on it steal shared-memory
-// bandwidth from the TMA engine that is trying to deliver their data, so back off between probes.
+// Polling an mbarrier is a shared-memory access; warps that spin on it steal shared-memory bandwidth from the TMA
+// engine that is trying to deliver their data, so back off between probes.
+#ifdef FRB_MBAR_HINT
+// experiment: let the hardware park the thread (try_wait with a suspend-time hint) instead of a nanosleep loop,
+// whose instructions were 30 % of everything k_hist issued
+__device__ __forceinline__ bool mbar_try_wait_hint(void* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait_hint(bar, parity, FRB_MBAR_HINT)) {}
+}
+#else
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned int ns = 32;
@@ -576,6 +598,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
     if (ns < 256) ns <<= 1;
   }
 }
+#endif
 // 1-D bulk copy global -> shared through the TMA engine, completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
