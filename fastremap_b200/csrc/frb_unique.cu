@@ -107,7 +107,7 @@ struct HistEvicted {
   u64 key;
   unsigned int cnt;
 };
-__device__ __noinline__ HistEvicted hist_map_add(u64 key, unsigned int c, bool act) {
+__device__ __forceinline__ HistEvicted hist_map_add(u64 key, unsigned int c, bool act) {  // one call site, inside the out-of-line hist_process
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u64* const s_key = hs_key[warp];
   unsigned int* const s_cnt = hs_cnt[warp];
