@@ -56,6 +56,12 @@ def flat_u8(t):
   return t.reshape(-1).view(torch.uint8)
 
 
+def digest(buf, nbytes=None):
+  """order-independent 64-bit digest of a device buffer of 8-byte words (A/B runs of kernel variants must agree)"""
+  v = (buf if nbytes is None else buf[:nbytes]).view(torch.int64)
+  return "%016x" % ((int(v.sum().item()) ^ (int((v * 0x1E3779B97F4A7C15 - 0x61C8864680B583EB >> 7).sum().item()) << 1)) & 0xFFFFFFFFFFFFFFFF)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--side", type=int, default=1024)
@@ -108,7 +114,7 @@ def main():
     work = torch.empty_like(vol)
     m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_KEEP, dst_wide=work, batch_rows=api._batch_rows(L), plane_bytes=PL * S * S * 8), args.reps,
                      setup=lambda: work.copy_(vol))
-    report("remap u64 in place, %d-entry table, preserve_missing_labels (config 3)" % L, n, 16, m, mn, labels_in_volume=nu)
+    report("remap u64 in place, %d-entry table, preserve_missing_labels (config 3)" % L, n, 16, m, mn, labels_in_volume=nu, digest=digest(work))
     del vol, work, table
 
   if "mask_except" in ops or "component_map" in ops:
@@ -123,12 +129,13 @@ def main():
       work = torch.empty_like(cc)
       m, mn, _ = timed(lambda: api._relabel(work, n, np.uint64, table, _lib.MISS_FILL, fill_bits=0, dst_wide=work, batch_rows=api._batch_rows(keep.numel()), plane_bytes=PL * S * S * 8), args.reps,
                        setup=lambda: work.copy_(cc))
-      report("mask_except u64 in place, %d kept of %d labels (config 5)" % (keep.numel(), nu), n, 16, m, mn)
+      report("mask_except u64 in place, %d kept of %d labels (config 5)" % (keep.numel(), nu), n, 16, m, mn, digest=digest(work))
       del work, table, uniq, keep, kb
     if "component_map" in ops:
       par = flat_u8(synth_device((S, S, S), (g, g, g), np.uint64, seed=5, zero_frac=0.0, cell_div=4))
       m, mn, out = timed(lambda: api.component_map_device(cc, n, np.uint64, par, np.uint64, max_labels=g ** 3, row_bytes=S * 8, plane_bytes=PL * S * S * 8), args.reps)
-      report("component_map (u64, u64) device arrays (config 5)", n, 16, m, mn, n_components=out[2])
+      report("component_map (u64, u64) device arrays (config 5)", n, 16, m, mn, n_components=out[2],
+             digest=digest(out[0], out[2] * 8) + digest(out[1], out[2] * 8))
       del par
     del cc
 

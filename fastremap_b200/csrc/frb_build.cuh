@@ -23,6 +23,7 @@
 namespace frb {
 
 static constexpr int BUILD_CACHE = 256;  // entries in the per-warp set of labels already offered
+static constexpr int BUILD_QUEUE = 64;   // K7: offers a warp has queued for its next batch of 32 (see build_pass)
 
 // out-of-line find-or-insert + combine (the rare path of the build kernels; keeps their hot loops small)
 template <int OP>
@@ -40,7 +41,16 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
                                            int tile_vecs, PlaneWalk pw) {
   constexpr int V = 16 / W;
   typedef typename UIntOf<W>::type T;
+  // QUEUED (K7, round 2): what survives the filters is not offered by the lane that found it but appended to a per-warp
+  // queue; whenever 32 offers wait, every lane takes ONE, reads its home slot now and settles it at the next tile end
+  // straight from that copy (present: one fire-and-forget reduction; empty: one CAS).  The old scheme below -- one
+  // deferred offer per lane, the rest synchronously -- left the warp waiting for two dependent round trips (re-read +
+  // CAS) in most tiles at 10^7 labels, because with 0.35 offers per lane and tile SOME lane nearly always had two
+  // (ncu, profiles/r02_ncu_full_component_map.csv: no unit above 35 % of its peak, 2 us per tile and CTA).
+  constexpr bool QUEUED = HEADS;
   __shared__ u64 s_seen[8][BUILD_CACHE];
+  __shared__ Slot s_queue[QUEUED ? 8 : 1][QUEUED ? BUILD_QUEUE : 1];
+  unsigned int qn = 0;  // entries in this warp's queue (the same value in every lane)
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int inserted = 0;  // labels this lane has inserted ...
@@ -118,9 +128,36 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
 
   auto resolve_pending = [&]() {
     if (pend) {
-      if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval))) offer(pkey, pval);
+      if (QUEUED) {
+        Slot* s = slots + (direct ? pkey : home_slot(pkey, mask));
+        if (pslot.key == pkey) {
+          if (!op_settled<OP>(pslot.val, pval)) op_apply<OP>(&s->val, pval);
+        } else if (pslot.key == FRB_EMPTY) {
+          const u64 old = atom_cas_u64(&s->key, FRB_EMPTY, pkey);
+          if (old == FRB_EMPTY) inserted++;
+          if (old == FRB_EMPTY || old == pkey) op_apply<OP>(&s->val, pval);
+          else offer(pkey, pval);
+        } else {
+          offer(pkey, pval);
+        }
+      } else if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval))) {
+        offer(pkey, pval);
+      }
       pend = false;
     }
+  };
+  // QUEUED: every lane takes one queued offer (from the tail) and reads its home slot; settled by resolve_pending
+  auto take_batch = [&]() {
+    const unsigned int take = qn < 32u ? qn : 32u;
+    if ((unsigned int)lane < take) {
+      const Slot e = s_queue[warp][qn - 1u - (unsigned int)lane];
+      pend = true;
+      pkey = e.key;
+      pval = e.val;
+      pslot = ld_slot_cg(slots + (direct ? pkey : home_slot(pkey, mask)));
+    }
+    qn -= take;
+    __syncwarp();
   };
 
   auto tile_end = [&](const uint4* stage, size_t vb) {
@@ -138,6 +175,37 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
     cand = 0;
     __syncwarp();
     // phase 2: remember them and queue / send the offers
+    if constexpr (QUEUED) {
+      u64 t = todo;
+      while (true) {
+        const bool has = t != 0;
+        if (!__any_sync(FRB_FULL_MASK, has)) break;
+        u64 key = 0, val = 0;
+        if (has) {
+          const unsigned int b = (unsigned int)(__ffsll((long long)t) - 1);
+          t &= t - 1;
+          const unsigned int u = b / V, j = b % V;
+          key = (u64)reinterpret_cast<const T*>(stage + stream_vec<IL>(u, warp, lane))[j];
+          val = bias + (u64)((vb + stream_vec<IL>(u, warp, lane)) * V + j);
+          s_seen[warp][(hash_key(key) >> 48) & (BUILD_CACHE - 1)] = key;
+        }
+        const bool queueable = has && (direct || key != FRB_EMPTY);  // the out-of-band all-ones label goes straight to the table
+        const unsigned int bal = __ballot_sync(FRB_FULL_MASK, queueable);
+        const unsigned int pos = qn + __popc(bal & ((1u << lane) - 1u));
+        if (queueable && pos < (unsigned int)BUILD_QUEUE) {
+          Slot e;
+          e.key = key;
+          e.val = val;
+          s_queue[warp][pos] = e;
+        } else if (has) {
+          offer(key, val);  // queue full (noise volumes): straight to the table
+        }
+        qn += __popc(bal);
+        if (qn > (unsigned int)BUILD_QUEUE) qn = BUILD_QUEUE;
+      }
+      __syncwarp();
+      if (qn >= 32u) take_batch();
+    } else {
     for (u64 m = todo; m; m &= m - 1) {
       const unsigned int b = (unsigned int)(__ffsll((long long)m) - 1);
       const unsigned int u = b / V, j = b % V;
@@ -153,6 +221,7 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
       } else {
         offer(key, val);
       }
+    }
     }
     __syncwarp();
     // every 16th tile the warp adds what it has inserted to the global count (one atomic per warp) and
@@ -179,6 +248,12 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw) : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
   stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
   resolve_pending();
+  if (QUEUED && warp < STREAM_WARPS) {  // what is still queued (the producer warp's qn is 0)
+    while (qn) {
+      take_batch();
+      resolve_pending();
+    }
+  }
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);
 }
 

@@ -27,9 +27,10 @@ struct GatherSel {
   u64 flat_offset;
   int wc, wp;
   __device__ __forceinline__ bool pick(u64 key, u64 val) const { return key != FRB_EMPTY && val != 0; }  // 0: withdrawn (frb_component_unhead)
-  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64) const {
+  __device__ __forceinline__ u64 fetch(u64, u64 val) const { return ld_elem_rt(parent, wp, (size_t)(val - 1 - flat_offset)); }
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64, u64, u64 fetched) const {
     st_elem_rt(keys_out, wc, pos, key);
-    st_elem_rt(parents_out, wp, pos, ld_elem_rt(parent, wp, (size_t)(val - 1 - flat_offset)));
+    st_elem_rt(parents_out, wp, pos, fetched);
   }
 };
 // Sharded volumes: a slab's first voxel was offered as a run start; if it carries the label the previous slab ended
@@ -51,7 +52,7 @@ __global__ void k_component_unhead(const void* cc, int w, u64 prev_bits, u64 fla
 __global__ void k_gather_side(u64* meta, GatherSel sel, u64 capacity) {
   if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT] && meta[FRB_META_SIDE_VAL] != 0) {  // the out-of-band all-ones label
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
-    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], 0);
+    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], 0, sel.fetch(FRB_EMPTY, meta[FRB_META_SIDE_VAL]));
   }
 }
 

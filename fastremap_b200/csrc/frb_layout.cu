@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(256) k_transpose_tiles(const __grid_constant__
 // row segment read or written is 256 bytes, which is what DRAM wants (128-byte segments reach ~0.6 of
 // the copy bandwidth, 256-byte ones ~0.9).  Needs A, B and every stride divisible by R and 4-byte
 // aligned bases.  Dynamic shared memory: (32HR) * (32H) words.
-template <int W, int H>
+// M: merged tile axes, as in k_transpose_tiles -- what makes the chunk grids of tobytes (64-byte rows inside a chunk)
+// eligible: A = (z in chunk) x (chunk index along z), B = (x in chunk) x (y in chunk) are both thousands long.
+template <int W, int H, bool M>
 __global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant__ LayoutArgs P) {
   constexpr int R = 4 / W;
   constexpr int TW = 32 * H;  // tile edge in words
@@ -183,7 +185,6 @@ __global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant_
   const uint32_t* __restrict__ in = (const uint32_t*)P.in;
   uint32_t* __restrict__ out = (uint32_t*)P.out;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u64 in_sb_w = P.in_sb / R, out_sa_w = P.out_sa / R;
   for (u64 t = blockIdx.x; t < P.total; t += gridDim.x) {
     u64 r = t;
     const u64 ta = r % P.tiles_a;
@@ -209,7 +210,9 @@ __global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant_
         for (int j = 0; j < R; j++) {
           const u64 b = b0 + (u64)R * rb + j;
 #pragma unroll
-          for (int h = 0; h < H; h++) w[ii][h][j] = (a_ok[h] && b < P.B) ? __ldcs(src + b * in_sb_w + 32 * h) : 0u;
+          const u64 row_w = b < P.B ? in_row_offset<M>(P, b) / R : 0;
+#pragma unroll
+          for (int h = 0; h < H; h++) w[ii][h][j] = (a_ok[h] && b < P.B) ? __ldcs(src + row_w + 32 * h) : 0u;
         }
       }
 #pragma unroll
@@ -244,9 +247,10 @@ __global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant_
     for (int i = 0; i < 4 * H * R; i++) {
       const int a = warp + 8 * i;
       if (a0 + a < P.A) {
+        const u64 row_w = out_row_offset<M>(P, a0 + a) / R;
 #pragma unroll
         for (int h = 0; h < H; h++)
-          if (b_ok[h]) __stcs(dst + (a0 + a) * out_sa_w + 32 * h, S[a * TW + ((lane + 32 * h + a / R) & (TW - 1))]);
+          if (b_ok[h]) __stcs(dst + row_w + 32 * h, S[a * TW + ((lane + 32 * h + a / R) & (TW - 1))]);
       }
     }
     __syncthreads();
@@ -315,29 +319,6 @@ static bool fill_batch(LayoutArgs& P, int nbatch, const uint64_t* dims, const ui
 template <int W>
 static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
   const u64 max_grid = (u64)sm_count() * 64;
-  if constexpr (W <= 2) {
-    constexpr u64 R = 4 / W;
-    u64 bits = P.A | P.B | P.in_sb | P.out_sa;
-    for (int j = 0; j < P.nb; j++) bits |= P.bis[j] | P.bos[j];
-    const bool aligned = bits % R == 0 && (uintptr_t)P.in % 4 == 0 && (uintptr_t)P.out % 4 == 0;
-    // 256-byte segments (H = 2) when both axes fill most of such a tile; 128-byte ones only pay for bytes
-    const int H = (P.A >= 48 * R && P.B >= 48 * R) ? 2 : ((W == 1 && P.A >= 32 * R && P.B >= 32 * R) ? 1 : 0);
-    if (aligned && H) {
-      const u64 T = 32 * H * R;
-      P.tiles_a = (P.A + T - 1) / T;
-      P.tiles_b = (P.B + T - 1) / T;
-      P.total = P.tiles_a * P.tiles_b * batches;
-      const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
-      const size_t smem = (size_t)T * 32 * H * sizeof(uint32_t);
-      if (H == 2) {
-        cudaFuncSetAttribute(k_transpose_packed<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device: always
-        k_transpose_packed<W, 2><<<grid, 256, smem, st>>>(P);
-      } else {
-        k_transpose_packed<W, 1><<<grid, 256, smem, st>>>(P);
-      }
-      return check_launch("k_transpose_packed");
-    }
-  }
   // A short tile axis makes short row segments (DRAM wants >= 256 bytes).  If a batch axis continues it
   // contiguously (in the input for A, in the output for B) the two are walked as ONE tile axis, e.g. the
   // channel axis of an (x, y, z, c) array together with z, or a chunk's rows across the chunk grid.
@@ -354,8 +335,8 @@ static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
     }
     P.nb--;
   };
-  constexpr u64 SHORT = 64;
-  if (P.A < SHORT && P.A > 1)
+  constexpr u64 SHORT = W >= 4 ? 64 : 512 / W;  // elements: rows under 256 bytes (4-/8-byte: 64 elements, as tuned), 512 bytes for 1-/2-byte (one packed tile edge is 256)
+  if (P.A < SHORT && P.A > 1 && P.A <= 0xFFFFFFFFull)
     for (int j = 0; j < P.nb; j++)
       if (P.bis[j] == P.A && P.A * P.bd[j] <= 0xFFFFFFFFull) {
         P.out_sa1 = P.bos[j];
@@ -365,7 +346,7 @@ static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
         merged = true;
         break;
       }
-  if (P.B < SHORT && P.B > 1)
+  if (P.B < SHORT && P.B > 1 && P.B <= 0xFFFFFFFFull)
     for (int j = 0; j < P.nb; j++)
       if (P.bos[j] == P.B && P.B * P.bd[j] <= 0xFFFFFFFFull) {
         P.in_sb1 = P.bis[j];
@@ -377,6 +358,31 @@ static int launch_transpose(LayoutArgs& P, u64 batches, cudaStream_t st) {
       }
   P.ai_magic = P.Ai > 1 ? ~0ull / P.Ai + 1 : 0;
   P.bi_magic = P.Bi > 1 ? ~0ull / P.Bi + 1 : 0;
+  if constexpr (W <= 2) {
+    constexpr u64 R = 4 / W;
+    u64 bits = P.A | P.B | P.in_sb | P.out_sa | P.Ai | P.Bi | P.in_sb1 | P.out_sa1;
+    for (int j = 0; j < P.nb; j++) bits |= P.bis[j] | P.bos[j];
+    const bool aligned = bits % R == 0 && (uintptr_t)P.in % 4 == 0 && (uintptr_t)P.out % 4 == 0;
+    // 256-byte segments (H = 2) when both axes fill most of such a tile; 128-byte ones only pay for bytes
+    const int H = (P.A >= 48 * R && P.B >= 48 * R) ? 2 : ((W == 1 && P.A >= 32 * R && P.B >= 32 * R) ? 1 : 0);
+    if (aligned && H) {
+      const u64 T = 32 * H * R;
+      P.tiles_a = (P.A + T - 1) / T;
+      P.tiles_b = (P.B + T - 1) / T;
+      P.total = P.tiles_a * P.tiles_b * batches;
+      const unsigned int grid = (unsigned int)(P.total < max_grid ? P.total : max_grid);
+      const size_t smem = (size_t)T * 32 * H * sizeof(uint32_t);
+#define FRB_PACKED(HH, MM)                                                                                              \
+  {                                                                                                                     \
+    cudaFuncSetAttribute(k_transpose_packed<W, HH, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); /* per device: always */ \
+    k_transpose_packed<W, HH, MM><<<grid, 256, smem, st>>>(P);                                                          \
+  }
+      if (H == 2) { if (merged) FRB_PACKED(2, true) else FRB_PACKED(2, false) }
+      else { if (merged) FRB_PACKED(1, true) else FRB_PACKED(1, false) }
+#undef FRB_PACKED
+      return check_launch("k_transpose_packed");
+    }
+  }
   const bool small = P.A <= 32 || P.B <= 32;  // short axes: 32 x 32 tiles waste less
   const int T = small ? 32 : 64;
   P.tiles_a = (P.A + T - 1) / T;

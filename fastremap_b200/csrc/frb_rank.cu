@@ -34,7 +34,8 @@ struct PendingSel {
   __device__ __forceinline__ bool pick(u64 key, u64 val) const {
     return key != FRB_EMPTY && (val & RANK_TAG) && ((val & ~RANK_TAG) - index_base) < index_count;
   }
-  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot) const {
+  __device__ __forceinline__ u64 fetch(u64, u64) const { return 0; }
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot, u64) const {
     key_out[pos] = (val & ~RANK_TAG) - index_base;
     slot_out[pos] = slot;
     label_out[pos] = key;
@@ -43,7 +44,7 @@ struct PendingSel {
 __global__ void k_pending_side(u64 cap, u64* meta, PendingSel sel, u64 capacity) {
   if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT] && sel.pick(0, meta[FRB_META_SIDE_VAL])) {
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
-    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], cap);  // "slot cap" = the out-of-band all-ones key
+    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], cap, 0);  // "slot cap" = the out-of-band all-ones key
   }
 }
 

@@ -288,6 +288,15 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
   }
 }
 
+// Tried in round 2 and removed (profiles/r02b_k3_variants.jsonl): "probe run heads only" -- only the first voxel of a run
+// inside a warp row loads its home pair, everyone else takes the head's result through one 64-bit shuffle.  The
+// hypothesis came from ncu (l1tex__data_pipe_lsu_wavefronts at 70 %: a divergent LDG.256 with all 32 lanes active costs
+// ~20 wavefronts however many lanes share a sector).  Bit-identical results, but SLOWER: remap 3.05 -> 3.92 ms,
+// mask_except 4.14 -> 4.80 ms (two rows per batch; 3.87 / 5.53 ms with one).  The extra ~20 instructions per row (two
+// shuffles up, ballot, clz, two shuffles, selects, divergent compare paths) cost more than the wavefronts saved: the
+// kernel is bound by issue slots and dependent latency at 24 warps per SM, not by the L1 data pipe.  Forcing 4 CTAs
+// per SM (56 registers, 108 bytes of spills) was slower still (3.86 / 5.90 ms), and so was a 4-deep TMA ring (4.20 /
+// 5.37 ms: more streaming reads in flight delay the table probes).
 template <int W, int NB>
 static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, size_t plane_bytes, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);

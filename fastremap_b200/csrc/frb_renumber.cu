@@ -8,6 +8,8 @@
 // 64-bit atomicMin, K2 (frb_rank.cu) sorts the labels by that index.  First indices are stored with
 // bit 63 set (FRB_RANK_TAG) so that they compare above every already assigned rank: ranking is
 // incremental and a volume may be built chunk by chunk.
+#include <stdlib.h>
+
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
 
@@ -122,6 +124,51 @@ k_stream_probe(const uint4* __restrict__ a, size_t nvec, void* wide, void* narro
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
 }
 
+// One pass through L2?  The feasibility probe of a single-pass renumber: ONE persistent, cooperatively
+// launched kernel walks the array in windows; per window: pass A reads it (the traffic of K1), grid barrier, pass B reads it
+// again (from L2, if the window is still there) and writes 8 B + 4 B per voxel (the traffic of K3), grid barrier.  No table,
+// no ranking: what this measures is the ceiling of the idea -- HBM traffic 20 instead of 28 B/voxel if pass B hits in L2.
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_window_probe(const uint4* __restrict__ a, size_t nvec, size_t win_vecs, void* wide, void* narrow, u64* out, unsigned int* barrier, int run) {
+  extern __shared__ __align__(128) unsigned char frb_dyn_smem[];
+  uint32_t acc = 0;
+  unsigned int generation = 0;
+  auto sync_grid = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      generation++;
+      __threadfence();
+      atomicAdd(barrier, 1u);
+      const unsigned int target = generation * gridDim.x;
+      while (*((volatile unsigned int*)barrier) < target) __nanosleep(20);
+      __threadfence();
+      // the ring's mbarriers are re-initialised by the next stream_rows call: retire the old objects first
+      u64* bars = reinterpret_cast<u64*>(frb_dyn_smem + (size_t)STREAM_STAGES * STREAM_STAGE_VECS * 16);
+      for (int s = 0; s < 2 * STREAM_STAGES; s++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+    }
+    __syncthreads();
+  };
+  for (size_t w0 = 0; w0 < nvec; w0 += win_vecs) {
+    const size_t nv = nvec - w0 < win_vecs ? nvec - w0 : win_vecs;
+    const TileMap map(nv, (size_t)run);
+    stream_rows<8, false, false, 0>(a + w0, nv, map, [&](int, const uint4& cur, bool valid, size_t, u64, bool) {
+      if (valid) acc ^= cur.x ^ cur.y ^ cur.z ^ cur.w;
+    }, [](const uint4*, size_t) {});
+    sync_grid();
+    char* wd = (char*)wide + w0 * 16;
+    char* nr = (char*)narrow + w0 * 8;
+    stream_rows<8, false, false, 0>(a + w0, nv, map, [&](int, const uint4& cur, bool valid, size_t i0, u64, bool) {
+      if (!valid) return;
+      acc ^= cur.y;
+      st_stream16(wd + i0 * 8, cur);
+      st_stream8(nr + i0 * 4, make_uint2(cur.x, cur.z));
+    }, [](const uint4*, size_t) {});
+    sync_grid();
+  }
+  acc = __reduce_xor_sync(FRB_FULL_MASK, acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, (u64)acc);
+}
+
 }  // namespace frb
 
 using namespace frb;
@@ -156,6 +203,23 @@ int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_n
   if (!src || !out || !aligned16(src) || ((mode & 3) >= 1 && !dst_wide) || ((mode & 3) >= 2 && !dst_narrow)) { set_error("frb_stream_probe: bad arguments"); return FRB_ERR_BAD_ARG; }
   const size_t nvec = nbytes / 16;
   const size_t tiles = (nvec + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS + 1;
+  if (mode & 8) {  // windowed two-pass probe in one cooperative kernel; out[1] is the grid barrier word (zeroed here)
+    if (!dst_wide || !dst_narrow) { set_error("frb_stream_probe: the window probe needs both destinations"); return FRB_ERR_BAD_ARG; }
+    const char* e = getenv("FRB_PROBE_WINDOW_MIB");
+    size_t win_vecs = (size_t)(e ? atoi(e) : 64) * (1u << 16);
+    if (win_vecs < (size_t)STREAM_TILE_VECS) win_vecs = STREAM_TILE_VECS;
+    const size_t wtiles = (win_vecs + STREAM_TILE_VECS - 1) / STREAM_TILE_VECS;
+    const int grid = stream_grid(k_window_probe, wtiles);
+    int run = fair_run(grid, wtiles);
+    const uint4* a = (const uint4*)src;
+    u64* o = (u64*)out;
+    unsigned int* bar = (unsigned int*)(o + 1);
+    cudaMemsetAsync(bar, 0, 8, (cudaStream_t)stream);
+    void* params[] = {&a, (void*)&nvec, &win_vecs, &dst_wide, &dst_narrow, &o, &bar, &run};
+    cudaError_t err = cudaLaunchCooperativeKernel((const void*)k_window_probe, dim3(grid), dim3(STREAM_THREADS), params, STREAM_SMEM_BYTES, (cudaStream_t)stream);
+    if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); return FRB_ERR_CUDA; }
+    return check_launch("k_window_probe");
+  }
   if (mode & 4)
     k_stream_probe<true><<<stream_grid(k_stream_probe<true>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, (cudaStream_t)stream>>>(
         (const uint4*)src, nvec, dst_wide, dst_narrow, mode & 3, (u64*)out, fair_run(stream_grid(k_stream_probe<true>, tiles), tiles));

@@ -174,7 +174,8 @@ struct ExportSel {
   u64* b_out;
   int mode;
   __device__ __forceinline__ bool pick(u64 key, u64) const { return key != FRB_EMPTY; }
-  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot) const {
+  __device__ __forceinline__ u64 fetch(u64, u64) const { return 0; }
+  __device__ __forceinline__ void emit(u64 pos, u64 key, u64 val, u64 slot, u64) const {
     if (mode == 0) { a_out[pos] = key; b_out[pos] = val; }
     else { a_out[pos] = val; b_out[pos] = slot; }
   }
@@ -182,7 +183,7 @@ struct ExportSel {
 __global__ void k_export_side(u64 cap, u64* meta, ExportSel sel, u64 capacity) {
   if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT]) {  // the out-of-band all-ones key ("slot cap")
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
-    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], cap);
+    if (pos < capacity) sel.emit(pos, FRB_EMPTY, meta[FRB_META_SIDE_VAL], cap, 0);
   }
 }
 

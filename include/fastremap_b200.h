@@ -282,7 +282,10 @@ int frb_synth_volume(void* out, int dtype, uint64_t nz, uint64_t ny, uint64_t nx
 
 /* calibration: the library's TMA-staged streaming loop with no arithmetic.  mode 0 reads nbytes
  * (xor checksum into *out); mode 1 also writes them to dst_wide; mode 2 also writes half of them
- * to dst_narrow (the 8 B read / 8 B + 4 B write shape of the renumber relabel pass). */
+ * to dst_narrow (the 8 B read / 8 B + 4 B write shape of the renumber relabel pass).  mode | 4: the copy
+ * also carries the 16 bytes in front of every tile.  mode | 8 (with mode 2): the windowed variant -- ONE
+ * persistent cooperative kernel, per window (FRB_PROBE_WINDOW_MIB, default 64) a read pass, a grid barrier,
+ * the read + write pass, a grid barrier; out must then hold two words (out[1] is the barrier word). */
 int frb_stream_probe(const void* src, size_t nbytes, void* dst_wide, void* dst_narrow, int mode, uint64_t* out, void* stream);
 /* bind this library's (statically linked) CUDA runtime to `device`; call once per process/thread
  * before the first launch when the caller's framework selected a device other than 0 */

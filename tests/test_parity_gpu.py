@@ -784,6 +784,19 @@ def test_tobytes_ragged_and_tensor(frb, oracle):
     frb.tobytes(np.zeros((4, 4, 4), dtype=np.complex64), (2, 2, 2))
 
 
+def test_tobytes_packed_merged_axes(frb, oracle):
+  """1- and 2-byte elements with chunk rows under 256 bytes: the chunk's row axis is merged with the grid axis that
+  continues it (k_transpose_packed<.., merged>); non-cubic shapes and chunks, random data, both directions."""
+  rng = np.random.default_rng(21)
+  for shape, chunk in [((128, 96, 256), (32, 48, 64)), ((256, 64, 128), (64, 32, 32)), ((64, 128, 512), (16, 64, 128)),
+                       ((136, 24, 264), (68, 12, 132)), ((132, 20, 258), (66, 10, 86))]:
+    for dtype in (np.uint8, np.uint16, np.int8):
+      for io in "CF":
+        img = np.copy(rng.integers(0, 250, size=shape).astype(dtype), order=io)
+        for oo in "CF":
+          assert frb.tobytes(img, chunk, order=oo) == oracle.tobytes(img, chunk, order=oo), (shape, chunk, dtype, io, oo)
+
+
 def test_transposition_full_size_properties(frb):
   """1024 x 1024 x 512 uint16 (1 GiB): C -> F -> C is the identity, and the F layout is checked against
   torch's own permuted copy on the device."""
