@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("FASTREMAP_B200_SO") or os.path.join(HERE, "libfastrema
 U8, U16, U32, U64, I8, I16, I32, I64 = range(8)
 OK, ERR_CUDA, ERR_BAD_ARG = 0, 3, 4
 META_WORDS = 16
-META_COUNT, META_OVERFLOW, META_SIDE_PRESENT, META_SIDE_VAL, META_MISSING_INDEX, META_LIST_COUNT, META_ASSIGNED = 0, 1, 2, 3, 4, 5, 6
+META_COUNT, META_OVERFLOW, META_SIDE_PRESENT, META_SIDE_VAL, META_MISSING_INDEX, META_LIST_COUNT, META_ASSIGNED, META_AUX1 = 0, 1, 2, 3, 4, 5, 6, 7
 RANK_TAG = 1 << 63
 OP_MIN, OP_MAX, OP_ADD, OP_SET = 0, 1, 2, 3
 MISS_KEEP, MISS_ERROR, MISS_FILL = 0, 1, 2
@@ -75,9 +75,9 @@ SIGNATURES = {
   "frb_sort_pairs_u64_ws_bytes": (_sz, [_sz]),
   "frb_sort_pairs_u64": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
   "frb_unravel_u16": (_i, [_vp, _sz, _i, _u64, _u64, _vp, _vp]),
-  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _u64, _vp]),
+  "frb_component_build": (_i, [_vp, _sz, _i, _u64, _vp, _u64, _vp, _u64, _u64, _vp, _u64, _vp]),
   "frb_component_unhead": (_i, [_vp, _i, _u64, _u64, _vp, _u64, _vp, _vp]),
-  "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp]),
+  "frb_component_gather": (_i, [_vp, _u64, _vp, _i, _vp, _i, _u64, _vp, _vp, _sz, _vp, _u64, _vp]),
   "frb_synth_volume": (_i, [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _dbl, _dbl, _u64, _vp]),
   "frb_small_table_cap": (_u64, [_sz, _i]),
   "frb_small_list_capacity": (_sz, [_sz, _i]),

@@ -30,6 +30,33 @@ template <int OP>
 __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v, unsigned int* inserted) {
   return table_update<OP>(slots, mask, direct, meta, key, v, inserted);
 }
+// K7's list of filled slots (so that its gather need not scan the table).  Layout, in 32-bit words:
+//   [0] R = regions (consumer warps of the build grid)   [1] region capacity   [2], [3] unused
+//   [4 .. 4 + R)   entries per region (written by each warp when it is done)
+//   then R regions of `region capacity` slot indices, one per consumer warp: appended to through a counter in shared
+//   memory (no global atomic, no round trip), in the order the warp walks the volume -- so the gather's reads of
+//   parent[] stay inside a few pages.
+// meta[AUX1] receives the number of entries listed; a region that overflowed adds 2^40 (the host then scans instead).
+static constexpr u64 LIST_OVERFLOW = 1ull << 40;
+__host__ __device__ __forceinline__ u64 slot_list_region_cap(u64 list_words, u64 regions) {
+  return list_words > 4 + regions ? (list_words - 4 - regions) / regions : 0;
+}
+// append slot index `at` to the calling warp's region (any subset of its lanes may call this, in any order)
+__device__ __forceinline__ void slot_list_append(unsigned int* list, u64 region_cap, unsigned int* warp_count, u64 at) {
+  const unsigned int pos = atomicAdd(warp_count, 1u);
+  if (pos < region_cap) {
+    const u64 regions = (u64)gridDim.x * STREAM_WARPS;
+    list[4 + regions + ((u64)blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5)) * region_cap + pos] = (unsigned int)at;
+  }
+}
+template <int OP>
+__device__ __noinline__ bool table_update_slow_listed(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v, unsigned int* inserted,
+                                                      unsigned int* list, u64 region_cap, unsigned int* warp_count) {
+  u64 at = FRB_EMPTY;
+  const bool ok = table_update<OP>(slots, mask, direct, meta, key, v, inserted, &at);
+  if (at != FRB_EMPTY) slot_list_append(list, region_cap, warp_count, at);
+  return ok;
+}
 
 // value offered for element i is bias + i.  HEADS: only run starts (a[i] != a[i-1]) are offered.
 // IL / DU: how a warp's rows are laid out in the tile and which of the lane's row slots holds the row
@@ -38,19 +65,23 @@ __device__ __noinline__ bool table_update_slow(Slot* slots, u64 mask, int direct
 template <int W, int OP, bool REVERSE, bool HEADS, int IL, int DU, bool VAR_TILE>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run,
-                                           int tile_vecs, PlaneWalk pw) {
+                                           int tile_vecs, PlaneWalk pw, unsigned int* slot_list = nullptr, u64 region_cap = 0) {
   constexpr int V = 16 / W;
   typedef typename UIntOf<W>::type T;
   // QUEUED (K7, round 2): what survives the filters is not offered by the lane that found it but appended to a per-warp
-  // queue; whenever 32 offers wait, every lane takes ONE, reads its home slot now and settles it at the next tile end
-  // straight from that copy (present: one fire-and-forget reduction; empty: one CAS).  The old scheme below -- one
+  // queue; whenever 32 offers wait, every free lane takes ONE, reads its home slot now and settles it at the next tile
+  // end straight from that copy (present: one fire-and-forget reduction; empty: one CAS; another label: the lane reads
+  // the second slot of the home pair and tries again a tile later -- at load 0.3 a quarter of all first probes).  Only
+  // what is still unsettled after the pair takes the out-of-line probing path.  The old scheme below -- one
   // deferred offer per lane, the rest synchronously -- left the warp waiting for two dependent round trips (re-read +
   // CAS) in most tiles at 10^7 labels, because with 0.35 offers per lane and tile SOME lane nearly always had two
   // (ncu, profiles/r02_ncu_full_component_map.csv: no unit above 35 % of its peak, 2 us per tile and CTA).
   constexpr bool QUEUED = HEADS;
   __shared__ u64 s_seen[8][BUILD_CACHE];
   __shared__ Slot s_queue[QUEUED ? 8 : 1][QUEUED ? BUILD_QUEUE : 1];
+  __shared__ unsigned int s_listed[8];  // QUEUED: entries this warp has appended to its region of the slot list
   unsigned int qn = 0;  // entries in this warp's queue (the same value in every lane)
+  constexpr u64 SECOND = 1ull << 62;  // QUEUED: flag in pval -- the pending offer looks at the second slot of its home pair
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int inserted = 0;  // labels this lane has inserted ...
@@ -59,8 +90,10 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   // a hashed table that is more than half full is too small: stop early (the host grows it and starts
   // over) instead of running into the probe limit at ~100 % load, where every offer walks 512 slots
   const u64 count_limit = direct ? ~0ull : (mask + 1) / 2 + 1;
-  if (warp < STREAM_WARPS)
+  if (warp < STREAM_WARPS) {
     for (int i = lane; i < BUILD_CACHE; i += 32) s_seen[warp][i] = FRB_EMPTY;
+    if (lane == 0) s_listed[warp] = 0;
+  }
   __syncwarp();
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements), unfiltered
@@ -86,8 +119,17 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   pslot.key = 0;
   pslot.val = 0;
 
+  // slot_list (K7, optional): every slot this pass fills is listed (layout above)
+  if (QUEUED && slot_list && blockIdx.x == 0 && threadIdx.x == 0) {
+    slot_list[0] = gridDim.x * STREAM_WARPS;
+    slot_list[1] = (unsigned int)region_cap;
+  }
   auto offer = [&](u64 key, u64 val) {
-    if (!table_update_slow<OP>(slots, mask, direct, meta, key, val, &inserted)) aborted = true;
+    if (QUEUED && slot_list) {
+      if (!table_update_slow_listed<OP>(slots, mask, direct, meta, key, val, &inserted, slot_list, region_cap, &s_listed[warp])) aborted = true;
+    } else if (!table_update_slow<OP>(slots, mask, direct, meta, key, val, &inserted)) {
+      aborted = true;
+    }
   };
 
   auto row_fn = [&](int u, const uint4& cur, bool valid, size_t, u64 prev, bool has_prev) {
@@ -129,28 +171,42 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   auto resolve_pending = [&]() {
     if (pend) {
       if (QUEUED) {
-        Slot* s = slots + (direct ? pkey : home_slot(pkey, mask));
+        const bool second = (pval & SECOND) != 0;
+        const u64 val = pval & ~SECOND;
+        const u64 h = direct ? pkey : (home_slot(pkey, mask) + (second ? 1 : 0));
+        Slot* s = slots + h;
+        pend = false;
         if (pslot.key == pkey) {
-          if (!op_settled<OP>(pslot.val, pval)) op_apply<OP>(&s->val, pval);
+          if (!op_settled<OP>(pslot.val, val)) op_apply<OP>(&s->val, val);
         } else if (pslot.key == FRB_EMPTY) {
           const u64 old = atom_cas_u64(&s->key, FRB_EMPTY, pkey);
-          if (old == FRB_EMPTY) inserted++;
-          if (old == FRB_EMPTY || old == pkey) op_apply<OP>(&s->val, pval);
-          else offer(pkey, pval);
+          if (old == FRB_EMPTY) {
+            inserted++;
+            if (slot_list) slot_list_append(slot_list, region_cap, &s_listed[warp], h);
+          }
+          if (old == FRB_EMPTY || old == pkey) op_apply<OP>(&s->val, val);
+          else offer(pkey, val);
+        } else if (!second && !direct) {
+          pval |= SECOND;  // another label lives in the home slot: look at the other slot of the pair, settle a tile later
+          pslot = ld_slot_cg(s + 1);
+          pend = true;
         } else {
-          offer(pkey, pval);
+          offer(pkey, val);
         }
-      } else if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval))) {
-        offer(pkey, pval);
+      } else {
+        if (!(pslot.key == pkey && op_settled<OP>(pslot.val, pval))) offer(pkey, pval);
+        pend = false;
       }
-      pend = false;
     }
   };
-  // QUEUED: every lane takes one queued offer (from the tail) and reads its home slot; settled by resolve_pending
+  // QUEUED: every free lane takes one queued offer (from the tail) and reads its home slot; settled by resolve_pending
   auto take_batch = [&]() {
-    const unsigned int take = qn < 32u ? qn : 32u;
-    if ((unsigned int)lane < take) {
-      const Slot e = s_queue[warp][qn - 1u - (unsigned int)lane];
+    const unsigned int free_lanes = __ballot_sync(FRB_FULL_MASK, !pend);
+    const unsigned int nfree = __popc(free_lanes);
+    const unsigned int take = qn < nfree ? qn : nfree;
+    const unsigned int mine = __popc(free_lanes & ((1u << lane) - 1u));
+    if (!pend && mine < take) {
+      const Slot e = s_queue[warp][qn - 1u - mine];
       pend = true;
       pkey = e.key;
       pval = e.val;
@@ -248,10 +304,16 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw) : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
   stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
   resolve_pending();
-  if (QUEUED && warp < STREAM_WARPS) {  // what is still queued (the producer warp's qn is 0)
-    while (qn) {
+  if (QUEUED && warp < STREAM_WARPS) {  // what is still queued or waiting for its second probe (the producer warp has nothing)
+    while (qn || __any_sync(FRB_FULL_MASK, pend)) {
       take_batch();
       resolve_pending();
+    }
+    __syncwarp();
+    if (slot_list && lane == 0) {
+      const unsigned int ln = s_listed[warp];
+      slot_list[4 + (u64)blockIdx.x * STREAM_WARPS + warp] = (u64)ln <= region_cap ? ln : 0u;
+      if (ln) atomicAdd(&meta[FRB_META_AUX1], (u64)ln <= region_cap ? (u64)ln : LIST_OVERFLOW);
     }
   }
   block_add_to(&meta[FRB_META_COUNT], inserted - reported);

@@ -284,15 +284,20 @@ __device__ __forceinline__ void op_apply(u64* addr, u64 v) {
 // Find-or-insert `key` and combine `v` into its value.  `first` is an optional already-loaded
 // copy of the home slot (speculative probe issued by the caller), else pass probe=false.
 // Returns false if the probe limit was hit (table too full): meta[OVERFLOW] is raised.
+// ins_slot (optional): receives the slot index if THIS call inserted the key into the slot array (not for the
+// out-of-band all-ones key) -- K7 lists the slots it fills so that its gather need not scan the table.
 template <int OP>
 __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, u64* meta, u64 key, u64 v,
-                                             unsigned int* inserted) {
+                                             unsigned int* inserted, u64* ins_slot = nullptr) {
   if (direct) {
     Slot* s = slots + key;
     Slot cur = ld_slot_cg(s);
     if (cur.key != key) {
       u64 prev = atom_cas_u64(&s->key, FRB_EMPTY, key);
-      if (prev == FRB_EMPTY) (*inserted)++;
+      if (prev == FRB_EMPTY) {
+        (*inserted)++;
+        if (ins_slot) *ins_slot = key;
+      }
     } else if (op_settled<OP>(cur.val, v)) {
       return true;
     }
@@ -317,6 +322,7 @@ __device__ __forceinline__ bool table_update(Slot* slots, u64 mask, int direct, 
       u64 prev = atom_cas_u64(&s->key, FRB_EMPTY, key);
       if (prev == FRB_EMPTY) {
         (*inserted)++;
+        if (ins_slot) *ins_slot = h;
         op_apply<OP>(&s->val, v);
         return true;
       }

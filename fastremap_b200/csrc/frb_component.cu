@@ -12,13 +12,6 @@
 
 namespace frb {
 
-template <int W, int IL, int DU, bool VAR_TILE>
-__global__ void __launch_bounds__(STREAM_THREADS)
-k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
-                  u64* __restrict__ meta, int run, int tile_vecs, PlaneWalk pw) {
-  build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs, pw);
-}
-
 // gather: scan the table (frb_scan.cuh) and emit (label, parent[winning run start]) for every label
 struct GatherSel {
   const void* parent;
@@ -33,6 +26,59 @@ struct GatherSel {
     st_elem_rt(parents_out, wp, pos, fetched);
   }
 };
+template <int W, int IL, int DU, bool VAR_TILE>
+__global__ void __launch_bounds__(STREAM_THREADS, 3)  // 72 registers: three CTAs per SM (the pass is latency-bound at 10^7 labels)
+k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
+                  u64* __restrict__ meta, int run, int tile_vecs, PlaneWalk pw, unsigned int* slot_list, u64 region_cap) {
+  build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs, pw, slot_list, region_cap);
+}
+
+// gather through the list of filled slots the build pass kept (layout: frb_build.cuh; complete -- the host checked
+// meta[AUX1]): no scan of a mostly empty table, no compaction.  A CTA takes one region at a time; its first output
+// position is the sum of the counts of the regions in front (a few thousand words, L2-resident); four independent
+// (slot, parent) read chains per thread.  A region lists its slots in the order its warp walked the volume, so the
+// reads of parent[] of one region stay inside a few 2 MB pages.
+__global__ void __launch_bounds__(256)
+k_component_gather_list(const unsigned int* __restrict__ list, const Slot* slots, GatherSel sel) {
+  constexpr int B = 4;
+  __shared__ unsigned long long s_base;
+  const unsigned int R = list[0], rcap = list[1];
+  const unsigned int* counts = list + 4;
+  const unsigned int* data = list + 4 + R;
+  for (unsigned int r = blockIdx.x; r < R; r += gridDim.x) {
+    const unsigned int cnt = counts[r];
+    if (cnt == 0) continue;  // (the same in every thread)
+    unsigned long long part = 0;
+    for (unsigned int q = threadIdx.x; q < r; q += 256) part += counts[q];
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    part = __reduce_add_sync(FRB_FULL_MASK, (unsigned int)part);  // a region holds < 2^32 / 32 entries: the warp sum fits
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_base, part);
+    __syncthreads();
+    const u64 base = s_base;
+    const unsigned int* mine = data + (u64)r * rcap;
+    for (unsigned int i0 = threadIdx.x; i0 < cnt; i0 += 256 * B) {
+      Slot sl[B];
+      u64 got[B];
+      bool live[B];
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        const unsigned int i = i0 + b * 256;
+        live[b] = i < cnt;
+        sl[b].key = 0;
+        sl[b].val = 0;
+        if (live[b]) sl[b] = ld_slot_cg_batch(slots + mine[i]);
+      }
+#pragma unroll
+      for (int b = 0; b < B; b++) got[b] = (live[b] && sl[b].val != 0) ? sel.fetch(sl[b].key, sl[b].val) : 0;
+#pragma unroll
+      for (int b = 0; b < B; b++)
+        if (live[b]) sel.emit(base + i0 + b * 256, sl[b].key, sl[b].val, 0, got[b]);
+    }
+  }
+}
+
 // Sharded volumes: a slab's first voxel was offered as a run start; if it carries the label the previous slab ended
 // with it is not one (fastremap.pyx:581: only cc[i] != cc[i-1] starts a run).  Withdraw that offer -- unless a later
 // run start of the label in this slab has overtaken it anyway.
@@ -49,6 +95,7 @@ __global__ void k_component_unhead(const void* cc, int w, u64 prev_bits, u64 fla
   }
 }
 
+__global__ void k_store_u64(u64* p, u64 v) { *p = v; }
 __global__ void k_gather_side(u64* meta, GatherSel sel, u64 capacity) {
   if (threadIdx.x == 0 && meta[FRB_META_SIDE_PRESENT] && meta[FRB_META_SIDE_VAL] != 0) {  // the out-of-band all-ones label
     const u64 pos = atomicAdd(&meta[FRB_META_LIST_COUNT], 1ull);
@@ -117,7 +164,8 @@ using namespace frb;
 extern "C" {
 
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, void* stream) {
+                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, uint32_t* slot_list, uint64_t slot_list_capacity,
+                        void* stream) {
   if (!dtype_ok(cc_dtype) || !slots || !meta || (cap & (cap - 1)) != 0 || (n && (!cc || !aligned16(cc)))) { set_error("frb_component_build: bad arguments"); return FRB_ERR_BAD_ARG; }
   if (n == 0) return FRB_OK;
   const int w = dtype_width(cc_dtype);
@@ -130,9 +178,15 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
   u64* m = (u64*)meta;
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
+  if (slot_list) {  // header + per-region counts (at most 8 warps x 4 CTAs x SMs regions): regions whose warp never runs stay empty
+    const size_t head = (size_t)(4 + 8 * 4 * sm_count() + 1) * sizeof(uint32_t);
+    if ((size_t)slot_list_capacity * sizeof(uint32_t) < 2 * head) { set_error("frb_component_build: slot list too small"); return FRB_ERR_BAD_ARG; }
+    cudaMemsetAsync(slot_list, 0, head, st);
+  }
 #define FRB_K7(WW, II, DD, VV) k_component_build<WW, II, DD, VV><<<stream_grid(k_component_build<WW, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
     p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, II, DD, VV>, tiles), tiles), tv, \
-    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_component_build<WW, II, DD, VV>, tiles)))
+    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_component_build<WW, II, DD, VV>, tiles)), \
+    (unsigned int*)slot_list, slot_list ? slot_list_region_cap((u64)slot_list_capacity, (u64)stream_grid(k_component_build<WW, II, DD, VV>, tiles) * STREAM_WARPS) : 0ull)
 #define FRB_K7_GEO(WW)                                                        \
   if (geo.tv != STREAM_TILE_VECS) { FRB_K7(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_K7(WW, 4, 1, false); }                          \
@@ -162,8 +216,10 @@ int frb_component_unhead(const void* cc, int cc_dtype, uint64_t prev_bits, uint6
 }
 
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
-                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream) {
-  if (!dtype_ok(cc_dtype) || !dtype_ok(p_dtype) || !slots || !meta || !parent || (capacity && (!keys_out || !parents_out))) { set_error("frb_component_gather: bad arguments"); return FRB_ERR_BAD_ARG; }
+                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, const uint32_t* slot_list,
+                         uint64_t slot_list_count, void* stream) {
+  if (!dtype_ok(cc_dtype) || !dtype_ok(p_dtype) || !slots || !meta || !parent || (capacity && (!keys_out || !parents_out)) ||
+      (slot_list && slot_list_count > capacity)) { set_error("frb_component_gather: bad arguments"); return FRB_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(&((u64*)meta)[FRB_META_LIST_COUNT], 0, sizeof(u64), st);
   GatherSel sel;
@@ -174,6 +230,16 @@ int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc
   sel.wc = dtype_width(cc_dtype);
   sel.wp = dtype_width(p_dtype);
   u64* m = (u64*)meta;
+  if (slot_list) {  // the complete list of filled slots: entry i of the output is slot slot_list[i]; then the all-ones label
+    if (slot_list_count) {
+      k_component_gather_list<<<sm_count() * 8, 256, 0, st>>>((const unsigned int*)slot_list, (const Slot*)slots, sel);
+      int rc = check_launch("k_component_gather_list");
+      if (rc) return rc;
+    }
+    k_store_u64<<<1, 1, 0, st>>>(&m[FRB_META_LIST_COUNT], (u64)slot_list_count);
+    k_gather_side<<<1, 32, 0, st>>>(m, sel, (u64)capacity);
+    return check_launch("k_gather_side");
+  }
   int rc = launch_table_scan(slots, cap, &m[FRB_META_LIST_COUNT], (u64)capacity, sel, "k_table_scan<gather>", st);
   if (rc) return rc;
   k_gather_side<<<1, 32, 0, st>>>(m, sel, (u64)capacity);

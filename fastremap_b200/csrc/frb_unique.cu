@@ -16,6 +16,7 @@ namespace frb {
 
 struct DenseSink {
   static constexpr bool USE_LOG = false;  // a dense bin takes a fire-and-forget reduction as it is
+  __device__ __forceinline__ bool logs() const { return false; }
   u64* counts;
   u64 min_bits;
   int w;
@@ -32,8 +33,17 @@ struct HashSink {
   u64 mask;
   int direct;
   u64* meta;
+  // Direct tables (8- and 16-bit labels: slot = label) need no log and no look before the update: the key is
+  // stored as it is (every writer stores the same value) and the count takes a reduction, both fire and forget;
+  // meta[COUNT] is then made by a scan of the 2^8 / 2^16 slots after the pass (k_direct_count).
+  __device__ __forceinline__ bool logs() const { return !direct; }
+  __device__ __forceinline__ void direct_add(u64 key, unsigned int c) const {
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(&slots[key].key)), "l"(key) : "memory");
+    red_add_u64(&slots[key].val, (u64)c);
+  }
   __device__ __forceinline__ void operator()(u64 key, unsigned int c, unsigned int* inserted) const {
-    table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
+    if (direct) direct_add(key, c);
+    else table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
   }
   // two-step form used by the batched sends: the home-slot keys of all pairs a warp is about to send are
   // read first (one L2 round trip for the lot), then a label already sitting in its home slot costs one
@@ -44,7 +54,8 @@ struct HashSink {
     return k;
   }
   __device__ __forceinline__ void commit(u64 key, unsigned int c, u64 home_key, unsigned int* inserted) const {
-    if (home_key == key && key != FRB_EMPTY) red_add_u64(&slots[direct ? key : home_slot(key, mask)].val, (u64)c);
+    if (direct) direct_add(key, c);
+    else if (home_key == key && key != FRB_EMPTY) red_add_u64(&slots[home_slot(key, mask)].val, (u64)c);
     else table_update<FRB_OP_ADD>(slots, mask, direct, meta, key, (u64)c, inserted);
   }
 };
@@ -169,7 +180,7 @@ __device__ __forceinline__ u64 vec_get_dyn(const uint4& v, int j) {
 // Send the (key, cnt) pairs of the lanes with `ev` on their way to global memory; called by all 32 lanes.
 template <typename Sink>
 __device__ __forceinline__ void hist_emit(u64 key, unsigned int cnt, bool ev, const Sink& sink, const HistLog& log, unsigned int* inserted) {
-  if (Sink::USE_LOG) {
+  if (Sink::USE_LOG && sink.logs()) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int m = __ballot_sync(FRB_FULL_MASK, ev);
     if (m == 0) return;
@@ -359,6 +370,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = nvec * V; i < n; i++) sink(ld_elem<W>(a, i), 1u, &inserted);
   if (count_target) block_add_to(count_target, inserted);
+}
+
+// meta[COUNT] of a direct table after a counting pass: the slots that hold a label
+__global__ void __launch_bounds__(256) k_direct_count(const Slot* slots, u64 cap, u64* meta) {
+  unsigned int mine = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) mine += ld_slot_cg(slots + i).key != FRB_EMPTY;
+  mine = __reduce_add_sync(FRB_FULL_MASK, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&meta[FRB_META_COUNT], (u64)mine);
 }
 
 // Pull a table into L2 (one prefetch per 128-byte line, nothing lands in a register).  The counting pass has
@@ -880,7 +899,8 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   u64* ct = &((u64*)meta)[FRB_META_COUNT];
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
-  const HistLog log = hist_log_of(ws, ws_bytes, n);
+  HistLog log = hist_log_of(ws, ws_bytes, n);
+  if (sink.direct) log.cap = 0;  // direct tables are updated fire-and-forget (HashSink::direct_add): no log, no fold
   if (log.cap) cudaMemsetAsync(ws, 0, hist_counts_bytes() + 256, st);  // regions that no warp owns in this launch stay empty
 #define FRB_KH(WW, II, DD, VV) k_hist<WW, HashSink, II, DD, VV><<<stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
     p, n, sink, log, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv, \
@@ -903,7 +923,13 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
 #undef FRB_KH_GEO
 #undef FRB_KH
   int rc = check_launch("k_hist<hash>");
-  if (rc || !log.cap) return rc;
+  if (rc) return rc;
+  if (sink.direct) {  // COUNT = labels in the table (the whole table: COUNT of a direct table is never partial)
+    cudaMemsetAsync(ct, 0, sizeof(u64), st);
+    k_direct_count<<<cap >= 65536 ? 32 : 1, 256, 0, st>>>((const Slot*)slots, cap, (u64*)meta);
+    return check_launch("k_direct_count");
+  }
+  if (!log.cap) return rc;
   return frb_hist_apply_log(ws, ws_bytes, n, dtype, slots, cap, meta, stream);
 }
 

@@ -55,7 +55,7 @@ enum {
   FRB_META_MISSING_INDEX = 4,/* smallest flat index whose label was not in the table      */
   FRB_META_LIST_COUNT = 5,   /* entries written by export / rank / unique                 */
   FRB_META_ASSIGNED = 6,     /* renumber: labels ranked so far (next rank to hand out)    */
-  FRB_META_AUX1 = 7
+  FRB_META_AUX1 = 7          /* component_map: slots appended to the build's slot list   */
 };
 /* renumber table values: FRB_RANK_TAG | first flat index while a label is unranked, its 0-based
  * rank in encounter order afterwards (ranks compare below every tagged index). */
@@ -260,16 +260,24 @@ int frb_unravel_u16(const uint64_t* index, size_t n, int ndim, uint64_t d1, uint
  * Replaces _component_map (fastremap.pyx:565-587): at every run start of cc the table
  * receives key cc[i] with value max(i+1); frb_component_gather then emits (cc label, parent[i])
  * for the winning run start of every label.  count in meta[FRB_META_LIST_COUNT].
- * row_bytes / plane_bytes: performance hints (0 = unknown), see frb_renumber_build / frb_hist_hash. */
+ * row_bytes / plane_bytes: performance hints (0 = unknown), see frb_renumber_build / frb_hist_hash.
+ * slot_list (optional, slot_list_capacity uint32 words): the build lists the index of every slot it fills -- per
+ * consumer warp in a region of its own, no atomics (header, per-region counts, regions: csrc/frb_build.cuh) -- and adds
+ * the number of listed slots to meta[FRB_META_AUX1]; a region that ran out of space adds 2^40.  When
+ * AUX1 + SIDE_PRESENT == COUNT the list is complete and frb_component_gather can walk it (slot_list,
+ * slot_list_count = AUX1) instead of scanning and compacting the whole slot array (no label may have been withdrawn
+ * by frb_component_unhead).  Size it at 4 words per expected label or more.  NULL: no list, the gather scans. */
 int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_offset, void* slots, uint64_t cap,
-                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, void* stream);
+                        uint64_t* meta, uint64_t row_bytes, uint64_t plane_bytes, uint32_t* slot_list, uint64_t slot_list_capacity,
+                        void* stream);
 /* z-sharded volumes: withdraw the offer frb_component_build made for the slab's first voxel if that voxel carries
  * prev_bits, the label the previous slab ended with (it continues a run, :581) and no later run start of the label in
  * this slab has overtaken it; frb_component_gather skips withdrawn labels. */
 int frb_component_unhead(const void* cc, int cc_dtype, uint64_t prev_bits, uint64_t flat_offset, void* slots, uint64_t cap, uint64_t* meta,
                          void* stream);
 int frb_component_gather(const void* slots, uint64_t cap, uint64_t* meta, int cc_dtype, const void* parent, int p_dtype,
-                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, void* stream);
+                         uint64_t flat_offset, void* keys_out, void* parents_out, size_t capacity, const uint32_t* slot_list,
+                         uint64_t slot_list_count, void* stream);
 
 /* ---- synthetic volumes (benchmark / test input) -------------------
  * Blocky "connectomics-like" labels: a gz*gy*gx grid of cells with splitmix64 ids, nearest
