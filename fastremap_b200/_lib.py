@@ -87,6 +87,7 @@ SIGNATURES = {
   "frb_stream_probe": (_i, [_vp, _sz, _vp, _vp, _i, _vp, _vp]),
   "frb_set_device": (_i, [_i]),
   "frb_set_tile_run": (None, [_i]),
+  "frb_set_relabel_variant": (None, [_i]),
   "frb_launch_count": (_u64, []),
   "frb_last_error": (ctypes.c_char_p, []),
 }

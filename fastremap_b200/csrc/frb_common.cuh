@@ -612,6 +612,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// L2 eviction priority of streamed data.  A volume that is read once (and written once) should not push the label
+// table out of the 126 MB L2: between two uses of a label's table sector -- one row, one plane further on -- tens to
+// hundreds of MB of volume stream through.  Lines brought in (or written) with evict_first are the first to go, so
+// whatever else the kernel reads with the default priority stays.
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar, u64 policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+// Used by the kernels that only READ the volume (interleaved rows: K1, K7, k_hist, K6), for arrays of 256 MB and more
+// (shorter ones -- pipeline chunks, small volumes -- may well be read again out of L2 by the next kernel).  Measured
+// at 1024^3 (profiles/r02i_evict_first.jsonl): component_map 3.73 -> 3.57 ms, unique on 900 k labels 1.40 -> 1.37 ms,
+// K1 1.285 -> 1.257 ms.  NOT for K3: it writes the lines it has just read, and with evict_first on its reads
+// k_relabel_auto<8> went from 3.53 to 3.62 ms; evict_first on its stores cost another 4-6 %.
+#ifndef FRB_EF_MIN_VECS
+#define FRB_EF_MIN_VECS (1ull << 24)
+#endif
+
 __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -650,6 +673,8 @@ __device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, co
       it.template init<REVERSE>(map);
       int s = 0;
       uint32_t round = 0;
+      const bool evict_first = IL != 0 && nvec >= (size_t)FRB_EF_MIN_VECS;
+      const u64 policy = evict_first ? l2_policy_evict_first() : 0;
       for (IDX k = 0; k < ntiles; k++) {
         if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);  // all 8 warps released the previous fill
         const size_t vb = it.tile() * TV;
@@ -660,7 +685,8 @@ __device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, co
         if (NEED_PREV && vb > 0) { dst -= 1; src -= 1; nv += 1; }
         const uint32_t bytes = (uint32_t)(nv * 16);
         mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(dst, src, bytes, &full[s]);
+        if (evict_first) bulk_g2s_hint(dst, src, bytes, &full[s], policy);
+        else bulk_g2s(dst, src, bytes, &full[s]);
         if (++s == S) { s = 0; round++; }
       }
     }

@@ -8,6 +8,8 @@ namespace frb {
 int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* b_out, size_t capacity, int mode,
                         cudaStream_t st);
 
+int relabel_variant();  // tuning knob (frb_set_relabel_variant): -1 sampler decides, 0 k_relabel_batched, 1 k_relabel_runs
+
 // frb_sort.cu -- LSD radix sort, 8 bits per pass, stable.
 // Sorts by bits [begin_bit, end_bit) of the key.  keys_alt / vals_alt are ping-pong buffers of
 // n elements; the sorted result always ends in keys / vals.  vals may be NULL (keys only).

@@ -232,6 +232,7 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
   static_assert(W == 8 && R % NB == 0, "64-bit labels, hashed tables only");
+  if (__ldcg(&A.meta_ro[FRB_META_AUX1]) != 0) return;  // the sampler chose k_relabel_runs (uniform: the word is stable)
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31;
   if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
@@ -297,6 +298,141 @@ k_relabel_batched(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int
 // kernel is bound by issue slots and dependent latency at 24 warps per SM, not by the L1 data pipe.  Forcing 4 CTAs
 // per SM (56 registers, 108 bytes of spills) was slower still (3.86 / 5.90 ms), and so was a 4-deep TMA ring (4.20 /
 // 5.37 ms: more streaming reads in flight delay the table probes).
+// One lookup per RUN, and the runs of a whole warp-tile looked up together (round 2).  k_relabel_batched keeps 2 rows
+// (128 voxels) of a warp in flight per table round trip, and registers (16 per row for the home pairs) cap it there; at
+// 10^6..10^7 labels the pass is bound by that latency (ncu: no unit above 70 %, long-scoreboard stalls, 54 % issue).
+// Here the 256 voxels of a warp-tile are first cut into runs of equal labels (a lane compares with the element in front
+// of it in memory, two ballots per row number the runs), the run heads' labels go to a list in shared memory, and then
+// LANE i LOOKS UP RUN i: every lane of a load instruction asks for a different label, and the ~50 runs of a tile
+// (4.8-voxel runs) are in flight together with two loads per lane -- the whole tile per round trip, at 16 registers.
+// Results go back through shared memory (run number -> result).  Exact for every policy: a result depends on the label
+// alone, and the first voxel missing from the table (error policy: atomicMin of its index) is the head of its run.
+static constexpr int RUNS_MAX = STREAM_ROWS * 64;  // runs in a warp-tile of 64-bit labels (every voxel its own run)
+template <int W>
+__global__ void __launch_bounds__(STREAM_THREADS)
+k_relabel_runs(const uint4* src, void* dst_wide, size_t n, RelabelArgs A, int run) {
+  if (__ldcg(&A.meta_ro[FRB_META_AUX1]) == 0) return;  // the sampler chose k_relabel_batched (uniform: the word is stable)
+  constexpr int V = 16 / W;
+  constexpr int R = STREAM_ROWS;
+  static_assert(W == 8 && V == 2 && R == 4, "64-bit labels, hashed tables only");
+  __shared__ u64 s_key[STREAM_WARPS][RUNS_MAX];            // label of run i; overwritten by its result
+  __shared__ unsigned char s_pos[STREAM_WARPS][RUNS_MAX];  // element position (0..255) of the run's head in the warp-tile
+  const size_t nvec = n / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int below = (1u << lane) - 1u;
+  if (A.guard && __ldcg(&A.meta_ro[FRB_META_OVERFLOW]) != 0) return;
+  auto tile_end = [&](const uint4* stage, size_t vb) {
+    u64* const keys = s_key[warp];
+    unsigned char* const pos = s_pos[warp];
+    // pass 1: number the runs.  first[u]: run number of the lane's element 0 in row u; split bit u: element 1 starts a run
+    unsigned int first[R];
+    unsigned int split = 0, total = 0;
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+      const bool valid = vb + (u * 32 + lane) < nvec;
+      const uint4 cur = valid ? stage[u * 32 + lane] : make_uint4(0, 0, 0, 0);
+      const u64 k0 = vec_get<W>(cur, 0), k1 = vec_get<W>(cur, 1);
+      // the element in front of mine in memory: the staged bytes hold it for every lane but the tile's first
+      const u64 before = (u == 0 && lane == 0) ? 0 : reinterpret_cast<const u64*>(stage + (u * 32 + lane))[-1];
+      const bool h0 = valid && ((u == 0 && lane == 0) || k0 != before);
+      const bool h1 = valid && k1 != k0;
+      const unsigned int b0 = __ballot_sync(FRB_FULL_MASK, h0), b1 = __ballot_sync(FRB_FULL_MASK, h1);
+      // runs opened in this row in front of my element 0 (heads are ordered: lane-major, element 0 before element 1)
+      const unsigned int mine = total + __popc(b0 & below) + __popc(b1 & below) + (h0 ? 1u : 0u) - 1u;
+      first[u] = mine;
+      if (h0) { keys[mine] = k0; pos[mine] = (unsigned char)(u * 64 + lane * 2); }
+      if (h1) { keys[mine + 1] = k1; pos[mine + 1] = (unsigned char)(u * 64 + lane * 2 + 1); split |= 1u << u; }
+      total += __popc(b0) + __popc(b1);
+    }
+    __syncwarp();
+    // pass 2: lane i looks up runs i, i + 32 (, i + 64 ...): all of a tile's lookups in flight together
+    for (unsigned int base = 0; base < total; base += 64) {
+      const unsigned int i0 = base + lane, i1 = base + 32 + lane;
+      const bool a0 = i0 < total, a1 = i1 < total;
+      const u64 k0 = a0 ? keys[i0] : 0, k1 = a1 ? keys[i1] : 0;
+      const u64 h0 = home_slot(k0, A.mask), h1 = home_slot(k1, A.mask);
+      Probe p0, p1;
+      p0.a.key = p0.b.key = p1.a.key = p1.b.key = FRB_EMPTY;
+      p0.a.val = p0.b.val = p1.a.val = p1.b.val = 0;
+      if (a0) { const SlotPair sp = ld_pair_ro_batch(A.slots + h0); p0.a = sp.a; p0.b = sp.b; }
+      if (a1) { const SlotPair sp = ld_pair_ro_batch(A.slots + h1); p1.a = sp.a; p1.b = sp.b; }
+      if (a0) keys[i0] = relabel_one<true>(A, k0, h0, p0, vb * V + pos[i0]);
+      if (a1) keys[i1] = relabel_one<true>(A, k1, h1, p1, vb * V + pos[i1]);
+    }
+    __syncwarp();
+    // pass 3: every voxel takes the result of its run
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+      if (vb + (u * 32 + lane) < nvec) {
+        u64 r[V];
+        r[0] = keys[first[u]];
+        r[1] = (split >> u) & 1u ? keys[first[u] + 1] : r[0];
+        store_results<V, W>(dst_wide, (vb + (u * 32 + lane)) * V, r);
+      }
+    }
+    __syncwarp();  // the lists are reused by the warp's next tile
+  };
+  const TileMap64 map(nvec, (size_t)run);
+  stream_rows<W, false, false, 0>(src, nvec, map, [](int, const uint4&, bool, size_t, u64, bool) {}, tile_end);
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar tail (< V elements)
+    for (size_t i = nvec * V; i < n; i++) {
+      const u64 key = ld_elem<W>(src, i);
+      u64 h;
+      const Probe first = first_probe<true>(A, key, &h);
+      st_elem<W>(dst_wide, i, relabel_one<true>(A, key, h, first, i));
+    }
+  }
+}
+
+// Which of the two?  k_relabel_runs wins when runs are long (remap of 9.5-voxel runs through 10^6 labels: 3.25 -> 2.92
+// ms) and loses when they are short (mask_except on 4.8-voxel runs, 10^7 labels: 4.13 -> 5.39 ms: its lookups no longer
+// coalesce inside a load instruction, and the table's L2 misses go up from 62 M to 101 M sectors).  The host cannot
+// know, so a sampler looks at 64 blocks of 4 KiB spread over the volume, counts the run heads, and leaves the choice in
+// the table's meta[AUX1] (1: runs), where both kernels -- launched back to back -- read it; the one not chosen returns
+// at once (~3 us).  meta words 8..10 are the sampler's scratch (left zero again).
+static constexpr int SAMPLE_BLOCKS = 64;
+#ifndef FRB_RUNS_MAX_HEADS
+#define FRB_RUNS_MAX_HEADS 40  // run heads per 256 voxels up to which k_relabel_runs is chosen
+#endif
+__global__ void __launch_bounds__(256) k_run_density_sample(const uint4* __restrict__ src, size_t nvec, u64* meta, int force) {
+  const size_t per = nvec / SAMPLE_BLOCKS;
+  size_t v = (size_t)blockIdx.x * per + threadIdx.x;
+  unsigned int heads = 0, seen = 0;
+  if (per >= 256 && v < nvec) {
+    const uint4 cur = ld_stream16(src + v);
+    const u64 k0 = vec_get<8>(cur, 0), k1 = vec_get<8>(cur, 1);
+    heads = (k1 != k0) ? 1u : 0u;
+    if (v > 0) heads += reinterpret_cast<const u64*>(src + v)[-1] != k0 ? 1u : 0u;
+    seen = 2;
+  }
+  heads = __reduce_add_sync(FRB_FULL_MASK, heads);
+  seen = __reduce_add_sync(FRB_FULL_MASK, seen);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&meta[8], (u64)heads);
+    atomicAdd(&meta[9], (u64)seen);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&meta[10], 1ull) == (u64)gridDim.x - 1) {  // last CTA: decide, then leave the scratch words zero
+      __threadfence();
+      const u64 h = atomicExch(&meta[8], 0ull), s = atomicExch(&meta[9], 0ull);
+      atomicExch(&meta[10], 0ull);
+      u64 choose = (s > 0 && h * 256 <= (u64)FRB_RUNS_MAX_HEADS * s) ? 1ull : 0ull;
+      if (force >= 0) choose = (u64)force;
+      meta[FRB_META_AUX1] = choose;
+    }
+  }
+}
+
+static int launch_relabel_runs(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, cudaStream_t st) {
+  const size_t tiles = stream_tiles(n, 8);
+  const int grid = stream_grid(k_relabel_runs<8>, tiles);
+  k_relabel_runs<8><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>((const uint4*)src, dst_wide, n, A, fair_run(grid, tiles));
+  return check_launch("k_relabel_runs");
+}
+
 template <int W, int NB>
 static int launch_relabel_batched(const void* src, void* dst_wide, size_t n, const RelabelArgs& A, size_t plane_bytes, cudaStream_t st) {
   const size_t tiles = stream_tiles(n, W);
@@ -463,6 +599,10 @@ int frb_relabel(const void* src, void* dst_wide, void* dst_narrow, int narrow_wi
   // 64-bit labels only: with 4 labels per vector the batch is 8+ probes per lane (80+ registers) and was
   // measured 2.5-3x SLOWER than the plain kernel's one-probe-per-distinct-label loop at every table size
   if (batch_rows > 1 && !A.direct && w == 8 && dst_wide && !dst_narrow) {
+    k_run_density_sample<<<SAMPLE_BLOCKS, 256, 0, st>>>((const uint4*)src, n / 2, A.meta, relabel_variant());
+    int rc = check_launch("k_run_density_sample");
+    if (rc) return rc;
+    if ((rc = launch_relabel_runs(src, dst_wide, n, A, st))) return rc;
     return batch_rows >= 4 ? launch_relabel_batched<8, 4>(src, dst_wide, n, A, (size_t)plane_bytes, st)
                            : launch_relabel_batched<8, 2>(src, dst_wide, n, A, (size_t)plane_bytes, st);
   }

@@ -30,6 +30,8 @@ int check_launch(const char* what) {
 
 int g_tile_run = 64;
 int tile_run() { return g_tile_run; }
+int g_relabel_variant = -1;
+int relabel_variant() { return g_relabel_variant; }
 
 int sm_count() {
   if (g_sm_count == 0) {
@@ -204,7 +206,7 @@ int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* 
 
 using namespace frb;
 
-namespace frb { extern int g_sm_count; extern int g_tile_run; }
+namespace frb { extern int g_sm_count; extern int g_tile_run; extern int g_relabel_variant; }
 
 extern "C" {
 
@@ -332,6 +334,7 @@ int frb_set_device(int device) {
 }
 
 void frb_set_tile_run(int run) { g_tile_run = run < 1 ? 1 : run; }
+void frb_set_relabel_variant(int variant) { g_relabel_variant = variant < 0 ? -1 : (variant ? 1 : 0); }
 
 uint64_t frb_launch_count(void) { return g_launches; }
 const char* frb_last_error(void) { return g_error; }

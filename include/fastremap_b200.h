@@ -301,6 +301,10 @@ int frb_set_device(int device);
 /* tuning knob: consecutive 16 KiB tiles a CTA processes before it jumps ahead by gridDim.x runs
  * (1 = grid-stride interleave, large = one contiguous chunk per CTA).  Default 64. */
 void frb_set_tile_run(int run);
+/* tuning knob: which lookup kernel frb_relabel uses for 64-bit labels when batch_rows > 1.  -1 (default): a sampler
+ * counts run heads in 64 blocks of the volume and chooses per call; 0: k_relabel_batched (two rows of home-pair loads
+ * in flight per warp); 1: k_relabel_runs (one lookup per run of equal labels, a warp-tile's runs in flight together). */
+void frb_set_relabel_variant(int variant);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t frb_launch_count(void);
 const char* frb_last_error(void);

@@ -439,9 +439,20 @@ def test_unique_torch_outputs(frb):
 
 
 @pytest.mark.parametrize("dtype", [np.uint32, np.uint64, np.int32, np.int64])
-def test_big_lookup_tables_batched(frb, oracle, dtype):
+@pytest.mark.parametrize("variant", [-1, 0, 1])
+def test_big_lookup_tables_batched(frb, oracle, dtype, variant):
   """remap / mask / mask_except / remap_from_array_kv through tables of > 2^14 labels (the batched-lookup
-  variant of K3), ragged length, half of the labels missing from the table."""
+  variants of K3: sampler's choice, k_relabel_batched, k_relabel_runs), ragged length, half of the labels missing
+  from the table."""
+  from fastremap_b200 import _lib
+  _lib.load().frb_set_relabel_variant(variant)
+  try:
+    _big_lookup_tables(frb, oracle, dtype)
+  finally:
+    _lib.load().frb_set_relabel_variant(-1)
+
+
+def _big_lookup_tables(frb, oracle, dtype):
   rng = np.random.default_rng(31)
   info = np.iinfo(dtype)
   pool = np.unique(rng.integers(max(int(info.min), -2 ** 62), min(int(info.max), 2 ** 62), size=60000, dtype=np.int64).astype(dtype))
