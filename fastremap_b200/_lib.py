@@ -63,6 +63,7 @@ SIGNATURES = {
   "frb_hist_apply_log": (_i, [_vp, _sz, _sz, _i, _vp, _u64, _vp, _vp]),
   "frb_sort_pairs_ws_bytes": (_sz, [_sz]),
   "frb_sort_table_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+  "frb_direct_export_sorted": (_i, [_vp, _u64, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
   "frb_unique_sort_ws_bytes": (_sz, [_sz, _i]),
   "frb_unique_sort_count": (_i, [_vp, _sz, _i, _vp, _vp, _sz, _vp]),
   "frb_unique_sort_emit": (_i, [_sz, _i, _vp, _vp, _sz, _vp, _vp]),

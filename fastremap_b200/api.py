@@ -1317,9 +1317,18 @@ def unique_counts_device(buf, n, dtype, strategy=None, max_labels=None, row_byte
     return uniq, cts, nu
   if strategy == "hash":
     table = LabelTable(dtype, _default_entries(n, max_labels, voxels_per_label=512), 0)
+    if table.direct:
+      # 8- / 16-bit labels: the slot index is the label, so the table needs no log, no export and no sort -- count, then
+      # an ordered compaction of its 2^8 / 2^16 slots (4 launches instead of 9: uint8 1024^3 0.34 -> 0.26 ms)
+      _lib.check(L.frb_hist_hash(D.ptr(buf), n, c, D.ptr(table.slots), table.cap, D.ptr(table.meta), row_bytes, plane_bytes,
+                                 None, 0, D.stream()), "frb_hist_hash")
+      uniq, cts, ws = D.alloc(table.cap * w), D.alloc(table.cap * 8), D.alloc(256)
+      _lib.check(L.frb_direct_export_sorted(D.ptr(table.slots), table.cap, c, D.ptr(table.meta), D.ptr(uniq), D.ptr(cts), table.cap,
+                                            D.ptr(ws), 256, D.stream()), "frb_direct_export_sorted")
+      return uniq, cts, int(table.read_meta()[_lib.META_LIST_COUNT])
     limit = max(n // HASH_MAX_FRACTION, 1 << 16)
-    hws_bytes = 0 if table.direct else int(L.frb_hist_ws_bytes(n))
-    hws = None if table.direct else D.alloc(hws_bytes)   # per-warp eviction logs of the counting pass (direct tables take their updates as they come)
+    hws_bytes = int(L.frb_hist_ws_bytes(n))
+    hws = D.alloc(hws_bytes)           # per-warp eviction logs of the counting pass
     have_logs = False                  # the logs of a finished pass can be folded into a bigger table without re-reading the volume
     while True:
       # count -> export -> sort, queued back to back: the number of labels stays on the device (the sort

@@ -380,6 +380,79 @@ __global__ void __launch_bounds__(256) k_direct_count(const Slot* slots, u64 cap
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&meta[FRB_META_COUNT], (u64)mine);
 }
 
+// Direct tables in the dtype's own order: slot index = label bits, so walking the slots (from the sign bit for signed
+// dtypes) IS the sorted order -- an ordered compaction replaces export + radix sort (five launches, one of them
+// cooperative).  Two launches of cap / 2048 CTAs: per-CTA counts, then every CTA adds up the counts in front of it and
+// emits its labels and counts.
+static constexpr int DIRECT_CHUNK = 2048;  // slots per CTA (256 threads x 8 consecutive slots)
+__global__ void __launch_bounds__(256) k_direct_block_counts(const Slot* slots, u64 cap, u64 flip, unsigned int* block_counts) {
+  unsigned int mine = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const u64 i = (u64)blockIdx.x * DIRECT_CHUNK + threadIdx.x * 8 + q;
+    if (i < cap) mine += ld_slot_cg(slots + (i ^ flip)).key != FRB_EMPTY;
+  }
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  mine = __reduce_add_sync(FRB_FULL_MASK, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+template <int W>
+__global__ void __launch_bounds__(256) k_direct_emit(const Slot* slots, u64 cap, u64 flip, const unsigned int* block_counts, u64* meta,
+                                                     void* uniq_out, u64* counts_out, u64 capacity) {
+  __shared__ unsigned int s_warp[8];
+  __shared__ unsigned int s_base;
+  if (threadIdx.x < 32) {  // CTAs in front of this one (at most 32 of them), and the total for meta
+    unsigned int before = 0, total = 0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) {
+      const unsigned int c = __ldcg(block_counts + b);
+      total += c;
+      if (b < blockIdx.x) before += c;
+    }
+    before = __reduce_add_sync(FRB_FULL_MASK, before);
+    total = __reduce_add_sync(FRB_FULL_MASK, total);
+    if (threadIdx.x == 0) {
+      s_base = before;
+      if (blockIdx.x == 0) meta[FRB_META_LIST_COUNT] = total;
+    }
+  }
+  Slot sl[8];
+  unsigned int mine = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const u64 i = (u64)blockIdx.x * DIRECT_CHUNK + threadIdx.x * 8 + q;
+    sl[q].key = FRB_EMPTY;
+    sl[q].val = 0;
+    if (i < cap) sl[q] = ld_slot_cg(slots + (i ^ flip));
+    mine += sl[q].key != FRB_EMPTY;
+  }
+  // exclusive scan of `mine` over the CTA's 256 threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int v = __shfl_up_sync(FRB_FULL_MASK, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned int pos = s_base + incl - mine;
+  for (int w2 = 0; w2 < warp; w2++) pos += s_warp[w2];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    if (sl[q].key != FRB_EMPTY) {
+      if (pos < capacity) {
+        st_elem<W>(uniq_out, pos, sl[q].key);
+        counts_out[pos] = sl[q].val;
+      }
+      pos++;
+    }
+  }
+}
+
 // Pull a table into L2 (one prefetch per 128-byte line, nothing lands in a register).  The counting pass has
 // just streamed the whole volume through L2, so the table initialised before it is back in HBM; folding the
 // logs into it is millions of RANDOM 32-byte accesses, which HBM serves at a small fraction of its streaming
@@ -954,6 +1027,25 @@ int frb_hist_apply_log(const void* ws, size_t ws_bytes, size_t n, int dtype, voi
   }
   k_hist_apply_log<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(log, regions, sink, &((u64*)meta)[FRB_META_COUNT]);
   return check_launch("k_hist_apply_log");
+}
+
+int frb_direct_export_sorted(const void* slots, uint64_t cap, int dtype, uint64_t* meta, void* uniq_out, uint64_t* vals_out,
+                             size_t capacity, void* ws, size_t ws_bytes, void* stream) {
+  const int w = dtype_ok(dtype) ? dtype_width(dtype) : 0;
+  if (w < 1 || w > 2 || !slots || !meta || cap != frb_table_direct_cap(dtype) || (capacity && (!uniq_out || !vals_out)) || !ws ||
+      ws_bytes < 256) {
+    set_error("frb_direct_export_sorted: bad arguments (8- / 16-bit dtypes, a direct table, 256 bytes of workspace)");
+    return FRB_ERR_BAD_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)((cap + DIRECT_CHUNK - 1) / DIRECT_CHUNK);  // 1 or 32
+  const u64 flip = dtype_signed(dtype) ? cap / 2 : 0;
+  k_direct_block_counts<<<blocks, 256, 0, st>>>((const Slot*)slots, cap, flip, (unsigned int*)ws);
+  int rc = check_launch("k_direct_block_counts");
+  if (rc) return rc;
+  if (w == 1) k_direct_emit<1><<<blocks, 256, 0, st>>>((const Slot*)slots, cap, flip, (const unsigned int*)ws, (u64*)meta, uniq_out, (u64*)vals_out, (u64)capacity);
+  else k_direct_emit<2><<<blocks, 256, 0, st>>>((const Slot*)slots, cap, flip, (const unsigned int*)ws, (u64*)meta, uniq_out, (u64*)vals_out, (u64)capacity);
+  return check_launch("k_direct_emit");
 }
 
 // byte offset inside ws of the 32-bit flag word: 0 after a pass = every eviction went through the logs

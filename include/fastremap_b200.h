@@ -229,6 +229,11 @@ size_t frb_sort_pairs_ws_bytes(size_t L);
  * &meta[FRB_META_LIST_COUNT] right after frb_table_export: no host round trip in between). */
 int frb_sort_table_pairs(uint64_t* keys, uint64_t* vals, size_t L, const uint64_t* count_dev, int dtype, void* uniq_out,
                          uint64_t* vals_out, void* ws, size_t ws_bytes, void* stream);
+/* direct tables (8- / 16-bit dtypes: slot index = label bits): the labels in the dtype's own order with their
+ * values, by an ordered compaction of the slot array -- replaces frb_table_export + frb_sort_table_pairs.
+ * meta[FRB_META_LIST_COUNT] receives the number of labels; ws: 256 bytes. */
+int frb_direct_export_sorted(const void* slots, uint64_t cap, int dtype, uint64_t* meta, void* uniq_out, uint64_t* vals_out,
+                             size_t capacity, void* ws, size_t ws_bytes, void* stream);
 /* sort strategy, two steps: _count copies + radix sorts the voxels inside ws and leaves the number
  * of distinct labels in meta[FRB_META_LIST_COUNT]; _emit run-length encodes the sorted copy. */
 size_t frb_unique_sort_ws_bytes(size_t n, int dtype);
