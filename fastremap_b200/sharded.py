@@ -172,7 +172,38 @@ def _two_phase_merge(build, local, dtype, group, world, timers=None):
   return merged, counts, k64
 
 
-def _own_table(merged, own_keys, own_count_dev, own_capacity, dtype):
+# K3 looks every voxel up in the rank's own table, and a sparser table means fewer lookups that go beyond the home pair
+# (single GPU: 3.52 ms with the 128 MiB table that n / 256 entries give it, 3.80 ms with a 32 MiB one at 88 k labels):
+# the own table gets up to 64 slots per label while it stays at 2^23 slots (128 MiB), never fewer than the lookup default.
+OWN_TABLE_SLOTS = 1 << 23
+
+
+def _own_slots_per_entry(own_capacity: int) -> int:
+  from . import api
+  return max(api.LOOKUP_SLOTS_PER_ENTRY, min(64, OWN_TABLE_SLOTS // max(int(own_capacity), 1)))
+
+
+def _tables_on_side_stream(dtype, merged_entries, own_capacity):
+  """The merged table and the rank's own lookup table, allocated and initialised on the side stream -- under K1 and the
+  exchange instead of between them and K3.  Returns (merged, own or None, event to wait for before their first use)."""
+  from . import _lib
+  from . import api
+  from . import device as D
+  main = torch.cuda.current_stream()
+  side = D.side_stream()
+  with torch.cuda.stream(side):
+    merged = api.LabelTable(dtype, merged_entries, _lib.EMPTY, slots_per_entry=MERGED_SLOTS_PER_ENTRY)
+    own = None if merged.direct else api.LabelTable(dtype, own_capacity, _lib.EMPTY, slots_per_entry=_own_slots_per_entry(own_capacity))
+    ready = torch.cuda.Event()
+    ready.record(side)
+  for t in (merged, own):
+    if t is not None:  # allocated on the side stream, used (and outlived) by kernels of the main stream
+      t.slots.record_stream(main)
+      t.meta.record_stream(main)
+  return merged, own, ready
+
+
+def _own_table(merged, own_keys, own_count_dev, own_capacity, dtype, own=None):
   """A lookup table for K3 that holds only THIS slab's labels with the global ranks K2 has just written into the
   merged table.  At 8 GPUs the merged table is 8x the size of a single GPU's and later ranks' labels sit deeper in
   its probe chains (K3 3.53 -> 3.69 ms); looked up through its own compact table every rank's K3 costs what a
@@ -182,7 +213,8 @@ def _own_table(merged, own_keys, own_count_dev, own_capacity, dtype):
   from . import device as D
   if merged.direct:
     return merged
-  own = api.LabelTable(dtype, own_capacity, _lib.EMPTY, slots_per_entry=api.LOOKUP_SLOTS_PER_ENTRY)
+  if own is None:
+    own = api.LabelTable(dtype, own_capacity, _lib.EMPTY, slots_per_entry=_own_slots_per_entry(own_capacity))
   _lib.check(_lib.load().frb_table_project(D.ptr(own_keys), own_count_dev, own_capacity, D.ptr(merged.slots), merged.cap, D.ptr(merged.meta),
                                            D.ptr(own.slots), own.cap, D.ptr(own.meta), D.stream()), "frb_table_project")
   return own
@@ -335,6 +367,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   _lib.check(L.frb_renumber_build(D.ptr(src_buf), n_local, c, offset, 1 if preserve_zero else 0, D.ptr(local.slots),
                                   local.cap, D.ptr(local.meta), row_bytes, D.stream()), "frb_renumber_build")
   api._ev(timers, "k1", 1)
+  merged, own, tables_ready = _tables_on_side_stream(dtype, total_labels, m)   # host work and init kernels under K1
   api._ev(timers, "merge", 0)
   api._ev(timers, "export", 0)
   keys_out, vals_out = packed[MW * 8:(MW + m) * 8], packed[(MW + m) * 8:block]
@@ -347,7 +380,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   dist.all_gather_into_tensor(gathered, packed[:block], group=group)
   api._ev(timers, "xchg_pairs", 1)
   api._ev(timers, "insert", 0)
-  merged = api.LabelTable(dtype, total_labels, _lib.EMPTY, slots_per_entry=MERGED_SLOTS_PER_ENTRY)
+  torch.cuda.current_stream().wait_event(tables_ready)
   _lib.check(L.frb_table_insert_packed(D.ptr(gathered), m, world, 0 if local.direct else local.cap, _lib.OP_MIN, merged.direct,
                                        D.ptr(merged.slots), merged.cap, D.ptr(merged.meta), D.stream()), "frb_table_insert_packed")
   api._ev(timers, "insert", 1)
@@ -359,7 +392,7 @@ def _renumber_sharded_one_shot(src_buf, n_local, dtype, c, start, preserve_zero,
   api._ev(timers, "project", 0)
   import ctypes
   own_count_dev = ctypes.c_void_p(packed.data_ptr() + 8 * _lib.META_COUNT)   # this rank's label count, still on the device
-  lookup = _own_table(merged, keys_out, own_count_dev, m, dtype)
+  lookup = _own_table(merged, keys_out, own_count_dev, m, dtype, own)
   api._ev(timers, "project", 1)
   ranked = torch.cuda.Event()
   ranked.record()
