@@ -197,3 +197,17 @@ def test_host_memcpy_threads():
   dst[:] = 0
   D.host_memcpy(dst.ctypes.data + 7, src.ctypes.data + 7, 1000)    # single piece
   assert np.array_equal(dst[7:1007], src[7:1007]) and dst[:7].sum() == 0 and dst[1007:].sum() == 0
+
+
+def test_type_stub_matches_the_package():
+  """fastremap_b200/__init__.pyi (shipped with py.typed) lists every public name with the parameters the functions really take."""
+  import ast
+  import inspect
+  tree = ast.parse(open(os.path.join(ROOT, "fastremap_b200", "__init__.pyi")).read())
+  stubs = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+  assert os.path.exists(os.path.join(ROOT, "fastremap_b200", "py.typed"))
+  for name in fr.__all__:
+    assert name in stubs, name
+    real = inspect.signature(getattr(fr, name)).parameters
+    a = stubs[name].args
+    assert [x.arg for x in a.args + a.kwonlyargs] == list(real), name
