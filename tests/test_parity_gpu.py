@@ -240,6 +240,25 @@ def test_component_map_vs_oracle(frb, oracle, dtypes):
     assert frb.component_map(c, p) == oracle.component_map(c, p)
 
 
+@pytest.mark.parametrize("dc", [np.uint64, np.int32])
+def test_component_map_listed_slots_vs_oracle(frb, oracle, dc):
+  """K7 with the slot list (tables of >= 2^20 slots: the build lists the slots it fills, the gather walks the list
+  instead of scanning the table): 2^25 voxels, ~300 k components with conflicting parents, against the oracle."""
+  from fastremap_b200 import api
+  from fastremap_b200.synth import synth_device
+  shape, n = (128, 512, 512), 128 * 512 * 512
+  cc_t = synth_device(shape, (40, 90, 90), dc, seed=43, zero_frac=0.05, noise=0.02)
+  par_t = synth_device(shape, (20, 45, 45), np.uint32, seed=44, zero_frac=0.0, noise=0.1)
+  cc_b, par_b = cc_t.reshape(-1).view(torch.uint8), par_t.reshape(-1).view(torch.uint8)
+  keys, pars, nl = api.component_map_device(cc_b, n, dc, par_b, np.uint32, max_labels=600_000, row_bytes=512 * np.dtype(dc).itemsize,
+                                            plane_bytes=512 * 512 * np.dtype(dc).itemsize)
+  assert nl > 250_000
+  w = np.dtype(dc).itemsize
+  got = dict(zip(keys[: nl * w].cpu().numpy().view(dc).tolist(), pars[: nl * 4].cpu().numpy().view(np.uint32).tolist()))
+  exp = oracle.component_map(cc_b.cpu().numpy().view(dc).reshape(shape), par_b.cpu().numpy().view(np.uint32).reshape(shape))
+  assert len(got) == nl and got == exp
+
+
 def test_refit_minmax_pairs_vs_oracle(frb, oracle):
   for dtype in DTYPES:
     a = synth((16, 20, 24), (4, 5, 6), dtype, seed=51, zero_frac=0.2)
