@@ -429,8 +429,8 @@ def renumber_device(src_buf, n, dtype, start=1, preserve_zero=True, write_wide=F
     _ev(timers, "k1", 1)
 
   while True:
-    rb = _RankBuffers(table, dtype)
     build(table)
+    rb = _RankBuffers(table, dtype)   # allocated while K1 runs (host work in front of the first launch is on the critical path)
     _ev(timers, "k2", 0)
     _rank(table, rb, dtype, start, 0, index_count)
     _ev(timers, "k2", 1)

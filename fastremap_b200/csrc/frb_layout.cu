@@ -206,11 +206,15 @@ __global__ void __launch_bounds__(256) k_transpose_packed(const __grid_constant_
 #pragma unroll
       for (int ii = 0; ii < NB; ii++) {
         const int rb = warp + 8 * (i0 + ii);
+        // the R rows of a group lie in one segment of a merged B axis (Bi, b0 and R * rb are multiples of R): one
+        // reciprocal multiply per group, not per row
+        const u64 bg = b0 + (u64)R * rb;
+        const u64 group_w = bg < P.B ? in_row_offset<M>(P, bg) / R : 0;
+        const u64 step_w = P.in_sb / R;
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          const u64 b = b0 + (u64)R * rb + j;
-#pragma unroll
-          const u64 row_w = b < P.B ? in_row_offset<M>(P, b) / R : 0;
+          const u64 b = bg + j;
+          const u64 row_w = group_w + j * step_w;
 #pragma unroll
           for (int h = 0; h < H; h++) w[ii][h][j] = (a_ok[h] && b < P.B) ? __ldcs(src + row_w + 32 * h) : 0u;
         }
