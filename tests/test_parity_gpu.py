@@ -240,6 +240,22 @@ def test_component_map_vs_oracle(frb, oracle, dtypes):
     assert frb.component_map(c, p) == oracle.component_map(c, p)
 
 
+def test_component_map_listed_slots_small(frb, oracle):
+  """the slot-list path of K7 on a small volume (a sizing hint of 600 k labels makes the table big enough for it),
+  ragged length, with and without the out-of-band all-ones label"""
+  from fastremap_b200 import api
+  rng = np.random.default_rng(77)
+  for n, extra in ((70001, False), (16 * 64 * 64, True)):
+    cc = np.repeat(rng.integers(1, 2 ** 62, size=n // 3 + 1, dtype=np.uint64), 3)[:n]
+    if extra:
+      cc[1000:1010] = np.uint64(2 ** 64 - 1)
+    par = rng.integers(0, 1000, size=n, dtype=np.uint32)
+    keys, pars, nl = api.component_map_device(torch.from_numpy(cc.view(np.uint8)).cuda(), n, np.uint64, torch.from_numpy(par.view(np.uint8)).cuda(),
+                                              np.uint32, max_labels=600_000)
+    got = dict(zip(keys[: nl * 8].cpu().numpy().view(np.uint64).tolist(), pars[: nl * 4].cpu().numpy().view(np.uint32).tolist()))
+    assert got == oracle.component_map(cc, par)
+
+
 @pytest.mark.parametrize("dc", [np.uint64, np.int32])
 def test_component_map_listed_slots_vs_oracle(frb, oracle, dc):
   """K7 with the slot list (tables of >= 2^20 slots: the build lists the slots it fills, the gather walks the list
