@@ -62,10 +62,12 @@ __device__ __noinline__ bool table_update_slow_listed(Slot* slots, u64 mask, int
 // IL / DU: how a warp's rows are laid out in the tile and which of the lane's row slots holds the row
 // directly above / below (row_geom; compile-time: the selection must not cost instructions, this loop
 // is issue-bound)
-template <int W, int OP, bool REVERSE, bool HEADS, int IL, int DU, bool VAR_TILE>
+// PZ: walk the volume as a balanced plane walk (pwz, frb_common.cuh) instead of `run` / `pw`
+template <int W, int OP, bool REVERSE, bool HEADS, int IL, int DU, bool VAR_TILE, bool PZ = false>
 __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n, u64 bias, int skip_zero,
                                            Slot* __restrict__ slots, u64 mask, int direct, u64* __restrict__ meta, int run,
-                                           int tile_vecs, PlaneWalk pw, unsigned int* slot_list = nullptr, u64 region_cap = 0) {
+                                           int tile_vecs, PlaneWalk pw, unsigned int* slot_list = nullptr, u64 region_cap = 0,
+                                           PlaneWalkZ pwz = PlaneWalkZ{0, 0, 0}) {
   constexpr int V = 16 / W;
   typedef typename UIntOf<W>::type T;
   // QUEUED (K7, round 2): what survives the filters is not offered by the lane that found it but appended to a per-warp
@@ -301,8 +303,12 @@ __device__ __forceinline__ void build_pass(const uint4* __restrict__ a, size_t n
   // plane walk (frb_common.cuh): a CTA follows one band of rows through a stack of planes, so the labels of the band
   // are still in the warps' sets of "already offered" when they come round again -- with tables too big for L2 an
   // offer is a random HBM access, and those, not the streaming, are what bounds the pass at 10^7 labels
-  const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw) : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
-  stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  if constexpr (PZ) {
+    stream_rows_z<W, REVERSE, true, IL>(a, nvec, TileMapZ(pwz), row_fn, tile_end);
+  } else {
+    const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw) : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+    stream_rows<W, REVERSE, true, IL, VAR_TILE>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+  }
   resolve_pending();
   if (QUEUED && warp < STREAM_WARPS) {  // what is still queued or waiting for its second probe (the producer warp has nothing)
     while (qn || __any_sync(FRB_FULL_MASK, pend)) {

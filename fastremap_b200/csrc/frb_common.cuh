@@ -465,8 +465,11 @@ __device__ __forceinline__ constexpr int ref_slot_ct(int u) {
 struct PlaneWalk {  // see plane_walk_for (host) and TileMapT's second constructor
   unsigned int plane_tiles, planes, band;
 };
+template <typename IDX> struct TileIterT;
 template <typename IDX>
 struct TileMapT {
+  typedef IDX index_type;
+  typedef TileIterT<IDX> iter_type;
   IDX tiles;   // tiles in the whole array
   IDX run;     // consecutive tiles per run
   IDX count;   // tiles owned by this CTA
@@ -552,6 +555,68 @@ struct TileIterT {
 };
 typedef TileMapT<unsigned int> TileMap;
 typedef TileMapT<size_t> TileMap64;
+
+// Balanced plane walk (round 2, second session).  The plane walk above gives every CTA ONE band and splits the planes of
+// a band among the CTAs that share it: with 444 CTAs and 64 bands, 60 bands have 7 CTAs (146 planes each) and 4 bands
+// have 6 (171 planes each) -- the kernel ends 16 % later than its average CTA.  Here the work items are (band, plane)
+// pairs in band-major order -- all planes of band 0, then all planes of band 1 ... -- and CTA c takes the contiguous
+// range [total * c / G, total * (c + 1) / G): every CTA still walks a stack of consecutive planes of one band (and
+// steps over to the next band at most a few times), and loads differ by one item at most.  The array must be exactly
+// planes * plane_tiles full tiles.
+struct PlaneWalkZ {
+  unsigned int plane_tiles, planes, band;  // band == 0: not applicable
+};
+struct TileIterZ;
+struct TileMapZ {
+  typedef unsigned int index_type;
+  typedef TileIterZ iter_type;
+  unsigned int count;  // tiles owned by this CTA
+  unsigned int tv;     // (interface of TileMapT; always the full tile)
+  PlaneWalkZ pw;
+  unsigned int t_first, z_first;  // first item of this CTA: its first tile and its plane
+  unsigned int t_last, z_last;    // last item: ITS first tile and plane (reverse walks start there)
+  __device__ __forceinline__ explicit TileMapZ(const PlaneWalkZ& w) {
+    tv = (unsigned int)STREAM_TILE_VECS;
+    pw = w;
+    const unsigned long long total = (unsigned long long)(w.plane_tiles / w.band) * w.planes;  // items
+    const unsigned long long i0 = total * blockIdx.x / gridDim.x, i1 = total * (blockIdx.x + 1ull) / gridDim.x;
+    count = (unsigned int)(i1 - i0) * w.band;
+    const unsigned long long il = i1 > i0 ? i1 - 1 : i0;
+    z_first = (unsigned int)(i0 % w.planes);
+    t_first = z_first * w.plane_tiles + (unsigned int)(i0 / w.planes) * w.band;
+    z_last = (unsigned int)(il % w.planes);
+    t_last = z_last * w.plane_tiles + (unsigned int)(il / w.planes) * w.band;
+  }
+};
+struct TileIterZ {
+  unsigned int t, o, zc;  // current tile, its offset inside the band, planes left in this band (forward) / plane index (reverse)
+  PlaneWalkZ pw;          // (kernel parameters: read from the constant bank where they are used)
+  template <bool REVERSE>
+  __device__ __forceinline__ void init(const TileMapZ& m) {
+    pw = m.pw;
+    if (REVERSE) { o = pw.band - 1; t = m.t_last + o; zc = m.z_last; }
+    else { o = 0; t = m.t_first; zc = pw.planes - m.z_first; }
+  }
+  __device__ __forceinline__ size_t tile() const { return (size_t)t; }
+  template <bool REVERSE>
+  __device__ __forceinline__ void step() {
+    if (REVERSE) {
+      if (o == 0) {
+        o = pw.band - 1;
+        if (zc == 0) { zc = pw.planes - 1; t += (pw.planes - 1u) * pw.plane_tiles - 1u; }  // first tile of the band in plane 0 -> last tile of the previous band in the last plane
+        else { zc--; t -= pw.plane_tiles - pw.band + 1u; }
+      } else { o--; t--; }
+    } else {
+      o++;
+      t++;
+      if (o == pw.band) {
+        o = 0;
+        if (--zc == 0) { zc = pw.planes; t -= (pw.planes - 1u) * pw.plane_tiles; }  // past the band's last plane -> the next band in plane 0
+        else t += pw.plane_tiles - pw.band;
+      }
+    }
+  }
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
@@ -644,9 +709,11 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 // read gain from the vertical alignment of a lane's rows.
 // VAR_TILE: the tile length is map.tv (a whole number of volume rows) instead of the constant 16 KiB; a
 // template flag because the constant folds into shifts in loops that are issue-bound (K1 + 18 % otherwise).
-template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename IDX, typename RowFn, typename TileEndFn, typename AfterTileFn>
-__device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, const TileMapT<IDX>& map, RowFn row_fn,
+template <int W, bool REVERSE, bool NEED_PREV, int IL, bool VAR_TILE, typename MAP, typename RowFn, typename TileEndFn, typename AfterTileFn>
+__device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, const MAP& map, RowFn row_fn,
                                                  TileEndFn tile_end, AfterTileFn after_tile) {
+  typedef typename MAP::index_type IDX;
+  typedef typename MAP::iter_type ITER;
   constexpr int V = 16 / W;
   constexpr int R = STREAM_ROWS;
   constexpr int S = STREAM_STAGES;
@@ -669,7 +736,7 @@ __device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, co
   if (warp == STREAM_WARPS) {
     // ---------------- producer: one elected lane feeds the ring
     if (lane == 0) {
-      TileIterT<IDX> it;
+      ITER it;
       it.template init<REVERSE>(map);
       int s = 0;
       uint32_t round = 0;
@@ -696,7 +763,7 @@ __device__ __forceinline__ void stream_rows_impl(const uint4* a, size_t nvec, co
   // ---------------- consumers
   constexpr int ROW_STRIDE = IL ? IL * 32 : 32;  // vectors between two rows of one warp
   const int first = stream_vec<IL>(0, warp, lane);
-  TileIterT<IDX> it;
+  ITER it;
   it.template init<REVERSE>(map);
   int s = 0;
   uint32_t round = 0;
@@ -809,6 +876,11 @@ __device__ __forceinline__ void stream_rows(const uint4* a, size_t nvec, const T
                                             TileEndFn tile_end) {
   stream_rows_impl<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
 }
+// the same loop over a balanced plane walk (TileMapZ): full tiles only
+template <int W, bool REVERSE, bool NEED_PREV, int IL, typename RowFn, typename TileEndFn>
+__device__ __forceinline__ void stream_rows_z(const uint4* a, size_t nvec, const TileMapZ& map, RowFn row_fn, TileEndFn tile_end) {
+  stream_rows_impl<W, REVERSE, NEED_PREV, IL, false>(a, nvec, map, row_fn, tile_end, [](size_t) {});
+}
 // barrier among the consumer warps of a streaming CTA (the producer warp never joins it)
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(STREAM_WARPS * 32) : "memory"); }
 
@@ -838,6 +910,20 @@ inline PlaneWalk plane_walk_for(size_t nbytes, size_t plane_bytes, int grid) {
   if (pt % band != 0 || pt / band > (size_t)grid || pt > (1u << 20) || planes > (1u << 20)) return pw;
   const size_t stacks = (size_t)grid / (pt / band);   // CTAs per band (at least)
   if (planes / (stacks + 1) < 4) return pw;
+  pw.plane_tiles = (unsigned int)pt;
+  pw.planes = (unsigned int)planes;
+  pw.band = (unsigned int)band;
+  return pw;
+}
+
+// Balanced plane walk (TileMapZ): possible when the array is a whole number of planes, a plane a whole number of bands of
+// `band` 16 KiB tiles, and every CTA gets a stack of at least 4 planes.
+inline PlaneWalkZ plane_walk_z_for(size_t nbytes, size_t plane_bytes, int grid, size_t band) {
+  PlaneWalkZ pw = {0, 0, 0};
+  const size_t tile_bytes = (size_t)STREAM_TILE_VECS * 16;
+  if (plane_bytes == 0 || band == 0 || grid < 1 || plane_bytes % (tile_bytes * band) != 0 || nbytes % plane_bytes != 0) return pw;
+  const size_t pt = plane_bytes / tile_bytes, planes = nbytes / plane_bytes;
+  if (pt > (1u << 20) || planes > (1u << 20) || pt * planes > 0xFFFFFFF0ull || (pt / band) * planes < 4 * (size_t)grid) return pw;
   pw.plane_tiles = (unsigned int)pt;
   pw.planes = (unsigned int)planes;
   pw.band = (unsigned int)band;

@@ -32,6 +32,14 @@ k_component_build(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot*
                   u64* __restrict__ meta, int run, int tile_vecs, PlaneWalk pw, unsigned int* slot_list, u64 region_cap) {
   build_pass<W, FRB_OP_MAX, true, true, IL, DU, VAR_TILE>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, run, tile_vecs, pw, slot_list, region_cap);
 }
+// the same pass over a balanced plane walk (whole 16 KiB tiles, rows of 4 KiB multiples: IL = 8)
+template <int W, int DU>
+__global__ void __launch_bounds__(STREAM_THREADS, 3)
+k_component_build_z(const uint4* __restrict__ cc, size_t n, u64 flat_offset, Slot* __restrict__ slots, u64 mask, int direct,
+                    u64* __restrict__ meta, PlaneWalkZ pwz, unsigned int* slot_list, u64 region_cap) {
+  build_pass<W, FRB_OP_MAX, true, true, 8, DU, false, true>(cc, n, flat_offset + 1, 0, slots, mask, direct, meta, 1, STREAM_TILE_VECS, PlaneWalk{0, 0, 0},
+                                                             slot_list, region_cap, pwz);
+}
 
 // gather through the list of filled slots the build pass kept (layout: frb_build.cuh; complete -- the host checked
 // meta[AUX1]): no scan of a mostly empty table, no compaction.  A CTA takes one region at a time; its first output
@@ -187,7 +195,18 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
     p, n, flat_offset, s, cap - 1, direct, m, fair_run(stream_grid(k_component_build<WW, II, DD, VV>, tiles), tiles), tv, \
     (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_component_build<WW, II, DD, VV>, tiles)), \
     (unsigned int*)slot_list, slot_list ? slot_list_region_cap((u64)slot_list_capacity, (u64)stream_grid(k_component_build<WW, II, DD, VV>, tiles) * STREAM_WARPS) : 0ull)
+#define FRB_K7Z(WW, DD) { \
+    const int gz = stream_grid(k_component_build_z<WW, DD>, tiles); \
+    const PlaneWalkZ pz = plane_walk_z_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, gz, (size_t)plane_band()); \
+    if (pz.band) { \
+      k_component_build_z<WW, DD><<<gz, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, flat_offset, s, cap - 1, direct, m, pz, (unsigned int*)slot_list, \
+          slot_list ? slot_list_region_cap((u64)slot_list_capacity, (u64)gz * STREAM_WARPS) : 0ull); \
+      return check_launch("k_component_build_z"); \
+    } }
 #define FRB_K7_GEO(WW)                                                        \
+  if (geo.tv == STREAM_TILE_VECS && geo.il == 8) {                            \
+    if (geo.du == 1) FRB_K7Z(WW, 1) else if (geo.du == 2) FRB_K7Z(WW, 2) else if (geo.du == 3) FRB_K7Z(WW, 3) else FRB_K7Z(WW, 4) \
+  }                                                                           \
   if (geo.tv != STREAM_TILE_VECS) { FRB_K7(WW, 8, 4, true); }                 \
   else if (geo.il == 4) { FRB_K7(WW, 4, 1, false); }                          \
   else if (geo.il == 2) { FRB_K7(WW, 2, 1, false); }                          \
@@ -203,6 +222,7 @@ int frb_component_build(const void* cc, size_t n, int cc_dtype, uint64_t flat_of
     default: FRB_K7_GEO(8) break;
   }
 #undef FRB_K7_GEO
+#undef FRB_K7Z
 #undef FRB_K7
   return check_launch("k_component_build");
 }

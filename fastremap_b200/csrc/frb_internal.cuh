@@ -8,6 +8,7 @@ namespace frb {
 int launch_table_export(const Slot* slots, u64 cap, u64* meta, u64* a_out, u64* b_out, size_t capacity, int mode,
                         cudaStream_t st);
 
+int plane_band();       // tiles per band of the balanced plane walk (K7, k_hist): 16; FRB_PLANE_BAND overrides it for A/B runs (0: the first session's one-band-per-CTA walk)
 int relabel_variant();  // tuning knob (frb_set_relabel_variant): -1 sampler decides, 0 k_relabel_batched, 1 k_relabel_runs
 
 // frb_sort.cu -- LSD radix sort, 8 bits per pass, stable.

@@ -30,6 +30,10 @@ int check_launch(const char* what) {
 
 int g_tile_run = 64;
 int tile_run() { return g_tile_run; }
+int plane_band() {
+  static const int band = getenv("FRB_PLANE_BAND") ? atoi(getenv("FRB_PLANE_BAND")) : 16;  // measured 4 .. 64: profiles/r02t_plane_walk_bands.jsonl
+  return band < 0 ? 0 : band;
+}
 int g_relabel_variant = -1;
 int relabel_variant() { return g_relabel_variant; }
 

@@ -288,10 +288,11 @@ __device__ __noinline__ unsigned int hist_process(int qhead, int count, const Si
   return inserted;
 }
 
-template <int W, typename Sink, int IL, int DU, bool VAR_TILE>
+// PZ: the volume is walked as a balanced plane walk (pwz, frb_common.cuh) instead of `run` / `pw`
+template <int W, typename Sink, int IL, int DU, bool VAR_TILE, bool PZ = false>
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restrict__ a, size_t n, const __grid_constant__ Sink sink,
                                                             const __grid_constant__ HistLog log, u64* count_target, int run, int tile_vecs,
-                                                            PlaneWalk pw) {
+                                                            PlaneWalk pw, PlaneWalkZ pwz) {
   constexpr int V = 16 / W;
   const size_t nvec = n / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -352,9 +353,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_hist(const uint4* __restr
     }
   };
 
-  const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw)
-                                             : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
-  stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, [](size_t) {});
+  if constexpr (PZ) {
+    stream_rows_z<W, false, false, IL>(a, nvec, TileMapZ(pwz), row_fn, [](const uint4*, size_t) {});
+  } else {
+    const TileMap map = (!VAR_TILE && pw.band) ? TileMap(pw)
+                                               : TileMap(nvec, (size_t)run, VAR_TILE ? (size_t)tile_vecs : (size_t)STREAM_TILE_VECS);
+    stream_rows<W, false, false, IL, VAR_TILE>(a, nvec, map, row_fn, [](const uint4*, size_t) {}, [](size_t) {});
+  }
   if (consumer) {
     // what the lanes still hold, what is still queued, then the map itself
 #pragma unroll
@@ -939,7 +944,7 @@ int frb_hist_dense(const void* a, size_t n, int dtype, uint64_t min_bits, uint64
   const RowGeom geo = row_geom((size_t)row_bytes);
   const int tv = geo.tv;
 #define FRB_KHD(WW, VV) k_hist<WW, DenseSink, 8, 4, VV><<<stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
-    p, n, sink, nolog, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv, nowalk)
+    p, n, sink, nolog, nullptr, fair_run(stream_grid(k_hist<WW, DenseSink, 8, 4, VV>, tiles), tiles), tv, nowalk, PlaneWalkZ{0, 0, 0})
 #define FRB_KHD_GEO(WW) if (tv != STREAM_TILE_VECS) { FRB_KHD(WW, true); } else { FRB_KHD(WW, false); }
   switch (w) {
     case 1: FRB_KHD_GEO(1) break;
@@ -975,11 +980,24 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
   HistLog log = hist_log_of(ws, ws_bytes, n);
   if (sink.direct) log.cap = 0;  // direct tables are updated fire-and-forget (HashSink::direct_add): no log, no fold
   if (log.cap) cudaMemsetAsync(ws, 0, hist_counts_bytes() + 256, st);  // regions that no warp owns in this launch stay empty
+  bool launched_z = false;
 #define FRB_KH(WW, II, DD, VV) k_hist<WW, HashSink, II, DD, VV><<<stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), STREAM_THREADS, STREAM_SMEM_BYTES, st>>>( \
     p, n, sink, log, ct, fair_run(stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles), tiles), tv, \
-    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles)))
+    (VV) ? PlaneWalk{0, 0, 0} : plane_walk_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, stream_grid(k_hist<WW, HashSink, II, DD, VV>, tiles)), \
+    PlaneWalkZ{0, 0, 0})
+#define FRB_KHZ(WW, DD) { \
+    const int gz = stream_grid(k_hist<WW, HashSink, 8, DD, false, true>, tiles); \
+    const PlaneWalkZ pz = plane_walk_z_for(n * (size_t)WW, (n % (16 / WW)) ? 0 : (size_t)plane_bytes, gz, (size_t)plane_band()); \
+    if (pz.band) { \
+      k_hist<WW, HashSink, 8, DD, false, true><<<gz, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(p, n, sink, log, ct, 1, tv, PlaneWalk{0, 0, 0}, pz); \
+      launched_z = true; \
+    } }
 #define FRB_KH_GEO(WW)                                                        \
-  if (geo.tv != STREAM_TILE_VECS) { FRB_KH(WW, 8, 4, true); }                 \
+  if (geo.tv == STREAM_TILE_VECS && geo.il == 8) {                            \
+    if (geo.du == 1) FRB_KHZ(WW, 1) else if (geo.du == 2) FRB_KHZ(WW, 2) else if (geo.du == 3) FRB_KHZ(WW, 3) else FRB_KHZ(WW, 4) \
+  }                                                                           \
+  if (launched_z) {}                                                          \
+  else if (geo.tv != STREAM_TILE_VECS) { FRB_KH(WW, 8, 4, true); }            \
   else if (geo.il == 4) { FRB_KH(WW, 4, 1, false); }                          \
   else if (geo.il == 2) { FRB_KH(WW, 2, 1, false); }                          \
   else if (geo.il == 1) { FRB_KH(WW, 1, 1, false); }                          \
@@ -994,6 +1012,7 @@ int frb_hist_hash(const void* a, size_t n, int dtype, void* slots, uint64_t cap,
     default: FRB_KH_GEO(8) break;
   }
 #undef FRB_KH_GEO
+#undef FRB_KHZ
 #undef FRB_KH
   int rc = check_launch("k_hist<hash>");
   if (rc) return rc;
