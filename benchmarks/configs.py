@@ -41,7 +41,9 @@ def flat_u8(t):
   return t.reshape(-1).view(torch.uint8)
 
 
-def timed(fn, reps, setup=None, warm=2):
+def timed(fn, reps, setup=None, warm=3):
+  """(median, min, last result) of `reps` timed runs after `warm` untimed ones, CUDA events.  The median, because a single run that
+  meets a cudaMalloc of the caching allocator (first use of a size) is 2x the others and would be a fifth of a 5-run mean."""
   ms, out = [], None
   for i in range(warm + reps):
     if setup:
@@ -54,7 +56,7 @@ def timed(fn, reps, setup=None, warm=2):
     torch.cuda.synchronize()
     if i >= warm:
       ms.append(e0.elapsed_time(e1))
-  return float(np.mean(ms)), float(np.min(ms)), out
+  return float(np.median(ms)), float(np.min(ms)), out
 
 
 def roofline(n, bytes_per_voxel, ms, peak, kernel):
@@ -74,7 +76,7 @@ def cpu_record(kind, what, voxels, secs):
 
 
 def record(cid, workload, n, ms, ms_min, roof, cpu, parity, how, **extra):
-  line = {"id": cid, "config": BASELINE_CONFIGS[cid[0]], "workload": workload, "voxels": n, "ms": ms, "ms_min": ms_min,
+  line = {"id": cid, "config": BASELINE_CONFIGS[cid[0]], "workload": workload, "voxels": n, "ms": ms, "ms_stat": "median of the timed runs (3 warm-ups)", "ms_min": ms_min,
           "Gvox/s": n / (ms / 1e3) / 1e9, "roofline": roof, "cpu_baseline": cpu, "parity": bool(parity), "parity_how": how}
   line.update(extra)
   return line
