@@ -68,12 +68,15 @@ def main():
   ap.add_argument("--reps", type=int, default=5)
   ap.add_argument("--ops", default="unique_dense,unique_sparse,remap,mask_except,component_map,minmax")
   ap.add_argument("--no-plane", action="store_true", help="withhold the plane_bytes hint: linear walk everywhere (A/B runs)")
+  ap.add_argument("--tile-run", type=int, default=0, help="frb_set_tile_run: consecutive tiles per CTA run of the linear walk (A/B runs)")
   args = ap.parse_args()
   S, ops = args.side, set(args.ops.split(","))
   PL = 0 if args.no_plane else 1
   n = S ** 3
   sc = S / 1024.0
   D.dev()
+  if args.tile_run:
+    _lib.load().frb_set_tile_run(args.tile_run)
 
   if "unique_dense" in ops or "minmax" in ops:
     vol = synth_device((S, S, S), (max(int(46 * sc), 1),) * 3, np.uint64, seed=0, zero_frac=0.1)
