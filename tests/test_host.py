@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -211,3 +212,30 @@ def test_type_stub_matches_the_package():
     real = inspect.signature(getattr(fr, name)).parameters
     a = stubs[name].args
     assert [x.arg for x in a.args + a.kwonlyargs] == list(real), name
+
+
+def test_import_fastremap_shim():
+  """fastremap_b200/compat on sys.path makes `import fastremap` resolve to this package (same function objects)."""
+  import importlib
+  compat = os.path.join(ROOT, "fastremap_b200", "compat")
+  saved = sys.modules.pop("fastremap", None)
+  sys.path.insert(0, compat)
+  try:
+    shim = importlib.import_module("fastremap")
+    assert os.path.dirname(os.path.dirname(shim.__file__)) == compat
+    for name in fr.__all__:
+      assert getattr(shim, name) is getattr(fr, name), name
+  finally:
+    sys.path.remove(compat)
+    sys.modules.pop("fastremap", None)
+    if saved is not None:
+      sys.modules["fastremap"] = saved
+
+
+def test_own_table_sparsity_rule():
+  """sharded renumber: the rank's own lookup table gets up to 64 slots per label while it stays at 2^23 slots, never fewer than 8"""
+  from fastremap_b200 import sharded, api
+  assert sharded._own_slots_per_entry(1) == 64
+  assert sharded._own_slots_per_entry(88_000) == 64
+  assert sharded._own_slots_per_entry(400_000) == (1 << 23) // 400_000
+  assert sharded._own_slots_per_entry(5_000_000) == api.LOOKUP_SLOTS_PER_ENTRY
