@@ -891,9 +891,20 @@ int tile_run();  // tuning knob (frb_runtime.cu): consecutive tiles per CTA run
 // chunks) get shorter runs, so that every CTA of the grid has work.  Decided on the host: the same
 // clamp inside the kernels cost k_hist 8 % (register allocation of its hot loop).
 inline int fair_run(int grid, size_t tiles) {
-  const size_t fair = tiles / (2 * (size_t)(grid < 1 ? 1 : grid));
-  const size_t run = (size_t)tile_run();
-  return (int)(run > fair ? (fair < 1 ? 1 : fair) : run);
+  const size_t g = (size_t)(grid < 1 ? 1 : grid);
+  const size_t fair = tiles / (2 * g);
+  const size_t rmax = (size_t)tile_run();
+  if (rmax > fair) return (int)(fair < 1 ? 1 : fair);
+  // Mid-sized arrays: the number of runs should be (close to) a multiple of the grid.  With runs of exactly 64 tiles a
+  // 512^3 uint64 volume is 1024 runs for 444 CTAs -- 136 CTAs get three runs, the others two, and the kernel ends 30 %
+  // later than its average CTA: K1 took 0.243 ms there (4.4 TB/s) and takes 0.183 ms with k = 3 runs of 50 tiles per CTA.
+  // Only while a CTA has few runs (k <= 8): at 1024^3 (k = 19) the imbalance is 3 %, and runs of 63 instead of 64 tiles
+  // -- 1008 KiB pieces instead of 1 MiB ones -- cost the big-table K3 8 % (mask_except 4.14 -> 4.46 ms), so long arrays
+  // keep the power of two.
+  const size_t k = (tiles + g * rmax - 1) / (g * rmax);
+  if (k > 8) return (int)rmax;
+  const size_t run = (tiles + k * g - 1) / (k * g);
+  return (int)(run < 1 ? 1 : run);
 }
 
 // Plane walk of a read-only streaming kernel (TileMapT's second constructor): possible when the array is a whole
