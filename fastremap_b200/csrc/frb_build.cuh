@@ -17,6 +17,8 @@
 //   3. the 16-byte home slot itself: read first (L2-coherent), issued one tile ahead of its use so
 //      the round trip overlaps the streaming; "label present with a better value" ends there.
 // Only what survives all three reaches atomicCAS / atomicMin / atomicMax.
+// K1 keeps one such deferred offer per lane (labels are few where it is timed); K7 queues the survivors per warp and
+// settles them 32 at a time straight from the pre-read slots, and lists the slots it fills (QUEUED, below).
 #pragma once
 #include "frb_common.cuh"
 

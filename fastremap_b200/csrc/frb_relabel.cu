@@ -9,6 +9,9 @@
 // reference's serial "same as previous voxel" shortcut is not needed; the first probe of each
 // element is issued unconditionally so all V loads are in flight before the first compare.
 // The table is read-only here (ld.global.nc, L1-allocating); the volume streams past L1.
+// Tables beyond L1 and 64-bit labels: k_relabel_batched (two rows of home-pair loads in flight per warp) or
+// k_relabel_runs (one lookup per run of equal labels, a warp-tile's runs in flight together), chosen per call by a
+// run-density sampler.
 #include "frb_internal.cuh"
 #include "frb_build.cuh"
 
